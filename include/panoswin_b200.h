@@ -1,0 +1,138 @@
+/*
+ * panoswin_b200.h — C ABI of libpanoswin_b200.so: the B200 (sm_100a) kernels behind the PanoSwin
+ * pano-style shifted-window attention path.
+ *
+ * The reference (1069066484/PanoSwinTransformerObjectDetection) has NO FFI: the path is pure Python
+ * (mmdet/models/backbones/simple_panoswin_transformer.py).  Each entry point below therefore cites the
+ * reference Python code it replaces; INTEGRATION.md shows the ctypes stub a reference maintainer adds.
+ *
+ * Conventions (every function):
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers owned by the caller;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work: no allocation, no sync;
+ *   - returns 0 on success, a NEGATIVE psw_status on argument errors, a POSITIVE cudaError_t when the
+ *     CUDA runtime refused the launch; psw_last_error_string() describes the last failure of the
+ *     calling thread;
+ *   - stateless and thread-safe; there is NO CPU fallback: without a B200 the launch fails loudly.
+ *   - dtype arguments: PSW_F32 selects the fp32 parity path (CUDA-core FMA, 1e-5 vs the reference),
+ *     PSW_BF16 the throughput path (bf16 storage, tcgen05 tensor cores, fp32 accumulate/softmax).
+ */
+#ifndef PANOSWIN_B200_H_
+#define PANOSWIN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSW_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PSW_API __attribute__((visibility("default")))
+#else
+#define PSW_API
+#endif
+
+enum psw_dtype { PSW_F32 = 0, PSW_BF16 = 1 };
+
+enum psw_status {
+  PSW_OK = 0,
+  PSW_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, misaligned pointer            */
+  PSW_ERR_UNSUPPORTED = -2,  /* shape outside what the sm_100a kernel was built for            */
+  PSW_ERR_NO_DEVICE = -3,    /* no CUDA device / not compute capability 10.x                   */
+  PSW_ERR_DRIVER = -4        /* driver entry point (tensor-map encode) unavailable             */
+};
+
+/* epilogue flags of psw_linear_fwd */
+#define PSW_EPI_GELU 1       /* exact erf GELU after the bias add (nn.GELU, reference :51,:57)  */
+
+PSW_API int psw_abi_version(void);
+PSW_API const char* psw_last_error_string(void);
+/* Returns 0 when device `dev` is an sm_100 (B200) part the kernels can run on. */
+PSW_API int psw_check_device(int dev);
+
+/*
+ * LayerNorm over the last dimension: y[r,:] = (x[r,:] - mean) * rstd * gamma + beta.
+ * Replaces norm1 / norm2 of PanoSwinTransformerBlock.forward
+ * (simple_panoswin_transformer.py:504, :534) and patch_embed.norm (:768-772).
+ * x [rows, C] (in_dtype), y [rows, C] (out_dtype), gamma/beta [C] fp32.  C % 4 == 0, C <= 4096.
+ * `pos` (nullable, fp32 [pos_rows, C]) is added after the affine, row r using pos[r % pos_rows]: the
+ * pano absolute position embedding of forward() (:960-962).
+ */
+PSW_API int psw_layernorm_fwd(const void* x, void* y, const float* gamma, const float* beta, const float* pos,
+                      int64_t rows, int C, int64_t pos_rows, float eps, int in_dtype, int out_dtype, void* stream);
+
+/*
+ * y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]) (+ residual[M,N]).
+ * Replaces nn.Linear of attn.qkv (:287), attn.proj (:309) with the block's first residual add (:533),
+ * Mlp fc1+GELU / fc2 (:55-61) with the second residual add (:534), and PatchMerging.reduction (:575).
+ * PSW_F32 : x, w, residual, y fp32 (CUDA-core FMA).
+ * PSW_BF16: x, w bf16; bias fp32 (nullable); accumulate fp32 on tcgen05/TMEM;
+ *           y is `out_dtype`; residual (nullable) has dtype `out_dtype`.  K % 32 == 0, N % 16 == 0.
+ * `flags`: PSW_EPI_GELU.
+ */
+PSW_API int psw_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                   int64_t M, int N, int K, int flags, int dtype, int out_dtype, void* stream);
+
+/*
+ * Fused (shifted-)window multi-head self-attention on an equirectangular token map.
+ * Replaces, in ONE pass over HBM, WindowTransition.forward (:376-409, pano shift with longitude
+ * wrap-around), pad_x (:486-491), window_partition (:64-75), the core of
+ * BasicWindowAttention.forward (:290-308: q*scale, q.k^T, great-circle bias of _sphere_bias :241-260
+ * with haversine22 of lzx/models/great_circle.py:71-86, optional planar shift mask, softmax, P.v),
+ * window_reverse (:78-92), the crop (:516) and the reverse transition (:394-397).
+ *
+ *   qkv      [B, H, W, 3C]  output of the qkv linear on UN-shifted tokens, channel order (3, heads, hd)
+ *   out      [B, H, W, C]   attention output (before proj), un-shifted token order
+ *   alpha, beta [(2*window-1)^2, heads] fp32 tables (sphere_position_{alpha,beta}_table_Te)
+ *   qkv_bias [3C] fp32 or NULL — q/k/v of a zero (padding) token: padded cells take part as keys/values
+ *   uv       [H, W, 2] fp32 token coordinates (make_uv_hw2 :153-189); ignored (may be NULL) in planar mode
+ *   mask     [nW, window^2, window^2] fp32 additive mask or NULL (planar mode, shifted blocks only)
+ *   pano_mode 1: attention runs on the (2H, ceil(W/2)) north-south layout; 0: planar Swin roll(-s,-s)
+ * PSW_BF16 requires window^2 <= 64 and C / heads == 32 (every shipped PanoSwin config).
+ */
+PSW_API int psw_window_attn_fwd(const void* qkv, void* out, const float* alpha, const float* beta,
+                        const float* qkv_bias, const float* uv, const float* mask,
+                        int B, int H, int W, int C, int heads, int window, int shift, int pano_mode,
+                        float scale, int dtype, void* stream);
+
+/*
+ * PatchMerging front half: 2x2 gather in the order (0,0),(1,0),(0,1),(1,1) with zero padding of odd
+ * H/W, then LayerNorm(4C) (:563-574).  x [B, H, W, C] (in_dtype) -> y [B, ceil(H/2)*ceil(W/2), 4C]
+ * (out_dtype).  The reduction Linear(4C -> 2C) (:575) is psw_linear_fwd.
+ */
+PSW_API int psw_patch_merge_ln_fwd(const void* x, void* y, const float* gamma, const float* beta,
+                           int B, int H, int W, int C, float eps, int in_dtype, int out_dtype, void* stream);
+
+/*
+ * Per-stage output head: LayerNorm then NHWC -> NCHW, fp32 contiguous output
+ * (SimplePanoSwinTransformer.forward :974-978).  x [B, HW, C] (in_dtype) -> y [B, C, HW] fp32.
+ */
+PSW_API int psw_layernorm_nchw_fwd(const void* x, float* y, const float* gamma, const float* beta,
+                           int B, int64_t HW, int C, float eps, int in_dtype, void* stream);
+
+/* dtype conversion helper for activations entering / leaving the bf16 path: n elements. */
+PSW_API int psw_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
+
+/*
+ * Diagnostics (used by tests / profiling only; same arguments as psw_window_attn_fwd, bf16 storage):
+ *   _simt_bf16  : the CUDA-core kernel on bf16 tensors (cross-check of the tensor-core kernel);
+ *   _tc_variant : the tcgen05 kernel with an explicit variant — 0: P operand read from TMEM,
+ *                 1: P operand staged through shared memory.
+ */
+/* Host-only: dump the kernels' window geometry (see psw_api.cu); map may be NULL to query hp / wp. */
+PSW_API int psw_debug_source_map(int H, int W, int window, int shift, int pano_mode, int* map, int capacity,
+                                 int* hp, int* wp);
+PSW_API int psw_window_attn_fwd_simt_bf16(const void* qkv, void* out, const float* alpha, const float* beta,
+                                          const float* qkv_bias, const float* uv, const float* mask,
+                                          int B, int H, int W, int C, int heads, int window, int shift,
+                                          int pano_mode, float scale, void* stream);
+PSW_API int psw_window_attn_fwd_tc_variant(const void* qkv, void* out, const float* alpha, const float* beta,
+                                           const float* qkv_bias, const float* uv, const float* mask,
+                                           int B, int H, int W, int C, int heads, int window, int shift,
+                                           int pano_mode, float scale, int variant, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANOSWIN_B200_H_ */

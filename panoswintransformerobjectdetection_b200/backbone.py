@@ -1,0 +1,490 @@
+"""Drop-in `SimplePanoSwinTransformer` whose forward runs on libpanoswin_b200 (sm_100a CUDA).
+
+Mirrors the reference module's public surface (mmdet/models/backbones/simple_panoswin_transformer.py):
+same constructor keywords (:781-801), `forward(x, pano_ratio_v=None) -> tuple of fp32 NCHW maps` (:940-979),
+`init_weights(pretrained)` (:885-907), `train(mode)` returning None (:981-983), `set_pano_mode` /
+`switch_pano_mode` (:880-883, :207-208), `num_features`, `out_indices`, the `BACKBONES` registry entry
+(:779-780) and — so that checkpoints and optimizer `paramwise_cfg` keys keep working — exactly the same
+parameter / buffer names.  The sub-modules below are parameter containers; the compute is
+the kernel sequence in `_forward_tokens`, which never materialises the shifted / padded / partitioned
+copies, the uv channels or the [nW,49,49,heads] bias tensor of the reference.
+
+Compute modes (`set_compute_dtype`): "bf16" (default; bf16 activations + tcgen05 GEMM/attention, fp32
+residual stream, fp32 softmax / LayerNorm statistics) and "fp32" (CUDA-core kernels, <=1e-5 of the reference).
+Forward only: training kernels (backward) are the next scope row.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .registry import BACKBONES
+
+__all__ = ["SimplePanoSwinTransformer", "make_uv_hw2", "make_relative_position_index", "planar_attention_mask"]
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side constants (tiny; computed once per resolution on the CPU exactly like the reference)
+# ------------------------------------------------------------------------------------------------
+def make_relative_position_index(window_size) -> torch.Tensor:
+    """idx[i,j] = (dr + wh-1)*(2*ww-1) + (dc + ww-1) for tokens i, j of a window (reference :95-129)."""
+    wh, ww = (window_size, window_size) if isinstance(window_size, int) else window_size
+    t = torch.arange(wh * ww)
+    r, c = torch.div(t, ww, rounding_mode="floor"), t % ww
+    return (r[:, None] - r[None, :] + wh - 1) * (2 * ww - 1) + (c[:, None] - c[None, :] + ww - 1)
+
+
+def make_uv_hw2(H: int, W: int, device="cpu") -> torch.Tensor:
+    """Token-centre longitude/latitude grid [H, W, 2], u in [-pi, pi), v in [-pi/2, pi/2); the angular
+    step is pi/H on both axes and the fp32 rounding order is the reference's (:173-188)."""
+    if W < H:
+        raise ValueError(f"make_uv_hw2 needs W >= H, got H={H} W={W}")
+    gap = math.pi / H
+    u = (torch.arange(W) * gap - math.pi) + 0.5 * gap
+    v = (torch.arange(H) * gap - math.pi * 0.5) + 0.5 * gap
+    uv = torch.stack([u[None, :].expand(H, W), v[:, None].expand(H, W)], dim=-1).contiguous()
+    return uv.to(device)
+
+
+def planar_attention_mask(H: int, W: int, window_size: int, shift_size: int) -> torch.Tensor:
+    """0 / -100 SW-MSA mask [nW, ws*ws, ws*ws] of planar mode (reference :664-688)."""
+    ws = window_size
+    Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
+    band_h = torch.zeros(Hp)
+    band_h[Hp - ws:Hp - shift_size] = 1
+    band_h[Hp - shift_size:] = 2
+    band_w = torch.zeros(Wp)
+    band_w[Wp - ws:Wp - shift_size] = 1
+    band_w[Wp - shift_size:] = 2
+    region = band_h[:, None] * 3 + band_w[None, :]
+    rw = region.view(Hp // ws, ws, Wp // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+    diff = rw[:, None, :] - rw[:, :, None]
+    return torch.where(diff != 0, torch.full_like(diff, -100.0), torch.zeros_like(diff)).contiguous()
+
+
+def _trunc_normal_(t: torch.Tensor, std: float = 0.02):
+    return nn.init.trunc_normal_(t, std=std)
+
+
+class DropPath(nn.Module):
+    """Stochastic depth (timm semantics).  Identity in eval mode / rate 0; kept for API parity."""
+
+    def __init__(self, drop_prob: float = 0.0):
+        super().__init__()
+        self.drop_prob = float(drop_prob)
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+        return x * mask / keep
+
+
+class DoubleModeModule(object):
+    """pano / planar switch shared by every level of the backbone (reference :192-208)."""
+
+    def __init__(self, pano_mode=True):
+        super().__init__()
+        self.pano_mode = pano_mode
+        self.set_pano_mode(pano_mode=pano_mode)
+
+    def set_pano_mode(self, pano_mode: bool):
+        self.pano_mode = pano_mode
+
+    def switch_pano_mode(self):
+        self.set_pano_mode(not self.pano_mode)
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers with the reference's names
+# ------------------------------------------------------------------------------------------------
+class Mlp(nn.Module):
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        if act_layer is not nn.GELU:
+            raise NotImplementedError("libpanoswin_b200 fuses the exact-erf GELU of the reference Mlp only")
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+
+class WindowAttention(nn.Module, DoubleModeModule):
+    """Holds qkv / proj / the two great-circle tables / the index buffer (reference :211-239, :315-323)."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0.0, proj_drop=0.0,
+                 pano_mode=True):
+        nn.Module.__init__(self)
+        DoubleModeModule.__init__(self, pano_mode=pano_mode)
+        self.dim = dim
+        self.window_size = (window_size, window_size) if isinstance(window_size, int) else tuple(window_size)
+        if self.window_size[0] != self.window_size[1]:
+            raise NotImplementedError("square windows only (as every reference config)")
+        assert dim % num_heads == 0, "channels should be divisible by heads, but we get channel {} and heads{}".format(dim, num_heads)
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        self.register_buffer("relative_position_index_OO", make_relative_position_index(self.window_size))
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        tsize = (2 * self.window_size[0] - 1) * (2 * self.window_size[1] - 1)
+        # the reference aliases alpha and beta at init (:145-147); they are independent tensors here
+        # (checkpoints store both) but start from the same draw so a fresh model matches its statistics
+        first = _trunc_normal_(torch.zeros(tsize, num_heads), std=0.02)
+        self.sphere_position_alpha_table_Te = nn.Parameter(first.clone())
+        self.sphere_position_beta_table_Te = nn.Parameter(first.clone())
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+
+
+class WindowTransition(nn.Module, DoubleModeModule):
+    """Shift description only: the pano shift / un-shift is address arithmetic inside the attention
+    kernel (psw::source_token), so this module carries `shift_size` and the mode flag, no compute."""
+
+    def __init__(self, shift_size=0, pano_mode=False):
+        nn.Module.__init__(self)
+        DoubleModeModule.__init__(self, pano_mode=pano_mode)
+        self.shift_size = shift_size
+
+
+class PanoSwinTransformerBlock(nn.Module, DoubleModeModule):
+    def __init__(self, dim, num_heads, window_size=7, shift_size=0, mlp_ratio=4.0, qkv_bias=True, qk_scale=None,
+                 drop=0.0, attn_drop=0.0, drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm, pano_mode=True):
+        nn.Module.__init__(self)
+        self.dim = dim
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.shift_size = shift_size
+        self.mlp_ratio = mlp_ratio
+        assert 0 <= self.shift_size < self.window_size, "shift_size must in 0-window_size"
+        if norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("libpanoswin_b200 implements nn.LayerNorm only")
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim=dim, window_size=window_size, num_heads=num_heads, qkv_bias=qkv_bias,
+                                    qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop, pano_mode=pano_mode)
+        self.window_transition = WindowTransition(shift_size=shift_size, pano_mode=pano_mode)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.H = None
+        self.W = None
+        DoubleModeModule.__init__(self, pano_mode=pano_mode)
+
+    def set_pano_mode(self, pano_mode):
+        self.attn.set_pano_mode(pano_mode=pano_mode)
+        self.window_transition.set_pano_mode(pano_mode=pano_mode)
+        self.pano_mode = pano_mode
+
+
+class PatchMerging(nn.Module):
+    def __init__(self, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = norm_layer(4 * dim)
+
+
+class BasicLayer(nn.Module, DoubleModeModule):
+    def __init__(self, dim, depth, num_heads, window_size=7, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop=0.0,
+                 attn_drop=0.0, drop_path=0.0, norm_layer=nn.LayerNorm, downsample=None, use_checkpoint=False,
+                 pano_mode=True):
+        nn.Module.__init__(self)
+        self.window_size = window_size
+        self.shift_size = window_size // 2
+        self.depth = depth
+        self.use_checkpoint = use_checkpoint
+        if depth % 2:
+            # reference :636-647 appends PitchAttentionModule, which cannot execute in pano mode as shipped
+            # (simple_panoswin_transformer.py:1038 vs lzx/pano_rotate.py:169); out of scope
+            raise NotImplementedError(
+                f"odd stage depth {depth} needs PitchAttentionModule, which the reference itself cannot run in pano "
+                "mode; use even depths (every shipped config does)")
+        self.blocks = nn.ModuleList([
+            PanoSwinTransformerBlock(
+                dim=dim, num_heads=num_heads, window_size=window_size,
+                shift_size=0 if (i % 2 == 0) else window_size // 2, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
+                drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path, norm_layer=norm_layer,
+                pano_mode=pano_mode)
+            for i in range(depth)])
+        self.downsample = downsample(dim=dim, norm_layer=norm_layer) if downsample is not None else None
+        DoubleModeModule.__init__(self, pano_mode=pano_mode)
+
+    def set_pano_mode(self, pano_mode=True):
+        self.pano_mode = pano_mode
+        for block in self.blocks:
+            block.set_pano_mode(pano_mode)
+
+
+class PatchEmbed(nn.Module):
+    """Stem parameters (reference :727-773): conv3x3-BN-ReLU, conv3x3-BN-ReLU, conv(patch)/stride(patch), LN."""
+
+    def __init__(self, patch_size=4, in_chans=3, embed_dim=96, norm_layer=None):
+        super().__init__()
+        patch_size = (patch_size, patch_size) if isinstance(patch_size, int) else tuple(patch_size)
+        self.patch_size = patch_size
+        self.in_chans = in_chans
+        self.embed_dim = embed_dim
+        d3 = embed_dim // 3
+        self.proj = nn.Sequential(
+            nn.Conv2d(in_chans, d3, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(d3), nn.ReLU(inplace=True),
+            nn.Conv2d(d3, d3 * 2, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(d3 * 2), nn.ReLU(inplace=True),
+            nn.Conv2d(d3 * 2, embed_dim, kernel_size=patch_size, stride=patch_size))
+        self.norm = norm_layer(embed_dim) if norm_layer is not None else None
+
+
+# ------------------------------------------------------------------------------------------------
+# the backbone
+# ------------------------------------------------------------------------------------------------
+@BACKBONES.register_module()
+class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
+    def __init__(self, patch_size=4, in_chans=3, embed_dim=96, depths=[2, 2, 7, 2], num_heads=[3, 6, 12, 24],
+                 window_size=7, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop_rate=0.0, attn_drop_rate=0.0,
+                 drop_path_rate=0.2, norm_layer=nn.LayerNorm, ape=False, patch_norm=True, out_indices=(0, 1, 2, 3),
+                 frozen_stages=-1, use_checkpoint=False, pano_mode=True):
+        nn.Module.__init__(self)
+        self.num_layers = len(depths)
+        self.embed_dim = embed_dim
+        self.ape = ape
+        self.patch_norm = patch_norm
+        self.out_indices = out_indices
+        self.frozen_stages = frozen_stages
+        self.window_size = window_size
+        self.patch_embed = PatchEmbed(patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim,
+                                      norm_layer=norm_layer if self.patch_norm else None)
+        if self.ape:
+            self.abs_encoder = nn.Linear(5, embed_dim)
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        dpr = [x.item() for x in torch.linspace(0, drop_path_rate, sum(depths))]
+        self.layers = nn.ModuleList()
+        for i_layer in range(self.num_layers):
+            self.layers.append(BasicLayer(
+                dim=int(embed_dim * 2 ** i_layer), depth=depths[i_layer], num_heads=num_heads[i_layer],
+                window_size=window_size, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop_rate,
+                attn_drop=attn_drop_rate, drop_path=dpr[sum(depths[:i_layer]):sum(depths[:i_layer + 1])],
+                norm_layer=norm_layer, downsample=PatchMerging if (i_layer < self.num_layers - 1) else None,
+                use_checkpoint=use_checkpoint, pano_mode=pano_mode))
+        self.num_features = [int(embed_dim * 2 ** i) for i in range(self.num_layers)]
+        for i_layer in out_indices:
+            self.add_module(f"norm{i_layer}", norm_layer(self.num_features[i_layer]))
+        self._compute_dtype = torch.bfloat16
+        self._const_cache: Dict[tuple, torch.Tensor] = {}
+        self._weight_cache: Dict[tuple, tuple] = {}
+        DoubleModeModule.__init__(self, pano_mode=pano_mode)
+
+    # ---- reference API ------------------------------------------------------------------------
+    def set_pano_mode(self, pano_mode=True):
+        self.pano_mode = pano_mode
+        for layer in self.layers:
+            layer.set_pano_mode(pano_mode)
+
+    def init_weights(self, pretrained=None):
+        def _init_weights(m):
+            if isinstance(m, nn.Linear):
+                _trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+        if isinstance(pretrained, str):
+            self.apply(_init_weights)
+            _load_checkpoint(self, pretrained)
+        elif pretrained is None:
+            self.apply(_init_weights)
+        else:
+            raise TypeError("pretrained must be a str or None")
+
+    def train(self, mode=True):
+        """Like the reference (:981-983) this returns None — do not chain `.eval()`."""
+        super(SimplePanoSwinTransformer, self).train(mode)
+
+    # ---- B200 additions -----------------------------------------------------------------------
+    def set_compute_dtype(self, dtype):
+        """'bf16' (throughput path, default) or 'fp32' (parity path)."""
+        table = {"bf16": torch.bfloat16, "fp32": torch.float32, torch.bfloat16: torch.bfloat16,
+                 torch.float32: torch.float32}
+        if dtype not in table:
+            raise ValueError("compute dtype must be 'bf16' or 'fp32'")
+        self._compute_dtype = table[dtype]
+        return self
+
+    @property
+    def compute_dtype(self):
+        return self._compute_dtype
+
+    # ---- cached constants / converted weights -------------------------------------------------
+    def _const(self, key, builder, device):
+        k = key + (str(device),)
+        t = self._const_cache.get(k)
+        if t is None:
+            t = builder().to(device).contiguous()
+            self._const_cache[k] = t
+        return t
+
+    def _w(self, p: torch.Tensor, dtype) -> torch.Tensor:
+        """Parameter in the compute dtype (bf16 copies are cached until the parameter changes)."""
+        if p.dtype == dtype:
+            return p.detach().contiguous()
+        k = (id(p), dtype)
+        hit = self._weight_cache.get(k)
+        if hit is not None and hit[0] == p._version and hit[1] == p.data_ptr():
+            return hit[2]
+        conv = ops.cast(p.detach().contiguous(), dtype)
+        self._weight_cache[k] = (p._version, p.data_ptr(), conv)
+        return conv
+
+    @staticmethod
+    def _f(p: Optional[torch.Tensor]):
+        return None if p is None else p.detach().contiguous()
+
+    # ---- stem ---------------------------------------------------------------------------------
+    def _stem(self, x: torch.Tensor) -> torch.Tensor:
+        """conv-BN-ReLU x2 + patch conv -> NHWC tokens [B, Hs, Ws, E].  Library convolutions (cuDNN through
+        torch) for now — SURVEY.md §8 f-2 lists the stem as the next row after the attention path."""
+        pe = self.patch_embed
+        ph, pw = pe.patch_size
+        _, _, H, W = x.shape
+        if W % pw != 0:
+            x = F.pad(x, (0, pw - W % pw))
+        if H % ph != 0:
+            x = F.pad(x, (0, 0, 0, ph - H % ph))
+        conv1, bn1, _, conv2, bn2, _, conv3 = pe.proj
+        if self._compute_dtype == torch.float32:
+            prev = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False
+            try:
+                y = F.relu(F.batch_norm(F.conv2d(x, conv1.weight, conv1.bias, padding=1), bn1.running_mean,
+                                        bn1.running_var, bn1.weight, bn1.bias, False, 0.0, bn1.eps))
+                y = F.relu(F.batch_norm(F.conv2d(y, conv2.weight, conv2.bias, padding=1), bn2.running_mean,
+                                        bn2.running_var, bn2.weight, bn2.bias, False, 0.0, bn2.eps))
+                y = F.conv2d(y, conv3.weight, conv3.bias, stride=pe.patch_size)
+            finally:
+                torch.backends.cudnn.allow_tf32 = prev
+            return y.permute(0, 2, 3, 1).contiguous()
+        # bf16: fold the eval-mode BatchNorm into the convolution, channels-last
+        def folded(conv, bn):
+            s = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            w = (conv.weight * s[:, None, None, None]).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            b = ((conv.bias - bn.running_mean) * s + bn.bias).to(torch.bfloat16)
+            return w, b
+        key = ("stem", tuple(p._version for p in pe.proj.parameters()), bn1.running_mean._version, bn2.running_mean._version)
+        if self._weight_cache.get("stem_key") != key:
+            self._weight_cache["stem"] = (folded(conv1, bn1), folded(conv2, bn2),
+                                          (conv3.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
+                                           conv3.bias.to(torch.bfloat16)))
+            self._weight_cache["stem_key"] = key
+        (w1, b1), (w2, b2), (w3, b3) = self._weight_cache["stem"]
+        y = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        y = F.relu_(F.conv2d(y, w1, b1, padding=1))
+        y = F.relu_(F.conv2d(y, w2, b2, padding=1))
+        y = F.conv2d(y, w3, b3, stride=pe.patch_size)
+        return y.permute(0, 2, 3, 1).contiguous()          # no copy when the conv output is channels-last
+
+    def _abs_position(self, Hs, Ws, device) -> torch.Tensor:
+        """fp32 [Hs*Ws, E] = abs_encoder(x, y, z, u, v) (reference :925-934); cached per resolution."""
+        ver = (self.abs_encoder.weight._version, self.abs_encoder.bias._version, self.abs_encoder.weight.data_ptr())
+        def build():
+            uv = make_uv_hw2(Hs, Ws)
+            u, v = uv[..., 0], uv[..., 1]
+            return torch.stack([torch.sin(u) * torch.sin(v), torch.cos(u) * torch.sin(v), torch.cos(v), u, v], -1).reshape(-1, 5)
+        xyzuv = self._const(("xyzuv", Hs, Ws), build, device)
+        k = ("pos", Hs, Ws, str(device))
+        hit = self._weight_cache.get(k)
+        if hit is None or hit[0] != ver:
+            pos = ops.linear(xyzuv, self._f(self.abs_encoder.weight), self._f(self.abs_encoder.bias))
+            self._weight_cache[k] = hit = (ver, pos)
+        return hit[1]
+
+    # ---- forward ------------------------------------------------------------------------------
+    def forward(self, x_bchw, pano_ratio_v=None):
+        if pano_ratio_v is not None:
+            warnings.warn("Parameter pano_ratio_v for is deprecated! Please set it to None!")
+        if self.pano_mode and x_bchw.shape[3] != x_bchw.shape[2] * 2:
+            warnings.warn("PanoSwin is configured in Pano mode, expecting channel3 == 2 * channel2, but get {} and {}, "
+                          "probably cause an error".format(x_bchw.shape[3], x_bchw.shape[2]))
+        if not x_bchw.is_cuda:
+            raise ops.PanoSwinB200Error("SimplePanoSwinTransformer (B200) needs a CUDA input; there is no CPU fallback")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("libpanoswin_b200 is forward-only so far (backward kernels: SURVEY.md §8 f-3); "
+                                      "call under torch.no_grad() / in eval mode")
+        if self.pano_mode and not self.ape:
+            raise AttributeError("pano_mode=True requires ape=True: the reference builds abs_encoder only when ape is set "
+                                 "(simple_panoswin_transformer.py:841-842) and always calls it in pano mode (:934)")
+        with torch.no_grad():
+            return self._forward_tokens(x_bchw.float())
+
+    def _forward_tokens(self, img: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+        cd = self._compute_dtype
+        dev = img.device
+        ws = self.window_size
+        tok = self._stem(img)                                     # [B, Hs, Ws, E] in the compute dtype
+        B, Hs, Ws, E = tok.shape
+        pos = self._abs_position(Hs, Ws, dev) if (self.pano_mode and self.ape) else None
+        if self.patch_embed.norm is not None:
+            n = self.patch_embed.norm
+            x = ops.layernorm(tok.view(B, Hs * Ws, E), self._f(n.weight), self._f(n.bias), n.eps, torch.float32, pos)
+        else:
+            x = tok.view(B, Hs * Ws, E).float()
+            if pos is not None:
+                x = x + pos[None]
+        H, W = Hs, Ws
+        outs = []
+        for i, layer in enumerate(self.layers):
+            C = self.num_features[i]
+            uv = self._const(("uv", H, W), lambda: make_uv_hw2(H, W), dev) if self.pano_mode else None
+            for blk in layer.blocks:
+                a = blk.attn
+                shift = blk.shift_size
+                mask = None
+                if not self.pano_mode and shift > 0:
+                    mask = self._const(("mask", H, W, ws, shift), lambda: planar_attention_mask(H, W, ws, shift), dev)
+                xn = ops.layernorm(x, self._f(blk.norm1.weight), self._f(blk.norm1.bias), blk.norm1.eps, cd)
+                qkv = ops.linear(xn, self._w(a.qkv.weight, cd), self._f(a.qkv.bias))
+                att = ops.window_attention(qkv.view(B, H, W, 3 * C), self._f(a.sphere_position_alpha_table_Te),
+                                           self._f(a.sphere_position_beta_table_Te), self._f(a.qkv.bias), uv, mask,
+                                           a.num_heads, ws, shift, self.pano_mode, a.scale)
+                x = ops.linear(att.view(B, H * W, C), self._w(a.proj.weight, cd), self._f(a.proj.bias), residual=x, out=x)
+                xn = ops.layernorm(x, self._f(blk.norm2.weight), self._f(blk.norm2.bias), blk.norm2.eps, cd)
+                hid = ops.linear(xn, self._w(blk.mlp.fc1.weight, cd), self._f(blk.mlp.fc1.bias), gelu=True)
+                x = ops.linear(hid, self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), residual=x, out=x)
+            if i in self.out_indices:
+                n = getattr(self, f"norm{i}")
+                outs.append(ops.layernorm_nchw(x, self._f(n.weight), self._f(n.bias), H, W, n.eps))
+            if layer.downsample is not None:
+                d = layer.downsample
+                xm = ops.patch_merge_layernorm(x, self._f(d.norm.weight), self._f(d.norm.bias), H, W, d.norm.eps, cd)
+                x = ops.linear(xm, self._w(d.reduction.weight, cd), None, out_dtype=torch.float32)
+                H, W = (H + 1) // 2, (W + 1) // 2
+        return tuple(outs)
+
+
+def _load_checkpoint(model: nn.Module, path: str):
+    """mmcv_custom.load_checkpoint when the reference tree is importable (it also resizes bias tables,
+    mmcv_custom/checkpoint.py:286-356); otherwise a plain non-strict state_dict load with the same
+    `state_dict` / `model` unwrapping and `module.` / `encoder.` prefix stripping."""
+    try:
+        from mmcv_custom import load_checkpoint            # type: ignore
+        from mmdet.utils import get_root_logger            # type: ignore
+        return load_checkpoint(model, path, strict=False, logger=get_root_logger())
+    except ImportError:
+        pass
+    ckpt = torch.load(path, map_location="cpu")
+    sd = ckpt.get("state_dict", ckpt.get("model", ckpt)) if isinstance(ckpt, dict) else ckpt
+    clean = {}
+    for k, v in sd.items():
+        for prefix in ("module.", "encoder.", "backbone."):
+            if k.startswith(prefix):
+                k = k[len(prefix):]
+        clean[k] = v
+    return model.load_state_dict(clean, strict=False)

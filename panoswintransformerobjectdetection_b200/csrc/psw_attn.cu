@@ -1,0 +1,57 @@
+// psw_window_attn_fwd: argument validation and dispatch between the fp32 parity kernel
+// (psw_attn_simt.cu) and the bf16 tcgen05 kernel (psw_attn_tc.cu).
+#include "psw_common.cuh"
+
+namespace psw {
+template <typename T>
+int window_attn_simt(const T* qkv, T* out, const float* alpha, const float* beta, const float* qkv_bias,
+                     const float* uv, const float* mask, int B, int H, int W, int C, int heads, int window, int shift,
+                     int pano, float scale, cudaStream_t st);
+int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const float* qkv_bias,
+                   const float* uv, const float* mask, int B, int H, int W, int C, int heads, int window, int shift,
+                   int pano, float scale, cudaStream_t st);
+}  // namespace psw
+
+using namespace psw;
+
+static int check_attn_args(const void* qkv, void* out, const float* alpha, const float* beta, const float* uv, int B,
+                           int H, int W, int C, int heads, int window, int shift, int pano_mode) {
+  PSW_REQUIRE(qkv && out && alpha && beta, PSW_ERR_BAD_ARG, "psw_window_attn_fwd: null pointer");
+  PSW_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && heads > 0 && window > 0, PSW_ERR_BAD_ARG,
+              "psw_window_attn_fwd: bad dims B=%d H=%d W=%d C=%d heads=%d window=%d", B, H, W, C, heads, window);
+  PSW_REQUIRE(C % heads == 0, PSW_ERR_BAD_ARG, "psw_window_attn_fwd: channels %d not divisible by heads %d", C, heads);
+  PSW_REQUIRE(shift >= 0 && shift < window, PSW_ERR_BAD_ARG, "psw_window_attn_fwd: shift_size must be in [0, window)");
+  PSW_REQUIRE(!pano_mode || uv, PSW_ERR_BAD_ARG, "psw_window_attn_fwd: pano mode needs the uv table");
+  PSW_REQUIRE((int64_t)B * H * W < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd: too many tokens");
+  return 0;
+}
+
+extern "C" PSW_API int psw_window_attn_fwd(const void* qkv, void* out, const float* alpha, const float* beta,
+                                   const float* qkv_bias, const float* uv, const float* mask, int B, int H, int W,
+                                   int C, int heads, int window, int shift, int pano_mode, float scale, int dtype,
+                                   void* stream) {
+  int rc = check_attn_args(qkv, out, alpha, beta, uv, B, H, W, C, heads, window, shift, pano_mode);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PSW_F32)
+    return window_attn_simt<float>((const float*)qkv, (float*)out, alpha, beta, qkv_bias, uv, mask, B, H, W, C, heads,
+                                   window, shift, pano_mode, scale, st);
+  PSW_REQUIRE(dtype == PSW_BF16, PSW_ERR_BAD_ARG, "psw_window_attn_fwd: unknown dtype %d", dtype);
+  PSW_REQUIRE(window * window <= 64 && C / heads == 32, PSW_ERR_UNSUPPORTED,
+              "psw_window_attn_fwd(bf16): tcgen05 kernel needs window^2 <= 64 and head_dim == 32 (window=%d head_dim=%d)",
+              window, C / heads);
+  PSW_REQUIRE(aligned16(qkv) && aligned16(out), PSW_ERR_BAD_ARG, "psw_window_attn_fwd(bf16): pointers must be 16-byte aligned");
+  return window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, qkv_bias, uv, mask, B, H, W, C, heads, window, shift,
+                        pano_mode, scale, st);
+}
+
+// Debug / cross-check entry (not part of the reference-facing contract): the CUDA-core kernel on bf16 storage.
+extern "C" PSW_API int psw_window_attn_fwd_simt_bf16(const void* qkv, void* out, const float* alpha, const float* beta,
+                                             const float* qkv_bias, const float* uv, const float* mask, int B, int H,
+                                             int W, int C, int heads, int window, int shift, int pano_mode,
+                                             float scale, void* stream) {
+  int rc = check_attn_args(qkv, out, alpha, beta, uv, B, H, W, C, heads, window, shift, pano_mode);
+  if (rc) return rc;
+  return window_attn_simt<bf16>((const bf16*)qkv, (bf16*)out, alpha, beta, qkv_bias, uv, mask, B, H, W, C, heads, window,
+                                shift, pano_mode, scale, (cudaStream_t)stream);
+}

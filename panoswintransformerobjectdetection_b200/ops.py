@@ -1,0 +1,161 @@
+"""Thin torch-tensor wrappers over the C ABI (include/panoswin_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every op below forwards raw
+device pointers to libpanoswin_b200.so.  Nothing in this module computes on the CPU or through
+torch kernels — if the tensors are not CUDA tensors, or the library is missing, the call raises.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import PSW_BF16, PSW_EPI_GELU, PSW_F32, PanoSwinB200Error
+
+_launches = 0          # kernels enqueued through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return PSW_F32
+    if t.dtype == torch.bfloat16:
+        return PSW_BF16
+    raise PanoSwinB200Error(f"unsupported tensor dtype {t.dtype} (fp32 or bf16 only)")
+
+
+def _chk(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise PanoSwinB200Error("libpanoswin_b200 runs on CUDA tensors only (there is no CPU fallback)")
+        if not t.is_contiguous():
+            raise PanoSwinB200Error("libpanoswin_b200 needs contiguous tensors")
+        dev = dev or t.device
+        if t.device != dev:
+            raise PanoSwinB200Error("all tensors of one call must live on the same device")
+    return dev
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _f32(t, name):
+    if t is not None and t.dtype != torch.float32:
+        raise PanoSwinB200Error(f"{name} must be fp32")
+    return t
+
+
+def _call(fn_name, *args):
+    global _launches
+    lib = _lib.load()
+    rc = getattr(lib, fn_name)(*args)
+    _lib.check(rc, fn_name)
+    _launches += 1
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out_dtype=None, pos=None, out=None):
+    """LayerNorm over the last dim (+ optional fp32 position table `pos` [pos_rows, C] added per row
+    modulo pos_rows).  Reference: norm1/norm2 (simple_panoswin_transformer.py:504,:534), :768-772, :962."""
+    dev = _chk(x, gamma, beta, pos, out)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    out_dtype = out_dtype or x.dtype
+    if out is None:
+        out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    pos_rows = 0 if pos is None else pos.numel() // C
+    with torch.cuda.device(dev):
+        _call("psw_layernorm_fwd", _ptr(x), _ptr(out), _ptr(_f32(gamma, "gamma")), _ptr(_f32(beta, "beta")),
+              _ptr(_f32(pos, "pos")), rows, C, pos_rows, float(eps), _dt(x), _dt(out), _stream(dev))
+    return out
+
+
+def linear(x, w, bias=None, residual=None, gelu=False, out_dtype=None, out=None):
+    """act(x @ w.T + bias) (+ residual).  x [..., K], w [N, K]; fp32 tensors run the CUDA-core parity
+    kernel, bf16 tensors the tcgen05 kernel.  Reference: nn.Linear at :287, :309(+:533), :55-61(+:534), :575."""
+    dev = _chk(x, w, bias, residual, out)
+    K = x.shape[-1]
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise PanoSwinB200Error(f"linear: weight {tuple(w.shape)} does not match input features {K}")
+    M = x.numel() // K
+    if x.dtype != w.dtype:
+        raise PanoSwinB200Error("linear: x and w must share a dtype")
+    out_dtype = out_dtype or (residual.dtype if residual is not None else x.dtype)
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (N,), dtype=out_dtype, device=x.device)
+    if residual is not None and (residual.dtype != out.dtype or residual.numel() != out.numel()):
+        raise PanoSwinB200Error("linear: residual must match the output's dtype and shape")
+    with torch.cuda.device(dev):
+        _call("psw_linear_fwd", _ptr(x), _ptr(w), _ptr(_f32(bias, "bias")), _ptr(residual), _ptr(out), M, N, K,
+              PSW_EPI_GELU if gelu else 0, _dt(x), _dt(out), _stream(dev))
+    return out
+
+
+def window_attention(qkv, alpha, beta, qkv_bias, uv, mask, heads, window, shift, pano_mode, scale, out=None,
+                     impl=None):
+    """Fused shift + partition + W-MSA core + reverse + un-shift.  qkv [B, H, W, 3C] -> [B, H, W, C].
+    `impl`: None (product path), 'simt' (CUDA-core kernel on bf16), 'tc0' / 'tc1' (tcgen05 variants)."""
+    dev = _chk(qkv, alpha, beta, qkv_bias, uv, mask, out)
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    if out is None:
+        out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
+    args = [_ptr(qkv), _ptr(out), _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta")), _ptr(_f32(qkv_bias, "qkv_bias")),
+            _ptr(_f32(uv, "uv")), _ptr(_f32(mask, "mask")), B, H, W, C, heads, window, shift, 1 if pano_mode else 0,
+            float(scale)]
+    with torch.cuda.device(dev):
+        if impl is None:
+            _call("psw_window_attn_fwd", *args, _dt(qkv), _stream(dev))
+        elif impl == "simt":
+            if qkv.dtype != torch.bfloat16:
+                raise PanoSwinB200Error("impl='simt' is the bf16 cross-check kernel")
+            _call("psw_window_attn_fwd_simt_bf16", *args, _stream(dev))
+        elif impl in ("tc0", "tc1"):
+            _call("psw_window_attn_fwd_tc_variant", *args, int(impl[-1]), _stream(dev))
+        else:
+            raise PanoSwinB200Error(f"unknown impl {impl!r}")
+    return out
+
+
+def patch_merge_layernorm(x, gamma, beta, H, W, eps=1e-5, out_dtype=None):
+    """x [B, H*W, C] -> LN(concat 2x2) [B, ceil(H/2)*ceil(W/2), 4C] (reference :563-574)."""
+    dev = _chk(x, gamma, beta)
+    B, S, C = x.shape
+    if S != H * W:
+        raise PanoSwinB200Error("input feature has wrong size")
+    out = torch.empty((B, ((H + 1) // 2) * ((W + 1) // 2), 4 * C), dtype=out_dtype or x.dtype, device=x.device)
+    with torch.cuda.device(dev):
+        _call("psw_patch_merge_ln_fwd", _ptr(x), _ptr(out), _ptr(_f32(gamma, "gamma")), _ptr(_f32(beta, "beta")),
+              B, H, W, C, float(eps), _dt(x), _dt(out), _stream(dev))
+    return out
+
+
+def layernorm_nchw(x, gamma, beta, H, W, eps=1e-5):
+    """x [B, H*W, C] -> LayerNorm -> fp32 [B, C, H, W] contiguous (reference :974-978)."""
+    dev = _chk(x, gamma, beta)
+    B, S, C = x.shape
+    if S != H * W:
+        raise PanoSwinB200Error("input feature has wrong size")
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(dev):
+        _call("psw_layernorm_nchw_fwd", _ptr(x), _ptr(out), _ptr(_f32(gamma, "gamma")), _ptr(_f32(beta, "beta")),
+              B, S, C, float(eps), _dt(x), _stream(dev))
+    return out
+
+
+def cast(x, dtype):
+    dev = _chk(x)
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    with torch.cuda.device(dev):
+        _call("psw_cast", _ptr(x), _ptr(out), x.numel(), _dt(x), _dt(out), _stream(dev))
+    return out

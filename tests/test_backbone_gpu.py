@@ -1,0 +1,109 @@
+"""End-to-end parity of the drop-in backbone on a B200: the fp32 path against the reference's golden
+vectors (<= 1e-5 rel-L2, north_star) and the bf16 path against the oracle within the stated bf16
+tolerance (per block <= 1e-2, stage features <= 2e-2 rel-L2)."""
+import pytest
+import torch
+
+from _expect import rel_l2
+from conftest import load_golden
+from oracle import panoswin_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _build(cfg, sd, dtype):
+    import panoswintransformerobjectdetection_b200 as P
+    m = P.build_backbone(dict(type="SimplePanoSwinTransformer", patch_size=cfg["patch_size"], in_chans=cfg["in_chans"],
+                              embed_dim=cfg["embed_dim"], depths=list(cfg["depths"]), num_heads=list(cfg["num_heads"]),
+                              window_size=cfg["window_size"], mlp_ratio=cfg["mlp_ratio"], qkv_bias=cfg["qkv_bias"],
+                              qk_scale=cfg["qk_scale"], ape=cfg["ape"], patch_norm=cfg["patch_norm"],
+                              out_indices=tuple(cfg["out_indices"]), pano_mode=cfg["pano_mode"]))
+    m.load_state_dict(sd, strict=True)
+    m.to(DEV)
+    m.eval()
+    m.set_compute_dtype(dtype)
+    return m
+
+
+@pytest.mark.parametrize("name", ["tiny_pano", "odd_pano", "hd_var_pano", "planar", "planar_tall"])
+def test_fp32_matches_reference_golden(name):
+    meta, z = load_golden(name)
+    cfg = meta["cfg"]
+    sd = O.make_state_dict(cfg, meta["param_seed"])
+    img = O.make_image(meta["shape"], meta["image_seed"], meta["kind"])
+    m = _build(cfg, sd, "fp32")
+    outs = m(img.to(DEV))
+    torch.cuda.synchronize()
+    assert len(outs) == meta["n_out"]
+    for i, o in enumerate(outs):
+        assert o.dtype == torch.float32 and o.is_contiguous() and list(o.shape) == list(z[f"out{i}_shape"])
+        assert rel_l2(o, torch.from_numpy(z[f"out{i}"])) <= 1e-5, (name, i)
+
+
+@pytest.mark.parametrize("name", ["tiny_pano", "odd_pano", "planar"])
+def test_bf16_within_stated_tolerance(name):
+    meta, z = load_golden(name)
+    cfg = meta["cfg"]
+    sd = O.make_state_dict(cfg, meta["param_seed"])
+    img = O.make_image(meta["shape"], meta["image_seed"], meta["kind"])
+    m = _build(cfg, sd, "bf16")
+    outs = m(img.to(DEV))
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        assert o.dtype == torch.float32 and torch.isfinite(o).all()
+        assert rel_l2(o, torch.from_numpy(z[f"out{i}"])) <= 2e-2, (name, i)
+
+
+@pytest.mark.parametrize("kind", ["panoswin_t_512", "panoswin_t_512_randn"])
+def test_panoswin_t_512x1024(kind):
+    """BASELINE.json config 1: PanoSwin-T, 1x3x512x1024, fp32 parity; same input through the bf16 path."""
+    meta, z = load_golden(kind)
+    cfg = meta["cfg"]
+    sd = O.make_state_dict(cfg, meta["param_seed"])
+    img = O.make_image(meta["shape"], meta["image_seed"], meta["kind"])
+    st = meta["stride"]
+    m = _build(cfg, sd, "fp32")
+    outs = m(img.to(DEV))
+    torch.cuda.synchronize()
+    want_shapes = [[1, 96, 128, 256], [1, 192, 64, 128], [1, 384, 32, 64], [1, 768, 16, 32]]
+    for i, o in enumerate(outs):
+        assert list(o.shape) == want_shapes[i]
+        assert rel_l2(o.reshape(-1)[::st], torch.from_numpy(z[f"out{i}"])) <= 1e-5, i
+        assert abs(float(o.double().norm()) / float(z[f"out{i}_norm"]) - 1) <= 1e-5
+    m.set_compute_dtype("bf16")
+    outs16 = m(img.to(DEV))
+    torch.cuda.synchronize()
+    for i, (o, o32) in enumerate(zip(outs16, outs)):
+        assert rel_l2(o, o32) <= 2e-2, i
+
+
+def test_batch_rows_are_independent_and_sharding_is_exact():
+    """Images never interact: a batch of 4 equals the concatenation of two batches of 2,
+    which is what sharding the batch across GPUs relies on."""
+    cfg = O.make_config(embed_dim=32, depths=(2, 2, 2, 2), num_heads=(1, 2, 4, 8))
+    sd = O.make_state_dict(cfg, 3)
+    img = O.make_image((4, 3, 64, 128), 4).to(DEV)
+    for dtype in ("fp32", "bf16"):
+        m = _build(cfg, sd, dtype)
+        full = m(img)
+        halves = [m(img[:2]), m(img[2:])]
+        for i, o in enumerate(full):
+            # cuDNN may pick another stem algorithm per batch size, hence a tolerance instead of equality
+            assert rel_l2(o, torch.cat([halves[0][i], halves[1][i]], 0)) <= (1e-5 if dtype == "fp32" else 5e-3), (dtype, i)
+
+
+def test_api_surface_on_gpu():
+    import warnings
+    cfg = O.make_config(embed_dim=32, depths=(2, 2), num_heads=(1, 2), out_indices=(1,))
+    m = _build(cfg, O.make_state_dict(cfg, 0), "bf16")
+    assert m.eval() is None                                   # reference train() returns None (:981-983)
+    img = O.make_image((1, 3, 64, 100), 1).to(DEV)           # W != 2H: the reference warns, so do we
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        outs = m(img, pano_ratio_v=[[0, 1.0, 48]])
+    assert len(w) >= 2 and len(outs) == 1 and outs[0].shape == (1, 64, 8, 13)
+    m.set_pano_mode(False)
+    assert m(img)[0].shape == (1, 64, 8, 13)
+    m.switch_pano_mode()
+    assert m.pano_mode is True and all(b.pano_mode for l in m.layers for b in l.blocks)

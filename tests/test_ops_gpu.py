@@ -1,0 +1,191 @@
+"""Op-level parity of libpanoswin_b200 (through the C ABI, via ops.py) against the CPU oracle.
+Tolerances: fp32 path <= 1e-5 rel-L2 (BASELINE.json north_star); bf16 path compared with an fp32
+evaluation of the SAME bf16-rounded inputs: <= 4e-3 where only the output rounding differs (GEMM, LN),
+<= 1e-2 for the attention core (bf16 P operand), the 'per-block' tolerance of SURVEY.md §8d."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from _expect import attention_core, rel_l2
+from oracle import panoswin_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from panoswintransformerobjectdetection_b200 import ops as o
+    return o
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+@pytest.mark.parametrize("C", [24, 96, 192, 384, 768, 1536, 3072])
+@pytest.mark.parametrize("io", ["f32f32", "f32bf16", "bf16bf16"])
+def test_layernorm(ops, C, io):
+    g = _g(C)
+    rows = 517
+    x = torch.randn(rows, C, generator=g) * 2 + 0.5
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    pos = torch.randn(47, C, generator=g)
+    xin = x if io.startswith("f32") else x.bfloat16()
+    odt = torch.float32 if io.endswith("f32") else torch.bfloat16
+    want = F.layer_norm(xin.float(), (C,), gamma, beta, 1e-5)
+    got = ops.layernorm(xin.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-5, odt)
+    assert got.dtype == odt
+    assert rel_l2(got.float(), want) <= (1e-6 if odt == torch.float32 else 4e-3)
+    want_pos = want + pos[torch.arange(rows) % 47]
+    got = ops.layernorm(xin.to(DEV), gamma.to(DEV), beta.to(DEV), 1e-5, odt, pos.to(DEV))
+    assert rel_l2(got.float(), want_pos) <= (1e-6 if odt == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 32, 96), (1, 13, 25, 32), (2, 7, 13, 64), (1, 4, 7, 128), (1, 32, 64, 384)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_patch_merge_layernorm(ops, shape, dt):
+    B, H, W, C = shape
+    g = _g(H * W)
+    x = torch.randn(B, H * W, C, generator=g).to(dt)
+    gamma, beta = torch.randn(4 * C, generator=g), torch.randn(4 * C, generator=g)
+    img = F.pad(x.float().view(B, H, W, C), (0, 0, 0, W % 2, 0, H % 2))
+    quad = torch.cat([img[:, 0::2, 0::2], img[:, 1::2, 0::2], img[:, 0::2, 1::2], img[:, 1::2, 1::2]], -1)
+    want = F.layer_norm(quad.reshape(B, -1, 4 * C), (4 * C,), gamma, beta, 1e-5)
+    got = ops.patch_merge_layernorm(x.to(DEV), gamma.to(DEV), beta.to(DEV), H, W, 1e-5, dt)
+    assert got.shape == want.shape
+    assert rel_l2(got.float(), want) <= (1e-6 if dt == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 32, 96), (1, 13, 25, 192), (3, 5, 9, 768), (1, 2, 4, 1024)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_layernorm_nchw(ops, shape, dt):
+    B, H, W, C = shape
+    g = _g(C + H)
+    x = torch.randn(B, H * W, C, generator=g).to(dt)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    want = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5).view(B, H, W, C).permute(0, 3, 1, 2).contiguous()
+    got = ops.layernorm_nchw(x.to(DEV), gamma.to(DEV), beta.to(DEV), H, W, 1e-5)
+    assert got.dtype == torch.float32 and got.is_contiguous() and got.shape == want.shape
+    assert rel_l2(got, want) <= 1e-6
+
+
+@pytest.mark.parametrize("mnk", [(300, 96, 96), (1000, 288, 96), (64, 32, 5), (513, 72, 24), (257, 96, 384), (129, 384, 1536)])
+@pytest.mark.parametrize("gelu,res", [(False, False), (True, False), (False, True)])
+def test_linear_fp32(ops, mnk, gelu, res):
+    M, N, K = mnk
+    g = _g(M + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g) if res else None
+    want = F.linear(x.double(), w.double(), b.double())
+    if gelu:
+        want = F.gelu(want)
+    if res:
+        want = want + r.double()
+    got = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), None if r is None else r.to(DEV), gelu)
+    assert rel_l2(got, want) <= 2e-6
+
+
+TC_SHAPES = [(300, 96, 96), (1000, 288, 96), (4096, 384, 96), (777, 96, 384), (512, 2304, 768), (256, 768, 3072),
+             (130, 192, 1536), (128, 1152, 384), (20000, 192, 192), (333, 128, 128), (100, 32, 32), (65, 576, 192)]
+
+
+@pytest.mark.parametrize("mnk", TC_SHAPES)
+@pytest.mark.parametrize("odt,gelu,res,bias", [(torch.bfloat16, False, False, True), (torch.bfloat16, True, False, True),
+                                               (torch.float32, False, True, True), (torch.float32, False, False, False),
+                                               (torch.bfloat16, False, True, True)])
+def test_linear_bf16_tcgen05(ops, mnk, odt, gelu, res, bias):
+    M, N, K = mnk
+    g = _g(M * 3 + N)
+    x = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, generator=g) if bias else None
+    r = torch.randn(M, N, generator=g).to(odt) if res else None
+    want = F.linear(x.double(), w.double(), None if b is None else b.double())
+    if gelu:
+        want = F.gelu(want)
+    if res:
+        want = want + r.double()
+    got = ops.linear(x.to(DEV), w.to(DEV), None if b is None else b.to(DEV), None if r is None else r.to(DEV), gelu,
+                     out_dtype=odt)
+    torch.cuda.synchronize()
+    assert got.dtype == odt and got.shape == (M, N)
+    assert torch.isfinite(got).all()
+    assert rel_l2(got.float(), want) <= (4e-3 if odt == torch.bfloat16 else 2e-5)
+
+
+def _attn_case(H, W, heads, hd, shift, pano, B=2, seed=0, ws=7):
+    g = _g(seed + H * 7 + W)
+    C = heads * hd
+    qkv = torch.randn(B, H, W, 3 * C, generator=g)
+    qkv[..., :C] *= 1.5
+    alpha = torch.randn((2 * ws - 1) ** 2, heads, generator=g) * 0.5
+    beta = torch.randn((2 * ws - 1) ** 2, heads, generator=g) * 0.5
+    qb = torch.randn(3 * C, generator=g) * 0.5
+    uv = O.uv_grid(H, W) if pano else torch.zeros(H, W, 2)
+    return qkv, alpha, beta, qb, uv, C
+
+
+ATTN_CASES = [  # H, W, heads, shift, pano
+    (16, 32, 2, 0, True), (16, 32, 2, 3, True), (13, 25, 3, 3, True), (13, 25, 1, 0, True), (7, 13, 4, 3, True),
+    (4, 7, 8, 3, True), (25, 50, 1, 3, True), (12, 31, 2, 3, False), (12, 31, 2, 0, False), (20, 16, 3, 3, False),
+]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+@pytest.mark.parametrize("hd", [32, 24])
+def test_window_attention_fp32(ops, case, hd):
+    H, W, heads, shift, pano = case
+    qkv, alpha, beta, qb, uv, C = _attn_case(H, W, heads, hd, shift, pano)
+    scale = hd ** -0.5
+    want = attention_core(qkv, alpha, beta, qb, uv, H, W, heads, 7, shift, pano, scale)
+    mask = O.planar_shift_mask(H, W, 7, shift).to(DEV) if (not pano and shift) else None
+    got = ops.window_attention(qkv.to(DEV), alpha.to(DEV), beta.to(DEV), qb.to(DEV), uv.to(DEV) if pano else None, mask,
+                               heads, 7, shift, pano, scale)
+    torch.cuda.synchronize()
+    assert rel_l2(got, want) <= 1e-5
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+@pytest.mark.parametrize("impl", [None, "simt", "tc0", "tc1"])
+def test_window_attention_bf16(ops, case, impl):
+    H, W, heads, shift, pano = case
+    qkv, alpha, beta, qb, uv, C = _attn_case(H, W, heads, 32, shift, pano, seed=5)
+    qkv = qkv.bfloat16()
+    scale = 32 ** -0.5
+    # padding tokens use the bf16-rounded bias on the tensor-core path; fp32 on the CUDA-core path
+    want = attention_core(qkv.float(), alpha, beta, qb.bfloat16().float() if impl != "simt" else qb, uv, H, W, heads, 7,
+                          shift, pano, scale)
+    mask = O.planar_shift_mask(H, W, 7, shift).to(DEV) if (not pano and shift) else None
+    got = ops.window_attention(qkv.to(DEV), alpha.to(DEV), beta.to(DEV), qb.to(DEV), uv.to(DEV) if pano else None, mask,
+                               heads, 7, shift, pano, scale, impl=impl)
+    torch.cuda.synchronize()
+    assert got.dtype == torch.bfloat16 and torch.isfinite(got.float()).all()
+    assert rel_l2(got.float(), want) <= 1e-2
+
+
+def test_window_attention_no_qkv_bias(ops):
+    H, W, heads, shift, pano = 13, 25, 2, 3, True
+    qkv, alpha, beta, _, uv, C = _attn_case(H, W, heads, 32, shift, pano, seed=9)
+    want = attention_core(qkv, alpha, beta, None, uv, H, W, heads, 7, shift, pano, 32 ** -0.5)
+    got = ops.window_attention(qkv.to(DEV), alpha.to(DEV), beta.to(DEV), None, uv.to(DEV), None, heads, 7, shift, pano, 32 ** -0.5)
+    assert rel_l2(got, want) <= 1e-5
+    got = ops.window_attention(qkv.bfloat16().to(DEV), alpha.to(DEV), beta.to(DEV), None, uv.to(DEV), None, heads, 7, shift,
+                               pano, 32 ** -0.5)
+    want = attention_core(qkv.bfloat16().float(), alpha, beta, None, uv, H, W, heads, 7, shift, pano, 32 ** -0.5)
+    assert rel_l2(got.float(), want) <= 1e-2
+
+
+def test_errors_are_loud(ops):
+    from panoswintransformerobjectdetection_b200.ops import PanoSwinB200Error
+    x = torch.randn(4, 96)
+    with pytest.raises(PanoSwinB200Error):
+        ops.layernorm(x, torch.ones(96), torch.zeros(96))                      # CPU tensors: no fallback
+    qkv = torch.randn(1, 14, 28, 3 * 48, device=DEV).bfloat16()               # head_dim 48 on the tcgen05 path
+    t = torch.zeros(169, 1, device=DEV)
+    with pytest.raises(PanoSwinB200Error):
+        ops.window_attention(qkv, t, t, None, torch.zeros(14, 28, 2, device=DEV), None, 1, 7, 0, True, 1.0)
+    with pytest.raises(PanoSwinB200Error):
+        ops.window_attention(qkv.float(), t, t, None, torch.zeros(14, 28, 2, device=DEV), None, 1, 7, 7, True, 1.0)   # shift >= window
