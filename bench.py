@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the PanoSwin-T backbone forward (BASELINE.json metric: images/s @512x1024, bf16, batch 32/GPU).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...    # the reference algorithm on the host CPU
+
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement").  A step is one forward of the whole backbone
+over one batch of synthetic 3x512x1024 panoramas.  `value` is device-resident throughput (CUDA events, max
+over ranks); `e2e` goes through the public module API with pinned host buffers (H2D of the images and D2H of
+the four feature maps inside the timed region); `roofline` is measured live with CUDA events around every
+launch of our kernels; `cpu_baseline` times the CPU oracle (port of the reference) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "PanoSwin-T backbone images/s @512x1024 (bf16 inference)"
+UNIT = "images/s"
+IMG_H, IMG_W = 512, 1024
+PANOSWIN_T = dict(embed_dim=96, depths=[2, 2, 6, 2], num_heads=[3, 6, 12, 24], window_size=7, ape=True,
+                  pano_mode=True, patch_size=4, mlp_ratio=4.0)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_tflops=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json; sustained bf16 figure, kernels timed inside a long step)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi, background) during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # the samples taken while the GPU was busy are the upper half of the distribution
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work of each launch (DESIGN.md "Kernels"): bytes that must cross HBM and FLOPs
+# ------------------------------------------------------------------------------------------------
+def launch_work(fn, a):
+    sz = {0: 4, 1: 2}
+    if fn == "psw_window_attn_fwd":
+        B, H, W, C = a[7], a[8], a[9], a[10]
+        heads, ws = a[11], a[12]
+        tok = B * H * W
+        es = sz[a[16]]
+        nwin_h = -(-(2 * H if a[14] else H) // ws)
+        nwin_w = -(-(((W + 1) // 2) if a[14] else W) // ws)
+        flops = 4.0 * (ws * ws) ** 2 * (C // heads) * B * nwin_h * nwin_w * heads
+        return dict(kind="window_attn", shape=f"B{B} {H}x{W} C{C} h{heads} s{a[13]}", bytes=4.0 * tok * C * es, flops=flops)
+    if fn == "psw_linear_fwd":
+        M, N, K = a[5], a[6], a[7]
+        es, eo = sz[a[9]], sz[a[10]]
+        byt = M * K * es + N * K * es + M * N * eo + (M * N * eo if a[3] else 0)
+        return dict(kind="linear", shape=f"M{M} N{N} K{K}" + (" gelu" if a[8] & 1 else "") + (" +res" if a[3] else ""),
+                    bytes=float(byt), flops=2.0 * M * N * K)
+    if fn == "psw_layernorm_fwd":
+        rows, C = a[5], a[6]
+        return dict(kind="layernorm", shape=f"rows{rows} C{C}", bytes=float(rows * C * (sz[a[9]] + sz[a[10]])), flops=8.0 * rows * C)
+    if fn == "psw_patch_merge_ln_fwd":
+        B, H, W, C = a[4], a[5], a[6], a[7]
+        rows = B * ((H + 1) // 2) * ((W + 1) // 2)
+        return dict(kind="patch_merge_ln", shape=f"B{B} {H}x{W} C{C}", bytes=float(B * H * W * C * sz[a[9]] + rows * 4 * C * sz[a[10]]),
+                    flops=8.0 * rows * 4 * C)
+    if fn == "psw_layernorm_nchw_fwd":
+        B, HW, C = a[4], a[5], a[6]
+        return dict(kind="layernorm_nchw", shape=f"B{B} HW{HW} C{C}", bytes=float(B * HW * C * (sz[a[8]] + 4)), flops=8.0 * B * HW * C)
+    return dict(kind=fn, shape="", bytes=0.0, flops=0.0)
+
+
+class Tracer:
+    def __init__(self):
+        self.rec = []
+
+    def __call__(self, fn, args, e0, e1):
+        self.rec.append((fn, launch_work(fn, args), e0, e1))
+
+    def summary(self, peaks, steps):
+        groups = {}
+        for fn, w, e0, e1 in self.rec:
+            ms = e0.elapsed_time(e1)
+            g = groups.setdefault(w["kind"], dict(ms=0.0, bytes=0.0, flops=0.0, launches=0, shapes={}))
+            g["ms"] += ms; g["bytes"] += w["bytes"]; g["flops"] += w["flops"]; g["launches"] += 1
+            s = g["shapes"].setdefault(w["shape"], dict(ms=0.0, bytes=0.0, flops=0.0, n=0))
+            s["ms"] += ms; s["bytes"] += w["bytes"]; s["flops"] += w["flops"]; s["n"] += 1
+        ridge = peaks["bf16_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        out = {}
+        for k, g in groups.items():
+            hbm_bound = (g["flops"] / max(g["bytes"], 1.0)) < ridge
+            gbs = g["bytes"] / (g["ms"] * 1e-3) / 1e9
+            tfs = g["flops"] / (g["ms"] * 1e-3) / 1e12
+            out[k] = dict(ms_per_step=g["ms"] / steps, launches_per_step=g["launches"] / steps, gbs=gbs, tflops=tfs,
+                          bound="hbm" if hbm_bound else "tensor",
+                          frac=(gbs / peaks["hbm_gbs"]) if hbm_bound else (tfs / peaks["bf16_tflops"]),
+                          shapes={sh: dict(ms=s["ms"] / s["n"], gbs=s["bytes"] / (s["ms"] * 1e-3) / 1e9,
+                                           tflops=s["flops"] / (s["ms"] * 1e-3) / 1e12) for sh, s in g["shapes"].items()})
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+def build_model(device):
+    import torch
+    from oracle import panoswin_oracle as O
+    import panoswintransformerobjectdetection_b200 as P
+    m = P.SimplePanoSwinTransformer(**{k: v for k, v in PANOSWIN_T.items()}, drop_path_rate=0.0)
+    cfg = O.make_config()                                   # PanoSwin-T; random-init weights (no checkpoints offline)
+    m.load_state_dict(O.make_state_dict(cfg, 1), strict=True)
+    m.to(device)
+    m.eval()
+    m.set_compute_dtype("bf16")
+    return m
+
+
+def cpu_reference_images_per_s(batch, warmup, steps, budget_s=None):
+    """The reference algorithm on the host CPU: the oracle (fp32 torch port, pinned to the real reference by
+    tests/golden) — the Python reference itself cannot travel to the GPU box (no /root/reference there)."""
+    import torch
+    from oracle import panoswin_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.make_config()
+    sd = O.make_state_dict(cfg, 1)
+    img = O.make_image((batch, 3, IMG_H, IMG_W), 2)
+    for _ in range(warmup):
+        O.backbone_forward(sd, cfg, img)
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.backbone_forward(sd, cfg, img)
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s and len(times) >= 2:
+            break
+    return batch / statistics.median(times), statistics.median(times), len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                              # the CPU arm runs on rank 0 alone
+    batch = 2
+    ips, med, n, threads = cpu_reference_images_per_s(batch, max(1, min(args.warmup, 2)), args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"PanoSwin-T backbone forward, {batch}x3x{IMG_H}x{IMG_W} per step on the host CPU "
+                               "(oracle port of the reference, fp32, eval, no_grad)"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} forwards of batch {batch} (median)"},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import panoswintransformerobjectdetection_b200 as P
+    from panoswintransformerobjectdetection_b200 import ops
+    from panoswintransformerobjectdetection_b200.runtime import HostPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    model = build_model(dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_img = torch.rand(B, 3, IMG_H, IMG_W, generator=g).pin_memory()
+    dev_img = host_img.to(dev)
+    peaks = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    keep = []
+    def step_device():
+        keep[:] = [model(dev_img)]
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_count()
+    ms_total = timed(step_device, args.steps)
+    launches = ops.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- per-kernel CUDA-event trace (same steps again, events around every launch of our kernels)
+    tracer = Tracer()
+    ops.set_tracer(tracer)
+    ms_traced = timed(step_device, args.steps) / args.steps
+    ops.set_tracer(None)
+    torch.cuda.synchronize()
+    kern = tracer.summary(peaks, args.steps)
+    ours_ms = sum(k["ms_per_step"] for k in kern.values())
+
+    # ---- end to end through the public API with pinned host buffers
+    pipe = HostPipeline(model, chunk=args.chunk)
+    for _ in range(2):
+        pipe(host_img)
+    outs = []
+    def step_e2e():
+        outs[:] = [pipe(host_img)]
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = world * B / (ms_e2e * 1e-3)
+    h2d = host_img.numel() * host_img.element_size()
+    d2h = sum(o.numel() * o.element_size() for o in outs[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    dominant = max(kern.items(), key=lambda kv: kv[1]["ms_per_step"])
+    def roof(name, k):
+        hb = k["bound"] == "hbm"
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.isfile(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(name)
+        return {"kernel": name, "bound": k["bound"], "achieved": k["gbs"] if hb else k["tflops"],
+                "peak": peaks["hbm_gbs"] if hb else peaks["bf16_tflops"], "unit": "GB/s" if hb else "TFLOP/s",
+                "frac": k["frac"], "traffic": traffic, "ms_per_step": k["ms_per_step"],
+                "share_of_step": k["ms_per_step"] / ms_traced, "peak_source": peaks["source"]}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, med, n, threads = cpu_reference_images_per_s(2, 1, 6, budget_s=20.0)
+        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n} fp32 forwards of 2x3x{IMG_H}x{IMG_W} on the host (median {med:.2f} s)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"PanoSwin-T backbone inference (BASELINE.json configs[1]), batch {B}x3x{IMG_H}x{IMG_W} per GPU, "
+                               "bf16 activations / fp32 residual stream, random-init weights",
+                   "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective in the forward",
+                   "l2": "inputs (201 MB of images, >=400 MB activations per layer) exceed the 126 MB L2; no explicit flush",
+                   "stem": "conv stem runs on cuDNN (torch), everything after it on libpanoswin_b200"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e, "chunks": args.chunk},
+        "gpu_launches": launches,
+        "roofline": roof(*dominant),
+        "roofline_window_attn": roof("window_attn", kern["window_attn"]) if "window_attn" in kern else None,
+        "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk != "shapes"}
+                    for k, v in kern.items()},
+        "ms_per_step_traced": ms_traced, "ms_our_kernels_per_step": ours_ms,
+        "cpu_baseline": cpu,
+    }
+    if args.detail:
+        with open(args.detail, "w") as fh:
+            json.dump({"kernels": kern, "line": line}, fh, indent=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--chunk", type=int, default=8, help="images per pipelined chunk on the end-to-end path")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", default=None, help="write the per-shape kernel table to this JSON file")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun when called directly with --gpus N
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), __file__] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -55,10 +55,28 @@ def _f32(t, name):
     return t
 
 
+_tracer = None         # optional callable(fn_name, args, start_event, end_event): per-launch CUDA-event timing
+
+
+def set_tracer(tracer):
+    """Install / remove (None) a per-launch tracer.  When set, every launch is bracketed by CUDA events
+    recorded on the launching stream (bench.py uses this for the live roofline numbers)."""
+    global _tracer
+    _tracer = tracer
+
+
 def _call(fn_name, *args):
     global _launches
     lib = _lib.load()
-    rc = getattr(lib, fn_name)(*args)
+    if _tracer is None:
+        rc = getattr(lib, fn_name)(*args)
+    else:
+        stream = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rc = getattr(lib, fn_name)(*args)
+        e1.record(stream)
+        _tracer(fn_name, args, e0, e1)
     _lib.check(rc, fn_name)
     _launches += 1
 
