@@ -86,15 +86,31 @@ PSW_API int psw_linear_fwd(const void* x, const void* w, const float* bias, cons
  *   out      [B, H, W, C]   attention output (before proj), un-shifted token order
  *   alpha, beta [(2*window-1)^2, heads] fp32 tables (sphere_position_{alpha,beta}_table_Te)
  *   qkv_bias [3C] fp32 or NULL — q/k/v of a zero (padding) token: padded cells take part as keys/values
- *   uv       [H, W, 2] fp32 token coordinates (make_uv_hw2 :153-189); ignored (may be NULL) in planar mode
+ *   uv       [H, W, 2] fp32 token coordinates (make_uv_hw2 :153-189); used by the PSW_F32 path in pano mode
+ *   hav_table fp16 great-circle distances of every window of one image, from psw_window_hav_table(); used by
+ *            the PSW_BF16 path in pano mode (it depends on H, W, window, shift only, so callers cache it)
  *   mask     [nW, window^2, window^2] fp32 additive mask or NULL (planar mode, shifted blocks only)
  *   pano_mode 1: attention runs on the (2H, ceil(W/2)) north-south layout; 0: planar Swin roll(-s,-s)
  * PSW_BF16 requires window^2 <= 64 and C / heads == 32 (every shipped PanoSwin config).
  */
 PSW_API int psw_window_attn_fwd(const void* qkv, void* out, const float* alpha, const float* beta,
-                        const float* qkv_bias, const float* uv, const float* mask,
+                        const float* qkv_bias, const float* uv, const void* hav_table, const float* mask,
                         int B, int H, int W, int C, int heads, int window, int shift, int pano_mode,
                         float scale, int dtype, void* stream);
+
+/*
+ * Windows per column / row of the shifted, padded map the attention runs on (pano: ceil(2H/window) x
+ * ceil(ceil(W/2)/window); planar: ceil(H/window) x ceil(W/window)).  Host-only helper.
+ */
+PSW_API int psw_window_grid(int H, int W, int window, int pano_mode, int* nwh, int* nww);
+
+/*
+ * Great-circle distance table for pano mode: table[win][i][j] = haversine22(uv_i, uv_j)
+ * (lzx/models/great_circle.py:71-86) for the window^2 tokens of every window of ONE image, padding tokens at
+ * uv = (0, 0) (reference :486-491, :344-347).  fp16, layout [nwh*nww][window^2][56] (row pitch 56 halfs).
+ * Depends on (H, W, window, shift) only — not on batch, heads or weights (uv carries no gradient).
+ */
+PSW_API int psw_window_hav_table(const float* uv, void* table, int H, int W, int window, int shift, void* stream);
 
 /*
  * PatchMerging front half: 2x2 gather in the order (0,0),(1,0),(0,1),(1,1) with zero padding of odd
@@ -116,9 +132,7 @@ PSW_API int psw_cast(const void* src, void* dst, int64_t n, int src_dtype, int d
 
 /*
  * Diagnostics (used by tests / profiling only; same arguments as psw_window_attn_fwd, bf16 storage):
- *   _simt_bf16  : the CUDA-core kernel on bf16 tensors (cross-check of the tensor-core kernel);
- *   _tc_variant : the tcgen05 kernel with an explicit variant — 0: P operand read from TMEM,
- *                 1: P operand staged through shared memory.
+ *   _simt_bf16  : the CUDA-core kernel on bf16 tensors (cross-check of the tensor-core kernel).
  */
 /* Host-only: dump the kernels' window geometry (see psw_api.cu); map may be NULL to query hp / wp. */
 PSW_API int psw_debug_source_map(int H, int W, int window, int shift, int pano_mode, int* map, int capacity,
@@ -127,10 +141,6 @@ PSW_API int psw_window_attn_fwd_simt_bf16(const void* qkv, void* out, const floa
                                           const float* qkv_bias, const float* uv, const float* mask,
                                           int B, int H, int W, int C, int heads, int window, int shift,
                                           int pano_mode, float scale, void* stream);
-PSW_API int psw_window_attn_fwd_tc_variant(const void* qkv, void* out, const float* alpha, const float* beta,
-                                           const float* qkv_bias, const float* uv, const float* mask,
-                                           int B, int H, int W, int C, int heads, int window, int shift,
-                                           int pano_mode, float scale, int variant, void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,29 +8,31 @@ int window_attn_simt(const T* qkv, T* out, const float* alpha, const float* beta
                      const float* uv, const float* mask, int B, int H, int W, int C, int heads, int window, int shift,
                      int pano, float scale, cudaStream_t st);
 int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const float* qkv_bias,
-                   const float* uv, const float* mask, int B, int H, int W, int C, int heads, int window, int shift,
-                   int pano, float scale, cudaStream_t st);
+                   const void* hav_table, const float* mask, int B, int H, int W, int C, int heads, int window,
+                   int shift, int pano, float scale, cudaStream_t st);
+int window_hav_table(const float* uv, void* table, int H, int W, int window, int shift, cudaStream_t st);
 }  // namespace psw
 
 using namespace psw;
 
-static int check_attn_args(const void* qkv, void* out, const float* alpha, const float* beta, const float* uv, int B,
+static int check_attn_args(const void* qkv, void* out, const float* alpha, const float* beta, const void* uv, int B,
                            int H, int W, int C, int heads, int window, int shift, int pano_mode) {
   PSW_REQUIRE(qkv && out && alpha && beta, PSW_ERR_BAD_ARG, "psw_window_attn_fwd: null pointer");
   PSW_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && heads > 0 && window > 0, PSW_ERR_BAD_ARG,
               "psw_window_attn_fwd: bad dims B=%d H=%d W=%d C=%d heads=%d window=%d", B, H, W, C, heads, window);
   PSW_REQUIRE(C % heads == 0, PSW_ERR_BAD_ARG, "psw_window_attn_fwd: channels %d not divisible by heads %d", C, heads);
   PSW_REQUIRE(shift >= 0 && shift < window, PSW_ERR_BAD_ARG, "psw_window_attn_fwd: shift_size must be in [0, window)");
-  PSW_REQUIRE(!pano_mode || uv, PSW_ERR_BAD_ARG, "psw_window_attn_fwd: pano mode needs the uv table");
+  PSW_REQUIRE(!pano_mode || uv, PSW_ERR_BAD_ARG, "psw_window_attn_fwd: pano mode needs the uv table (fp32) / the great-circle table (bf16)");
   PSW_REQUIRE((int64_t)B * H * W < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd: too many tokens");
   return 0;
 }
 
 extern "C" PSW_API int psw_window_attn_fwd(const void* qkv, void* out, const float* alpha, const float* beta,
-                                   const float* qkv_bias, const float* uv, const float* mask, int B, int H, int W,
-                                   int C, int heads, int window, int shift, int pano_mode, float scale, int dtype,
-                                   void* stream) {
-  int rc = check_attn_args(qkv, out, alpha, beta, uv, B, H, W, C, heads, window, shift, pano_mode);
+                                   const float* qkv_bias, const float* uv, const void* hav_table, const float* mask,
+                                   int B, int H, int W, int C, int heads, int window, int shift, int pano_mode,
+                                   float scale, int dtype, void* stream) {
+  int rc = check_attn_args(qkv, out, alpha, beta, dtype == PSW_BF16 ? hav_table : (const void*)uv, B, H, W, C, heads,
+                           window, shift, pano_mode);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == PSW_F32)
@@ -41,8 +43,26 @@ extern "C" PSW_API int psw_window_attn_fwd(const void* qkv, void* out, const flo
               "psw_window_attn_fwd(bf16): tcgen05 kernel needs window^2 <= 64 and head_dim == 32 (window=%d head_dim=%d)",
               window, C / heads);
   PSW_REQUIRE(aligned16(qkv) && aligned16(out), PSW_ERR_BAD_ARG, "psw_window_attn_fwd(bf16): pointers must be 16-byte aligned");
-  return window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, qkv_bias, uv, mask, B, H, W, C, heads, window, shift,
-                        pano_mode, scale, st);
+  PSW_REQUIRE(aligned16(hav_table), PSW_ERR_BAD_ARG, "psw_window_attn_fwd(bf16): great-circle table must be 16-byte aligned");
+  return window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, qkv_bias, hav_table, mask, B, H, W, C, heads, window,
+                        shift, pano_mode, scale, st);
+}
+
+extern "C" PSW_API int psw_window_grid(int H, int W, int window, int pano_mode, int* nwh, int* nww) {
+  PSW_REQUIRE(H > 0 && W > 0 && window > 0 && nwh && nww, PSW_ERR_BAD_ARG, "psw_window_grid: bad arguments");
+  WinGeom g = make_geom(H, W, window, 0, pano_mode);
+  *nwh = g.nWh;
+  *nww = g.nWw;
+  return 0;
+}
+
+extern "C" PSW_API int psw_window_hav_table(const float* uv, void* table, int H, int W, int window, int shift,
+                                            void* stream) {
+  PSW_REQUIRE(uv && table, PSW_ERR_BAD_ARG, "psw_window_hav_table: null pointer");
+  PSW_REQUIRE(H > 0 && W > 0 && window > 0 && window * window <= 64 && shift >= 0 && shift < window, PSW_ERR_BAD_ARG,
+              "psw_window_hav_table: bad dims H=%d W=%d window=%d shift=%d", H, W, window, shift);
+  PSW_REQUIRE(aligned16(table), PSW_ERR_BAD_ARG, "psw_window_hav_table: table must be 16-byte aligned");
+  return window_hav_table(uv, table, H, W, window, shift, (cudaStream_t)stream);
 }
 
 // Debug / cross-check entry (not part of the reference-facing contract): the CUDA-core kernel on bf16 storage.

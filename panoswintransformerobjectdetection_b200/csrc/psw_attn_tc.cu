@@ -3,24 +3,28 @@
 // BasicWindowAttention core / window_reverse of the reference
 // (simple_panoswin_transformer.py:376-409, :486-491, :64-92, :290-308) in one pass over HBM.
 //
-// Work unit = one (window, head): 49 tokens x head_dim 32.  Two consecutive units form a "pair" that
-// shares one 128-row tensor-core tile:
-//   S[128x128] = [Q_u0;Q_u1] . [K_u0;K_u1]^T      tcgen05.mma M=128 N=128 K=32, only the two diagonal
-//                                                 64x64 blocks are used (tensor pipe is far from the bound)
-//   O[128x64]  = P[128x64 keys] . [V_u0 | V_u1]   tcgen05.mma M=128 N=64 K=64, P read from TMEM (or smem),
+// Work decomposition.  A "unit" is one (window, head): 49 tokens x head_dim 32.  The tensor-core tile has
+// 128 rows = two units: the SAME head of two consecutive windows (w0 = 2k, w1 = 2k+1).  A work item is a
+// window pair x a chunk of HC heads, so everything that depends only on the windows (token maps, the
+// great-circle distance rows) is fetched once per item and reused by its HC steps:
+//   S[128x128] = [Q_u0;Q_u1] . [K_u0;K_u1]^T      tcgen05.mma M=128 N=128 K=32; only the two diagonal 64x64
+//                                                 blocks are used (the tensor pipe is far from the bound)
+//   O[128x64]  = P[128x64 keys] . [V_u0 | V_u1]   tcgen05.mma M=128 N=64 K=64, P read from TMEM (bf16),
 //                                                 V consumed MN-major straight from its [key][dim] rows;
 //                                                 rows of unit u use output columns [32u, 32u+32)
-// Thread r of the CTA owns row r of the tile (TMEM lane r): it reads its 49 logits with tcgen05.ld,
-// adds the great-circle bias d(i,j)*alpha[idx]+beta[idx] (d from shared memory, computed once per window
-// from the fp32 uv table), does the softmax in registers (exp2, fp32), writes un-normalised bf16 P back,
-// and finally scales its O row by 1/sum and stores it with 128-bit stores to the token's UN-shifted
-// position.  q/k/v rows are gathered by cp.async (16 B) directly from the un-shifted [B,H,W,3C] qkv tensor
-// into the 64B-swizzled UMMA layout: the pano shift with longitude wrap-around, the odd-W zero column,
-// the window padding (padding tokens = qkv bias) and the partition are pure address arithmetic
-// (psw::source_token).  The next pair is prefetched while the current one is computed; 2-3 CTAs per SM
-// overlap each other's MMA / softmax / store phases.
+// Thread r owns tile row r (TMEM lane r): tcgen05.ld of its 49 logits, + d(i,j)*alpha[idx]+beta[idx]
+// (d from the fp16 distance table staged in shared memory, tables per head in shared memory), softmax in
+// registers (exp2, fp32), un-normalised bf16 P back to TMEM, finally O row * 1/sum stored with 128-bit
+// stores at the token's UN-shifted position.  q/k/v rows are gathered with cp.async (16 B) straight from the
+// un-shifted [B,H,W,3C] qkv tensor into the 64B-swizzled UMMA layout: pano shift with longitude wrap-around,
+// the odd-W zero column, window padding (padding tokens = qkv bias) and partition are address arithmetic
+// (psw::source_token).  One q/k/v buffer per CTA: Q/K of the next step are prefetched as soon as the S MMA
+// has retired, V as soon as the PV MMA has retired; 4 CTAs per SM (TMEM 4 x 128 columns) overlap each
+// other's MMA / softmax / store phases.
 //
 // Algorithmic HBM bytes per unit: 49 * 32 * 2 B * 4 (q, k, v read + o written) = 12,544 B.
+#include <cuda_fp16.h>
+
 #include "psw_common.cuh"
 
 namespace psw {
@@ -28,14 +32,12 @@ namespace psw {
 constexpr int AT_THREADS = 128;
 constexpr int AT_PART_BYTES = 128 * 64;            // 128 rows x 64 B (32 bf16), SWIZZLE_64B
 constexpr int AT_BUF_BYTES = 3 * AT_PART_BYTES;    // q, k, v
-constexpr int AT_HAV_PITCH = 52;                   // floats per distance-matrix row (16 B aligned rows)
+constexpr int AT_HAV_PITCH = 56;                   // halfs per distance-table row (112 B = 7 x 16 B)
 constexpr int AT_TMEM_COLS = 128;
 constexpr int AT_P_COL = 0;                        // P (bf16x2 packed): TMEM columns [0, 32)
 constexpr int AT_O_COL = 32;                       // O (fp32): TMEM columns [32, 96)
+constexpr int AT_CTAS_PER_SM = 4;
 constexpr float LOG2E = 1.4426950408889634f;
-#ifndef PSW_ATTN_TC_DEFAULT_VARIANT
-#define PSW_ATTN_TC_DEFAULT_VARIANT 0              // 0: P stays in TMEM (A-from-TMEM MMA), 1: P through smem
-#endif
 
 __device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
@@ -56,6 +58,42 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Great-circle distance table: hav[win][i][j] = haversine22(uv_i, uv_j) for the 49 tokens of every window
+// of ONE image (it depends on the window position only, not on batch / head / weights), fp16, row pitch 56.
+// Built once per (H, W, shift) by the host and kept L2-resident; padding tokens sit at uv = (0, 0)
+// (reference :486-491, :344-347).  Formula and evaluation order: lzx/models/great_circle.py:82-86, fp32.
+// ---------------------------------------------------------------------------------------------------
+__global__ void hav_table_kernel(const float* __restrict__ uv, __half* __restrict__ table, WinGeom g) {
+  const int ws = g.ws, N = ws * ws;
+  __shared__ float su[64], sv[64], scv[64];
+  const int wi = blockIdx.x;
+  const int wr = wi / g.nWw, wc = wi - wr * g.nWw;
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    const int r = t / ws, c = t - r * ws;
+    const int s = source_token(g, wr * ws + r, wc * ws + c);
+    float uu = 0.f, vv = 0.f;
+    if (s >= 0) { uu = uv[2 * s]; vv = uv[2 * s + 1]; }
+    su[t] = uu; sv[t] = vv; scv[t] = cosf(vv);
+  }
+  __syncthreads();
+  __half* out = table + (size_t)wi * N * AT_HAV_PITCH;
+  for (int q = threadIdx.x; q < N * AT_HAV_PITCH; q += blockDim.x) {
+    const int i = q / AT_HAV_PITCH, j = q - i * AT_HAV_PITCH;
+    float d = 0.f;
+    if (j < N) {
+      const float sdv = sinf(0.5f * fabsf(sv[j] - sv[i]));
+      const float sdu = sinf(0.5f * (su[j] - su[i]));
+      const float a = sdv * sdv + (scv[j] * scv[i]) * (sdu * sdu);
+      d = asinf(sqrtf(fminf(a, 1.0f))) * 2.0f;
+    }
+    out[q] = __float2half_rn(d);
+  }
+}
 
 struct AttnParams {
   const bf16* qkv;
@@ -63,48 +101,58 @@ struct AttnParams {
   const float* alpha;
   const float* beta;
   const float* qkv_bias;
-  const float* uv;
+  const __half* hav;      // [wpi][N][56] or nullptr (planar mode: d == 0)
   const float* mask;
   WinGeom g;
   int B, C, heads;
+  int hc;                 // heads per work item (divides heads)
+  int n_windows;          // B * windows per image
+  int n_items;            // ceil(n_windows / 2) * (heads / hc)
   float scale;
-  int64_t total_units;
 };
 
-template <int WS, bool P_IN_TMEM>
-__global__ void __launch_bounds__(AT_THREADS)
+// One pipeline step = one head of one window pair.
+struct Step {
+  int item;               // work item index (for range checks)
+  int wp;                 // window pair: windows 2*wp, 2*wp + 1
+  int e;                  // head
+  int el;                 // head index inside the item, 0 .. hc-1
+  int n;                  // running step count of this CTA (parity selects the table slot)
+};
+
+template <int WS>
+__global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
 window_attn_tc_kernel(const AttnParams p) {
   constexpr int N = WS * WS;                     // tokens per window (<= 64)
   constexpr int TW = 2 * WS - 1;                 // relative-position table width
   constexpr int TAB = TW * TW;
+  constexpr int TABP = (TAB + 1) & ~1;           // padded to an even count
   static_assert(N <= 64, "window too large for the 64-row unit tile");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* bufs = smem;                                                  // [2][3][128 x 64 B]
-  uint8_t* psm = bufs + 2 * AT_BUF_BYTES;                                // [128 x 128 B] P (smem variant only)
-  float* hav = reinterpret_cast<float*>(psm + (P_IN_TMEM ? 0 : 128 * 128));  // [2][N][52]
-  float2* tab = reinterpret_cast<float2*>(hav + 2 * N * AT_HAV_PITCH);   // [2][TAB] (alpha, beta) * log2(e)
-  int* tok_src = reinterpret_cast<int*>(tab + 2 * TAB);                  // [4][64]
-  float* tok_u = reinterpret_cast<float*>(tok_src + 4 * 64);             // [4][64]
-  float* tok_v = tok_u + 4 * 64;                                         // [4][64]
-  float* tok_cv = tok_v + 4 * 64;                                        // [4][64] cos(v)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tok_cv + 4 * 64);         // [2]: S ready, O ready
+  uint8_t* buf = smem;                                                   // [3][128 x 64 B]
+  __half* hav_s = reinterpret_cast<__half*>(buf + AT_BUF_BYTES);         // [2 units][N][56]
+  float2* tab = reinterpret_cast<float2*>(hav_s + 2 * N * AT_HAV_PITCH); // [2 slots][TABP] (alpha, beta) * log2(e)
+  int* src = reinterpret_cast<int*>(tab + 2 * TABP);                     // [2 slots][2 units][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(src + 2 * 2 * 64);        // [2]: S ready, O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   bf16* bias_bf = reinterpret_cast<bf16*>(tmem_slot + 4);                // [3C] (16 B aligned)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int C = p.C, heads = p.heads;
+  const int C = p.C, heads = p.heads, C3 = 3 * p.C;
   const WinGeom g = p.g;
   const int wpi = g.nWh * g.nWw;
   const int64_t HW = (int64_t)g.H * g.W;
+  const int n_hc = heads / p.hc;
 
   // ---------------------------------------------------------------- one-time setup
-  for (int i = tid; i < (2 * AT_BUF_BYTES + (P_IN_TMEM ? 0 : 128 * 128)) / 16; i += AT_THREADS)
-    reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0, 0, 0, 0);          // padding rows must stay finite
-  for (int i = tid; i < 2 * N * AT_HAV_PITCH; i += AT_THREADS) hav[i] = 0.f;   // planar mode: d == 0
-  for (int i = tid; i < 3 * C; i += AT_THREADS) bias_bf[i] = __float2bfloat16_rn(p.qkv_bias ? p.qkv_bias[i] : 0.f);
+  for (int i = tid; i < AT_BUF_BYTES / 16; i += AT_THREADS)
+    reinterpret_cast<uint4*>(buf)[i] = make_uint4(0, 0, 0, 0);           // padding rows must stay finite
+  for (int i = tid; i < 2 * N * AT_HAV_PITCH / 2; i += AT_THREADS)
+    reinterpret_cast<uint32_t*>(hav_s)[i] = 0u;                          // planar mode: d == 0
+  for (int i = tid; i < C3; i += AT_THREADS) bias_bf[i] = __float2bfloat16_rn(p.qkv_bias ? p.qkv_bias[i] : 0.f);
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -120,147 +168,139 @@ window_attn_tc_kernel(const AttnParams p) {
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 
-  const int64_t n_pairs = (p.total_units + 1) >> 1;
-  const int64_t pair_begin = n_pairs * blockIdx.x / gridDim.x;
-  const int64_t pair_end = n_pairs * (blockIdx.x + 1) / gridDim.x;
+  const int item_begin = (int)((int64_t)p.n_items * blockIdx.x / gridDim.x);
+  const int item_end = (int)((int64_t)p.n_items * (blockIdx.x + 1) / gridDim.x);
 
-  int tok_ready_win = -1;          // windows <= this have their token maps in tok_*[win & 3]
-  int hav_win0 = -1, hav_win1 = -1;  // window whose distance matrix sits in hav slot 0 / 1
+  // this thread's tile row
+  const int unit = tid >> 6;                               // warp-uniform
+  const int ti = tid & 63;
+  const int ic = ti < N ? ti : 0;
+  const int ri = ic / WS, ci = ic - ri * WS;
 
-  // token map + coordinates of window `win` (all threads call; threads < N work)
-  auto prep_tokens = [&](int win) {
-    if (tid < N) {
-      const int wi = win % wpi;
+  auto first_step = [&](int item) {
+    Step s;
+    s.item = item;
+    s.wp = item / n_hc;
+    s.e = (item - s.wp * n_hc) * p.hc;
+    s.el = 0;
+    s.n = 0;
+    return s;
+  };
+  auto next_step = [&](Step s) {
+    ++s.n;
+    if (++s.el < p.hc) { ++s.e; return s; }
+    s.el = 0;
+    ++s.item;
+    if (s.e + 1 < heads) { ++s.e; } else { s.e = 0; ++s.wp; }
+    return s;
+  };
+  // token maps of both windows of pair `wp` -> src[slot] (thread = (unit, token))
+  auto prep_src = [&](int wp) {
+    const int w = 2 * wp + unit;
+    int s = -1;
+    if (ti < N && w < p.n_windows) {
+      const int wi = w % wpi;
       const int wr = wi / g.nWw, wc = wi - wr * g.nWw;
-      const int r = tid / WS, c = tid - r * WS;
-      const int s = source_token(g, wr * WS + r, wc * WS + c);
-      float uu = 0.f, vv = 0.f;
-      if (g.pano && s >= 0) {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(p.uv) + s);
-        uu = t.x; vv = t.y;
+      s = source_token(g, wr * WS + ri, wc * WS + ci);
+    }
+    src[(wp & 1) * 128 + tid] = s;
+  };
+  // gather rows of `parts` (bit 0: Q, bit 1: K, bit 2: V) of step `st`; also its per-head tables with Q/K
+  auto issue_loads = [&](const Step& st, int parts) {
+    const int c = tid & 3;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int w = 2 * st.wp + u;
+      if (w >= p.n_windows) continue;
+      const int b = w / wpi;
+      const bf16* base = p.qkv + ((int64_t)b * HW) * C3 + st.e * 32 + c * 8;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int t = (tid >> 2) + 32 * k;
+        if (t >= N) continue;
+        const int s = src[(st.wp & 1) * 128 + u * 64 + t];
+        const int row = u * 64 + t;
+        uint8_t* dst = buf + row * 64 + ((c ^ ((row >> 1) & 3)) << 4);
+        const bf16* g_row = base + (int64_t)s * C3;
+        const bf16* b_row = bias_bf + st.e * 32 + c * 8;
+#pragma unroll
+        for (int part = 0; part < 3; ++part) {
+          if (!(parts & (1 << part))) continue;
+          if (s >= 0) cp_async16(dst + part * AT_PART_BYTES, g_row + part * C);
+          else *reinterpret_cast<uint4*>(dst + part * AT_PART_BYTES) = *reinterpret_cast<const uint4*>(b_row + part * C);
+        }
       }
-      const int o = (win & 3) * 64 + tid;
-      tok_src[o] = s;
-      tok_u[o] = uu;
-      tok_v[o] = vv;
-      tok_cv[o] = cosf(vv);
     }
-  };
-  // great-circle distance matrix of window `win` (haversine22, lzx/models/great_circle.py:82-86)
-  auto compute_hav = [&](int win) {
-    const int ts = (win & 3) * 64;
-    float* h = hav + (win & 1) * N * AT_HAV_PITCH;
-    for (int q = tid; q < N * N; q += AT_THREADS) {
-      const int i = q / N, j = q - i * N;
-      const float sdv = __sinf(0.5f * (tok_v[ts + j] - tok_v[ts + i]));
-      const float sdu = __sinf(0.5f * (tok_u[ts + j] - tok_u[ts + i]));
-      float a = sdv * sdv + tok_cv[ts + j] * tok_cv[ts + i] * (sdu * sdu);
-      a = fminf(fmaxf(a, 0.f), 1.f);
-      h[i * AT_HAV_PITCH + j] = 2.0f * asinf(sqrtf(a));
-    }
-  };
-  // gather q/k/v rows of pair `pr` into buffer `buf` (cp.async 16 B; padding tokens take the qkv bias)
-  auto issue_loads = [&](int64_t pr, int buf) {
-    uint8_t* base = bufs + buf * AT_BUF_BYTES;
-    for (int id = tid; id < 2 * 3 * N * 4; id += AT_THREADS) {
-      const int chunk = id & 3;
-      const int item = id >> 2;
-      const int unit = item / (3 * N);
-      const int rem = item - unit * 3 * N;
-      const int part = rem / N;
-      const int t = rem - part * N;
-      const int64_t u = 2 * pr + unit;
-      if (u >= p.total_units) continue;
-      const int win = (int)(u / heads);
-      const int e = (int)(u - (int64_t)win * heads);
-      const int row = unit * 64 + t;
-      uint8_t* dst = base + part * AT_PART_BYTES + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
-      const int s = tok_src[(win & 3) * 64 + t];
-      const int ch = part * C + e * 32 + chunk * 8;
-      if (s >= 0) {
-        const int b = win / wpi;
-        cp_async16(dst, p.qkv + ((int64_t)b * HW + s) * (3 * C) + ch);
-      } else {
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(bias_bf + ch);
+    if (parts & 1) {
+      float* trow = reinterpret_cast<float*>(tab + (st.n & 1) * TABP);
+      for (int k = tid; k < TAB; k += AT_THREADS) {
+        cp_async4(trow + 2 * k, p.alpha + k * heads + st.e);
+        cp_async4(trow + 2 * k + 1, p.beta + k * heads + st.e);
       }
     }
   };
-  auto prep_pair_tokens = [&](int64_t pr) {
-    const int64_t u0 = 2 * pr;
-    int64_t u1 = u0 + 1;
-    if (u1 >= p.total_units) u1 = u0;
-    const int w0 = (int)(u0 / heads), w1 = (int)(u1 / heads);
-    for (int w = (tok_ready_win + 1 > w0 ? tok_ready_win + 1 : w0); w <= w1; ++w) prep_tokens(w);
-    if (w1 > tok_ready_win) tok_ready_win = w1;
+  // my own distance-table row of pair `wp` (no other thread reads it: no barrier needed, only my wait_group)
+  auto issue_hav = [&](int wp) {
+    const int w = 2 * wp + unit;
+    if (p.hav == nullptr || ti >= N || w >= p.n_windows) return;
+    const __half* grow = p.hav + ((size_t)(w % wpi) * N + ti) * AT_HAV_PITCH;
+    __half* srow = hav_s + (unit * N + ti) * AT_HAV_PITCH;
+#pragma unroll
+    for (int k = 0; k < AT_HAV_PITCH / 8; ++k) cp_async16(srow + 8 * k, grow + 8 * k);
   };
 
-  if (pair_begin < pair_end) {
-    prep_pair_tokens(pair_begin);
+  Step cur = first_step(item_begin);
+  if (item_begin < item_end) {
+    prep_src(cur.wp);
     __syncthreads();
-    issue_loads(pair_begin, 0);
+    issue_loads(cur, 3);
   }
-  cp_async_commit();
+  cp_async_commit();                                       // group A: Q, K, tables
+  if (item_begin < item_end) issue_loads(cur, 4);
+  cp_async_commit();                                       // group B: V
+  if (item_begin < item_end) issue_hav(cur.wp);
+  cp_async_commit();                                       // group C: distance rows
 
-  int it = 0;
-  for (int64_t pr = pair_begin; pr < pair_end; ++pr, ++it) {
-    const int buf = it & 1;
-    const uint32_t par = (uint32_t)(it & 1);
-    __syncthreads();         // every thread is done with the previous pair's token maps / tables / TMEM rows
-    // ---- A. prefetch the next pair (its buffer was released by the PV commit of the previous iteration)
-    if (pr + 1 < pair_end) prep_pair_tokens(pr + 1);
-    __syncthreads();
-    if (pr + 1 < pair_end) issue_loads(pr + 1, buf ^ 1);
-    cp_async_commit();
+  uint32_t par = 0;
+  while (cur.item < item_end) {
+    const Step nxt = next_step(cur);
+    const bool has_next = nxt.item < item_end;
+    // ---- 0. token maps of the next window pair (other slot)
+    __syncthreads();         // everyone is done with the previous step's token maps / tables / TMEM rows
+    if (has_next && nxt.wp != cur.wp) prep_src(nxt.wp);
 
-    // ---- B. per-window distance matrix + per-head tables of this pair
-    const int64_t u0 = 2 * pr;
-    const bool valid1 = (u0 + 1) < p.total_units;
-    const int win0 = (int)(u0 / heads);
-    const int e0 = (int)(u0 - (int64_t)win0 * heads);
-    const int win1 = valid1 ? (int)((u0 + 1) / heads) : win0;
-    const int e1 = valid1 ? (int)((u0 + 1) - (int64_t)win1 * heads) : e0;
-    if (g.pano) {
-      if ((win0 & 1) ? (hav_win1 != win0) : (hav_win0 != win0)) {
-        compute_hav(win0);
-        if (win0 & 1) hav_win1 = win0; else hav_win0 = win0;
-      }
-      if (win1 != win0 && ((win1 & 1) ? (hav_win1 != win1) : (hav_win0 != win1))) {
-        compute_hav(win1);
-        if (win1 & 1) hav_win1 = win1; else hav_win0 = win1;
-      }
+    // ---- 1. Q, K and the tables of this step have landed (groups B, C may still be in flight)
+    cp_async_wait<2>();
+    {
+      float2* t2 = tab + (cur.n & 1) * TABP;              // scale my own entries (the ones I copied) by log2(e)
+      for (int k = tid; k < TAB; k += AT_THREADS) t2[k] = make_float2(t2[k].x * LOG2E, t2[k].y * LOG2E);
     }
-    for (int i = tid; i < 2 * TAB; i += AT_THREADS) {
-      const int unit = i / TAB;
-      const int k = i - unit * TAB;
-      const int e = unit ? e1 : e0;
-      tab[i] = make_float2(__ldg(p.alpha + k * heads + e) * LOG2E, __ldg(p.beta + k * heads + e) * LOG2E);
-    }
-
-    // ---- C. this pair's q/k/v have landed
-    cp_async_wait<1>();
     fence_async_shared();
     __syncthreads();
 
-    // ---- D. S = Q . K^T (both units at once, block diagonal)
-    const uint32_t sq = smem_u32(bufs + buf * AT_BUF_BYTES);
+    // ---- 2. S = Q . K^T (both units at once, block diagonal)
+    const uint32_t sq = smem_u32(buf);
     if (tid == 0) {
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
       const uint64_t dq = umma_smem_desc(sq, 16, 512, UMMA_SWIZZLE_64B);
       const uint64_t dk = umma_smem_desc(sq + AT_PART_BYTES, 16, 512, UMMA_SWIZZLE_64B);
       umma_ss(tmem_base, dq, dk, idesc, 0);
-      umma_ss(tmem_base, dq + 2, dk + 2, idesc, 1);          // head_dim 16..31: +32 B inside the swizzle row
+      umma_ss(tmem_base, dq + 2, dk + 2, idesc, 1);        // head_dim 16..31: +32 B inside the swizzle row
       umma_commit(&bars[0]);
     }
     mbar_wait(&bars[0], par);
     tc_fence_after();
 
-    // ---- E. bias + softmax on my row
-    const int unit = tid >> 6;                               // warp-uniform
-    const int i = tid & 63;
-    const bool row_valid = (i < N) && (unit == 0 || valid1);
-    const int ic = i < N ? i : 0;
-    const int my_win = unit ? win1 : win0;
+    // ---- 3. Q/K buffers are free: prefetch the next step's Q, K, tables
+    if (has_next) issue_loads(nxt, 3);
+    cp_async_commit();                                     // group A'
+
+    // ---- 4. bias + softmax on my row (needs groups B, C of this step: everything but A')
+    cp_async_wait<1>();
+    fence_async_shared();                                  // my V rows -> visible to the PV MMA after the barrier
+    const int my_w = 2 * cur.wp + unit;
+    const bool row_valid = (ti < N) && (my_w < p.n_windows);
     float sum = 1.f;
     {
       uint32_t sr[N];
@@ -288,24 +328,24 @@ window_attn_tc_kernel(const AttnParams p) {
           sr[k] = t1;
         }
       }
-      const float* hrow = hav + (my_win & 1) * N * AT_HAV_PITCH + ic * AT_HAV_PITCH;
-      const int ri = ic / WS, ci = ic - ri * WS;
-      const float2* trow = tab + unit * TAB + (ri + WS - 1) * TW + (ci + WS - 1);
-      const float* mrow = p.mask ? p.mask + ((int64_t)(my_win % wpi) * N + ic) * N : nullptr;
+      const uint4* h8 = reinterpret_cast<const uint4*>(hav_s + (unit * N + ic) * AT_HAV_PITCH);   // 8 halfs per load
+      const float2* trow = tab + (cur.n & 1) * TABP + (ri + WS - 1) * TW + (ci + WS - 1);
+      const float* mrow = p.mask ? p.mask + ((int64_t)((my_w < p.n_windows ? my_w : 0) % wpi) * N + ic) * N : nullptr;
       const float sc = p.scale * LOG2E;
       float t[N];
       float mx = -INFINITY;
-      const float4* h4 = reinterpret_cast<const float4*>(hrow);   // rows are 16 B aligned (pitch 52 floats)
 #pragma unroll
-      for (int jc = 0; jc < (N + 3) / 4; ++jc) {
-        const float4 hq = h4[jc];
-        const float hv[4] = {hq.x, hq.y, hq.z, hq.w};
+      for (int jc = 0; jc < (N + 7) / 8; ++jc) {
+        const uint4 hq = h8[jc];
+        const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int j = 4 * jc + q;
+        for (int q = 0; q < 8; ++q) {
+          const int j = 8 * jc + q;
           if (j < N) {
+            const __half2 hh = *reinterpret_cast<const __half2*>(&hw[q >> 1]);
+            const float hv = (q & 1) ? __high2float(hh) : __low2float(hh);
             const float2 ab = trow[-((j / WS) * TW + (j % WS))];
-            float bia = fmaf(hv[q], ab.x, ab.y);
+            float bia = fmaf(hv, ab.x, ab.y);
             if (mrow) bia = fmaf(__ldg(mrow + j), LOG2E, bia);
             t[j] = fmaf(__uint_as_float(sr[j]), sc, bia);
             mx = fmaxf(mx, t[j]);
@@ -321,21 +361,13 @@ window_attn_tc_kernel(const AttnParams p) {
         if (2 * k + 1 < N) { p1 = fast_exp2(t[2 * k + 1] - mx); sum += p1; }
         pk[k] = row_valid ? pack_bf16x2(p0, p1) : 0u;
       }
-      if constexpr (P_IN_TMEM) {
-        tmem_st_x32(tmem_base + lane_base + AT_P_COL, pk);
-        tmem_st_wait();
-      } else {
-        uint8_t* prow = psm + tid * 128;                     // K-major, SWIZZLE_128B
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(prow + ((c ^ (tid & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-        fence_async_shared();
-      }
+      tmem_st_x32(tmem_base + lane_base + AT_P_COL, pk);
+      tmem_st_wait();
     }
     tc_fence_before();
     __syncthreads();
 
-    // ---- F. O = P . [V_u0 | V_u1]
+    // ---- 5. O = P . [V_u0 | V_u1]
     if (tid == 0) {
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);     // B (V) is MN-major: [key][dim] rows
@@ -343,29 +375,29 @@ window_attn_tc_kernel(const AttnParams p) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {                              // 16 keys per MMA = two 8-key groups of 512 B
         const uint64_t dv = umma_smem_desc(sv + k * 1024, 4096, 512, UMMA_SWIZZLE_64B);
-        if constexpr (P_IN_TMEM) {
-          umma_ts(tmem_base + AT_O_COL, tmem_base + AT_P_COL + k * 8, dv, idesc, k > 0);
-        } else {
-          const uint64_t dp = umma_smem_desc(smem_u32(psm) + k * 32, 16, 1024, UMMA_SWIZZLE_128B);
-          umma_ss(tmem_base + AT_O_COL, dp, dv, idesc, k > 0);
-        }
+        umma_ts(tmem_base + AT_O_COL, tmem_base + AT_P_COL + k * 8, dv, idesc, k > 0);
       }
       umma_commit(&bars[1]);
     }
     mbar_wait(&bars[1], par);
     tc_fence_after();
 
-    // ---- G. normalise and store my output row at the token's un-shifted position
+    // ---- 6. V buffer and (at the end of an item) the distance rows are free: prefetch
+    if (has_next) issue_loads(nxt, 4);
+    cp_async_commit();                                     // group B'
+    if (has_next && nxt.wp != cur.wp) issue_hav(nxt.wp);
+    cp_async_commit();                                     // group C'
+
+    // ---- 7. normalise and store my output row at the token's un-shifted position
     {
       uint32_t orow[32];
       tmem_ld_x32(tmem_base + lane_base + AT_O_COL + (uint32_t)(unit * 32), orow);
       tmem_ld_wait();
-      const int s = tok_src[(my_win & 3) * 64 + ic];
+      const int s = src[(cur.wp & 1) * 128 + unit * 64 + ic];
       if (row_valid && s >= 0) {
         const float inv = 1.0f / sum;
-        const int b = my_win / wpi;
-        const int e = unit ? e1 : e0;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)b * HW + s) * C + e * 32);
+        const int b = my_w / wpi;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)b * HW + s) * C + cur.e * 32);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 v;
@@ -378,6 +410,8 @@ window_attn_tc_kernel(const AttnParams p) {
       }
     }
     tc_fence_before();       // the next iteration's barrier orders these TMEM reads before the next S MMA
+    par ^= 1;
+    cur = nxt;
   }
 
   cp_async_wait<0>();
@@ -389,63 +423,50 @@ window_attn_tc_kernel(const AttnParams p) {
   }
 }
 
-static size_t attn_tc_smem_bytes(int ws, int C, bool p_in_tmem) {
-  const int N = ws * ws, TAB = (2 * ws - 1) * (2 * ws - 1);
+static size_t attn_tc_smem_bytes(int ws, int C) {
+  const int N = ws * ws, TAB = (2 * ws - 1) * (2 * ws - 1), TABP = (TAB + 1) & ~1;
   size_t b = 1024;                                   // alignment slack
-  b += 2 * AT_BUF_BYTES;
-  b += p_in_tmem ? 0 : 128 * 128;
-  b += (size_t)2 * N * AT_HAV_PITCH * 4;
-  b += (size_t)2 * TAB * 8;
-  b += 4 * 64 * 4 * 4;
+  b += AT_BUF_BYTES;
+  b += (size_t)2 * N * AT_HAV_PITCH * 2;
+  b += (size_t)2 * TABP * 8;
+  b += 2 * 2 * 64 * 4;
   b += 2 * 8 + 16;
   b += (size_t)3 * C * 2;
-  return b;
-}
-
-template <int WS, bool P_IN_TMEM>
-static int launch_attn_tc(const AttnParams& p, int ctas_per_sm, cudaStream_t st) {
-  const size_t smem = attn_tc_smem_bytes(WS, p.C, P_IN_TMEM);
-  auto kern = window_attn_tc_kernel<WS, P_IN_TMEM>;
-  PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t n_pairs = (p.total_units + 1) / 2;
-  int64_t grid = (int64_t)num_sms() * ctas_per_sm;
-  if (grid > n_pairs) grid = n_pairs;
-  kern<<<(unsigned)grid, AT_THREADS, smem, st>>>(p);
-  return launch_status("window_attn_tc_kernel");
-}
-
-// variant: 0 = P through TMEM (tcgen05.mma A-from-TMEM), 1 = P through shared memory
-int window_attn_tc_variant(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const float* qkv_bias,
-                           const float* uv, const float* mask, int B, int H, int W, int C, int heads, int window,
-                           int shift, int pano, float scale, int variant, cudaStream_t st) {
-  AttnParams p;
-  p.qkv = qkv; p.out = out; p.alpha = alpha; p.beta = beta; p.qkv_bias = qkv_bias; p.uv = uv; p.mask = mask;
-  p.g = make_geom(H, W, window, shift, pano);
-  p.B = B; p.C = C; p.heads = heads; p.scale = scale;
-  p.total_units = (int64_t)B * p.g.nWh * p.g.nWw * heads;
-  PSW_REQUIRE(window == 7, PSW_ERR_UNSUPPORTED,
-              "psw_window_attn_fwd(bf16): the tcgen05 kernel is instantiated for window 7 (every shipped PanoSwin config); got %d",
-              window);
-  if (variant == 0) return launch_attn_tc<7, true>(p, 2, st);
-  return launch_attn_tc<7, false>(p, 2, st);
+  // at least 46 KiB so that no more than 4 CTAs (4 x 128 TMEM columns) ever share an SM
+  return b < 46 * 1024 ? 46 * 1024 : b;
 }
 
 int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const float* qkv_bias,
-                   const float* uv, const float* mask, int B, int H, int W, int C, int heads, int window, int shift,
-                   int pano, float scale, cudaStream_t st) {
-  return window_attn_tc_variant(qkv, out, alpha, beta, qkv_bias, uv, mask, B, H, W, C, heads, window, shift, pano, scale,
-                                PSW_ATTN_TC_DEFAULT_VARIANT, st);
+                   const void* hav_table, const float* mask, int B, int H, int W, int C, int heads, int window,
+                   int shift, int pano, float scale, cudaStream_t st) {
+  PSW_REQUIRE(window == 7, PSW_ERR_UNSUPPORTED,
+              "psw_window_attn_fwd(bf16): the tcgen05 kernel is instantiated for window 7 (every shipped PanoSwin config); got %d",
+              window);
+  PSW_REQUIRE(!pano || hav_table, PSW_ERR_BAD_ARG,
+              "psw_window_attn_fwd(bf16): pano mode needs the great-circle table (psw_window_hav_table)");
+  AttnParams p;
+  p.qkv = qkv; p.out = out; p.alpha = alpha; p.beta = beta; p.qkv_bias = qkv_bias;
+  p.hav = pano ? (const __half*)hav_table : nullptr;
+  p.mask = mask;
+  p.g = make_geom(H, W, window, shift, pano);
+  p.B = B; p.C = C; p.heads = heads; p.scale = scale;
+  p.hc = heads % 3 == 0 ? 3 : (heads % 4 == 0 ? 4 : (heads % 2 == 0 ? 2 : 1));
+  p.n_windows = B * p.g.nWh * p.g.nWw;
+  p.n_items = ((p.n_windows + 1) / 2) * (heads / p.hc);
+  const size_t smem = attn_tc_smem_bytes(window, C);
+  PSW_REQUIRE(smem <= 220 * 1024, PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd(bf16): C=%d too large", C);
+  auto kern = window_attn_tc_kernel<7>;
+  PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = num_sms() * AT_CTAS_PER_SM;
+  if (grid > p.n_items) grid = p.n_items;
+  kern<<<grid, AT_THREADS, smem, st>>>(p);
+  return launch_status("window_attn_tc_kernel");
+}
+
+int window_hav_table(const float* uv, void* table, int H, int W, int window, int shift, cudaStream_t st) {
+  WinGeom g = make_geom(H, W, window, shift, 1);
+  hav_table_kernel<<<g.nWh * g.nWw, 128, 0, st>>>(uv, (__half*)table, g);
+  return launch_status("hav_table_kernel");
 }
 
 }  // namespace psw
-
-extern "C" PSW_API int psw_window_attn_fwd_tc_variant(const void* qkv, void* out, const float* alpha, const float* beta,
-                                              const float* qkv_bias, const float* uv, const float* mask, int B, int H,
-                                              int W, int C, int heads, int window, int shift, int pano_mode,
-                                              float scale, int variant, void* stream) {
-  using namespace psw;
-  PSW_REQUIRE(qkv && out && alpha && beta, PSW_ERR_BAD_ARG, "psw_window_attn_fwd_tc_variant: null pointer");
-  PSW_REQUIRE(C / heads == 32 && C % heads == 0, PSW_ERR_UNSUPPORTED, "head_dim must be 32");
-  return window_attn_tc_variant((const bf16*)qkv, (bf16*)out, alpha, beta, qkv_bias, uv, mask, B, H, W, C, heads, window,
-                                shift, pano_mode, scale, variant, (cudaStream_t)stream);
-}

@@ -1,14 +1,21 @@
 // K2 (throughput path): y = act(x . w^T + bias) (+ residual) with bf16 operands on the 5th-generation
-// tensor cores (tcgen05.mma, fp32 accumulators in TMEM), operands staged by TMA.
+// tensor cores (tcgen05.mma, fp32 accumulators in TMEM), every global access a TMA transfer.
 //
-// Persistent, warp-specialised CTA (one per SM, 192 threads):
+// Persistent, warp-specialised CTA (one per SM, 320 threads):
 //   warp 0      TMA producer : [128 x 64] x-tile and [BLOCK_N x 64] w-tile per stage, SWIZZLE_128B, mbarrier ring
 //   warp 1      MMA issuer   : one thread issues 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) per stage; commits free
 //                              the smem slot and, per tile, publish the accumulator
-//   warps 2..5  epilogue     : tcgen05.ld accumulator rows -> +bias -> [GELU] -> [+residual] -> global store
-// The accumulator is double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
-// MMAs of tile i+1.  Tiles are ordered n-fastest, so CTAs of one wave share the x-tile through L2.
-// Rows beyond M and K beyond the tensor are zero-filled by TMA; stores are guarded.
+//   warps 2..9  epilogue     : two warps per TMEM lane quadrant, alternating 64-byte-wide column chunks:
+//                              tcgen05.ld 32 rows x CW columns -> +bias -> [GELU] -> [+residual] -> swizzled smem
+//                              tile -> TMA store (coalesced, clipped at M / N).  Residual tiles are TMA-loaded two
+//                              chunks ahead into a per-warp ring, so no thread ever issues a strided global access.
+// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of
+// tile i+1.  Tiles are ordered n-fastest, so CTAs of one wave share the x-tile through L2.
+// Rows beyond M and K beyond the tensor are zero-filled by TMA.
+//
+// GELU on this path: 0.5 x (1 + tanh(x (c0 + c1 x^2 + c2 x^4))) with a minimax fit of the exact erf GELU
+// (max abs error 5.1e-5 over the real line, below bf16 resolution of the activations) and MUFU.TANH — the
+// fp32 parity path keeps erff.
 #include "psw_common.cuh"
 
 namespace psw {
@@ -16,13 +23,16 @@ namespace psw {
 constexpr int TC_BM = 128;         // UMMA M
 constexpr int TC_BK = 64;          // one 128-byte swizzle row of bf16
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_TILE_BYTES = 32 * 64;      // epilogue staging tile: 32 rows x 64 B, SWIZZLE_64B
 
 struct TcSmemTail {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
   uint64_t tfull[2];
   uint64_t tempty[2];
+  uint64_t res_bar[TC_EPI_WARPS][2];
   uint32_t tmem_base;
 };
 
@@ -33,60 +43,34 @@ __device__ __forceinline__ void tmem_alloc_rt(uint32_t* slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float xc = fminf(fmaxf(x, -9.0f), 9.0f);
+  const float x2 = xc * xc;
+  const float p = fmaf(fmaf(-3.20974528e-04f, x2, 3.68320430e-02f), x2, 7.97686932e-01f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xc * p));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
 
-template <typename TO> struct OutVec;
-template <> struct OutVec<float> {
-  static __device__ __forceinline__ void load16(const float* p, float (&v)[16]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
-      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-    }
-  }
-  static __device__ __forceinline__ void store16(float* p, const float (&v)[16]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  }
-};
-template <> struct OutVec<bf16> {
-  static __device__ __forceinline__ void load16(const bf16* p, float (&v)[16]) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      uint4 t = __ldg(reinterpret_cast<const uint4*>(p) + i);
-      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-        v[8 * i + 2 * j] = __low2float(h);
-        v[8 * i + 2 * j + 1] = __high2float(h);
-      }
-    }
-  }
-  static __device__ __forceinline__ void store16(bf16* p, const float (&v)[16]) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      uint4 t;
-      t.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-      t.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-      t.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-      t.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-      reinterpret_cast<uint4*>(p)[i] = t;
-    }
-  }
-};
+template <typename TO> struct Chunk;             // CW output columns = one 64-byte row of the staging tile
+template <> struct Chunk<float> { static constexpr int CW = 16; };
+template <> struct Chunk<bf16> { static constexpr int CW = 32; };
 
-template <bool GELU, typename TO>
+template <bool GELU, bool RES, typename TO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                 const float* __restrict__ bias, const TO* __restrict__ residual, TO* __restrict__ y, int64_t M, int N,
-                 int K, int block_n, int stages, int tmem_cols) {
+                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r,
+                 const float* __restrict__ bias, int64_t M, int N, int K, int block_n, int stages) {
+  constexpr int CW = Chunk<TO>::CW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = TC_BM * TC_BK * 2;                 // 16 KiB
   const uint32_t b_bytes = (uint32_t)block_n * TC_BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(smem + (size_t)stages * stage_bytes);
+  uint8_t* epi_smem = smem + (size_t)stages * stage_bytes;    // per warp: 2 out tiles (+ 2 residual tiles)
+  constexpr int EPI_PER_WARP = (RES ? 4 : 2) * TC_TILE_BYTES;
+  TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(epi_smem + TC_EPI_WARPS * EPI_PER_WARP);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,22 +78,28 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const int64_t m_tiles = (M + TC_BM - 1) / TC_BM;
   const int64_t total_tiles = m_tiles * n_tiles;
   const int k_blocks = (K + TC_BK - 1) / TC_BK;
-  const uint32_t acc_stride = (uint32_t)tmem_cols >> 1;
+  const uint32_t acc_stride = 256;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
+    tma_prefetch_desc(&map_y);
+    if (RES) tma_prefetch_desc(&map_r);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&tail->full[s], 1);
       mbar_init(&tail->empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tail->tfull[s], 1);
-      mbar_init(&tail->tempty[s], 4);
+      mbar_init(&tail->tempty[s], TC_EPI_WARPS);
+    }
+    for (int w = 0; w < TC_EPI_WARPS; ++w) {
+      mbar_init(&tail->res_bar[w][0], 1);
+      mbar_init(&tail->res_bar[w][1], 1);
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc_rt(&tail->tmem_base, (uint32_t)tmem_cols);
+  if (warp == 1) tmem_alloc_rt(&tail->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -162,85 +152,182 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
     }
   } else {
-    // ------------------------------- epilogue (4 warps) --------------------------
+    // ------------------------------- epilogue (8 warps) --------------------------
+    const int ew = warp - 2;
     const int quad = warp & 3;                                // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;                                 // the two warps of a quadrant alternate chunks
+    uint8_t* my_smem = epi_smem + ew * EPI_PER_WARP;
+    uint8_t* out_buf[2] = {my_smem, my_smem + TC_TILE_BYTES};
+    uint8_t* res_buf[2] = {my_smem + 2 * TC_TILE_BYTES, my_smem + 3 * TC_TILE_BYTES};
+    uint64_t* res_bar = tail->res_bar[ew];
+    const int n_chunks = block_n / CW;
+    const int sw = (lane >> 1) & 3;                           // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+    uint8_t* my_row_out[2] = {out_buf[0] + lane * 64, out_buf[1] + lane * 64};
+    const uint8_t* my_row_res[2] = {res_buf[0] + lane * 64, res_buf[1] + lane * 64};
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint32_t out_cnt = 0;                                     // chunks stored so far (selects the out buffer)
+    uint32_t res_issued = 0, res_used = 0;                    // residual ring counters (2 deep)
+    uint32_t tile_iter = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
       const int64_t m_t = tile / n_tiles;
       const int n_t = (int)(tile - m_t * n_tiles);
+      const int row0 = (int)(m_t * TC_BM) + quad * 32;
+      const int col0 = n_t * block_n;
+      // chunks of this warp in this tile: c = first, first + 2, ... (first alternates with the tile parity so an
+      // odd chunk count still balances the two warps of a quadrant)
+      const int first = (half + (int)(tile_iter & 1u) * (n_chunks & 1)) & 1;
+      if (RES) {
+        // prefetch the first two residual chunks of this tile before waiting for the accumulator
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c = first + 2 * j;
+            if (c < n_chunks) {
+              const uint32_t b = res_issued & 1;
+              mbar_expect_tx(&res_bar[b], TC_TILE_BYTES);
+              tma_load_2d(res_buf[b], &map_r, &res_bar[b], col0 + c * CW, row0);
+              ++res_issued;
+            }
+          }
+        }
+      }
       mbar_wait(&tail->tfull[acc], acc_phase);
       tc_fence_after();
-      const int64_t row = m_t * TC_BM + quad * 32 + lane;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * acc_stride;
-      for (int c0 = 0; c0 < block_n; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld_x16(t_addr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        const int col = n_t * block_n + c0;
-        if (row < M && col < N) {
-          float v[16];
+      for (int c = first; c < n_chunks; c += 2) {
+        float v[CW];
+        if constexpr (CW == 32) {
+          uint32_t r[32];
+          tmem_ld_x32(t_addr + (uint32_t)(c * CW), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        } else {
+          uint32_t r[16];
+          tmem_ld_x16(t_addr + (uint32_t)(c * CW), r);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-          if (bias) {
+        }
+        const int col = col0 + c * CW;
+        if (bias) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col) + i);
+          for (int i = 0; i < CW / 4; ++i) {
+            if (col + 4 * i < N) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col) + i);
               v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
             }
           }
-          if (GELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
-          }
-          if (residual) {
-            float rr[16];
-            OutVec<TO>::load16(residual + row * N + col, rr);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += rr[i];
-          }
-          OutVec<TO>::store16(y + row * N + col, v);
         }
+        if (GELU) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] = gelu_fast(v[i]);
+        }
+        if (RES) {
+          const uint32_t b = res_used & 1;
+          mbar_wait(&res_bar[b], (res_used >> 1) & 1);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 t = *reinterpret_cast<const uint4*>(my_row_res[b] + ((q ^ sw) << 4));
+            const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+            if constexpr (CW == 16) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) v[4 * q + i] += __uint_as_float(w4[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w4[i]);
+                v[8 * q + 2 * i] += __low2float(h);
+                v[8 * q + 2 * i + 1] += __high2float(h);
+              }
+            }
+          }
+          ++res_used;
+          __syncwarp();                                       // every lane has read the tile: the slot is free
+          if (lane == 0 && c + 4 < n_chunks) {                // keep the ring two chunks ahead
+            const uint32_t nb = res_issued & 1;
+            mbar_expect_tx(&res_bar[nb], TC_TILE_BYTES);
+            tma_load_2d(res_buf[nb], &map_r, &res_bar[nb], col0 + (c + 4) * CW, row0);
+            ++res_issued;
+          }
+        }
+        // stage the chunk in shared memory (64-byte rows, 64B swizzle -> conflict-free 16-byte stores)
+        const uint32_t ob = out_cnt & 1;
+        if (lane == 0) tma_store_wait_read<1>();              // the store issued two chunks ago has left this buffer
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 t;
+          if constexpr (CW == 16) {
+            t = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                           __float_as_uint(v[4 * q + 3]));
+          } else {
+            t = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+          }
+          *reinterpret_cast<uint4*>(my_row_out[ob] + ((q ^ sw) << 4)) = t;
+        }
+        fence_async_shared();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_y, out_buf[ob], col, row0);       // clipped at M and N by the tensor map
+          tma_store_commit();
+        }
+        ++out_cnt;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait<0>();                       // all stores of this warp are complete
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_rt(tmem_base, (uint32_t)tmem_cols);
+    tmem_dealloc_rt(tmem_base, 512);
   }
 }
 
-// Largest tile width <= 256 that is a multiple of 16 and divides N (falls back to 256/zero-filled tail).
+// Tile width: a multiple of 32 (epilogue chunks), <= 256 (TMEM double buffer); 192 keeps four pipeline stages
+// next to the epilogue staging, so it is preferred whenever it divides N.
 static int pick_block_n(int N) {
-  if (N <= 256) return N;
-  for (int bn = 256; bn >= 64; bn -= 16)
+  if (N <= 256) return (N + 31) / 32 * 32;
+  const int prefs[] = {192, 256, 224, 160, 128, 96, 64};
+  for (int bn : prefs)
     if (N % bn == 0) return bn;
-  return 256;
+  return 192;                                                 // ragged last tile: zero-filled loads, clipped stores
 }
 
-template <bool GELU, typename TO>
-static int launch_tc(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, const void* residual, void* y,
-                     int64_t M, int N, int K, int block_n, cudaStream_t st) {
+template <bool GELU, bool RES, typename TO>
+static int launch_tc(const void* x, const void* w, const float* bias, const void* residual, void* y, int64_t M, int N,
+                     int K, cudaStream_t st) {
+  constexpr int CW = Chunk<TO>::CW;
+  const int block_n = pick_block_n(N);
+  CUtensorMap mx, mw, my, mr;
+  int rc = make_tensor_map_2d(&mx, x, (uint64_t)M, (uint64_t)K, TC_BM, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&mw, w, (uint64_t)N, (uint64_t)K, (uint32_t)block_n, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&my, y, (uint64_t)M, (uint64_t)N, 32, CW, (int)sizeof(TO), CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&mr, RES ? residual : y, (uint64_t)M, (uint64_t)N, 32, CW, (int)sizeof(TO), CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)block_n * TC_BK * 2;
-  int stages = (int)((200 * 1024) / stage_bytes);
+  const size_t epi_bytes = (size_t)TC_EPI_WARPS * (RES ? 4 : 2) * TC_TILE_BYTES;
+  const size_t fixed = 1024 + epi_bytes + sizeof(TcSmemTail);
+  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   PSW_REQUIRE(stages >= 2, PSW_ERR_UNSUPPORTED, "psw_linear_fwd(bf16): tile too large for shared memory");
-  const size_t smem = 1024 + stages * stage_bytes + sizeof(TcSmemTail);
-  int pow2 = 32;
-  while (pow2 < block_n) pow2 <<= 1;
-  const int tmem_cols = 2 * pow2;                                      // double-buffered accumulator
+  const size_t smem = fixed + stages * stage_bytes;
   const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * ((N + block_n - 1) / block_n);
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  auto kern = linear_tc_kernel<GELU, TO>;
+  auto kern = linear_tc_kernel<GELU, RES, TO>;
   PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, TC_THREADS, smem, st>>>(mx, mw, bias, (const TO*)residual, (TO*)y, M, N, K, block_n, stages, tmem_cols);
+  kern<<<grid, TC_THREADS, smem, st>>>(mx, mw, my, mr, bias, M, N, K, block_n, stages);
   return launch_status("linear_tc_kernel");
 }
 
@@ -265,17 +352,18 @@ extern "C" PSW_API int psw_linear_fwd(const void* x, const void* w, const float*
   PSW_REQUIRE(M < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_linear_fwd(bf16): M too large");
   PSW_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(bias) && aligned16(residual), PSW_ERR_BAD_ARG,
               "psw_linear_fwd(bf16): pointers must be 16-byte aligned");
-  const int block_n = pick_block_n(N);
-  CUtensorMap mx, mw;
-  int rc = make_tensor_map_2d(&mx, x, (uint64_t)M, (uint64_t)K, TC_BM, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
-  rc = make_tensor_map_2d(&mw, w, (uint64_t)N, (uint64_t)K, (uint32_t)block_n, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
+  PSW_REQUIRE(out_dtype == PSW_BF16 || out_dtype == PSW_F32, PSW_ERR_BAD_ARG, "psw_linear_fwd: unknown out_dtype %d", out_dtype);
   const bool gelu = (flags & PSW_EPI_GELU) != 0;
-  if (out_dtype == PSW_BF16)
-    return gelu ? launch_tc<true, bf16>(mx, mw, bias, residual, y, M, N, K, block_n, st)
-                : launch_tc<false, bf16>(mx, mw, bias, residual, y, M, N, K, block_n, st);
-  PSW_REQUIRE(out_dtype == PSW_F32, PSW_ERR_BAD_ARG, "psw_linear_fwd: unknown out_dtype %d", out_dtype);
-  return gelu ? launch_tc<true, float>(mx, mw, bias, residual, y, M, N, K, block_n, st)
-              : launch_tc<false, float>(mx, mw, bias, residual, y, M, N, K, block_n, st);
+  const bool res = residual != nullptr;
+  const int sel = (gelu ? 4 : 0) | (res ? 2 : 0) | (out_dtype == PSW_F32 ? 1 : 0);
+  switch (sel) {
+    case 0: return launch_tc<false, false, bf16>(x, w, bias, residual, y, M, N, K, st);
+    case 1: return launch_tc<false, false, float>(x, w, bias, residual, y, M, N, K, st);
+    case 2: return launch_tc<false, true, bf16>(x, w, bias, residual, y, M, N, K, st);
+    case 3: return launch_tc<false, true, float>(x, w, bias, residual, y, M, N, K, st);
+    case 4: return launch_tc<true, false, bf16>(x, w, bias, residual, y, M, N, K, st);
+    case 5: return launch_tc<true, false, float>(x, w, bias, residual, y, M, N, K, st);
+    case 6: return launch_tc<true, true, bf16>(x, w, bias, residual, y, M, N, K, st);
+    default: return launch_tc<true, true, float>(x, w, bias, residual, y, M, N, K, st);
+  }
 }

@@ -119,27 +119,50 @@ def linear(x, w, bias=None, residual=None, gelu=False, out_dtype=None, out=None)
     return out
 
 
+def window_grid(H, W, window, pano_mode):
+    """(windows per column, windows per row) of the map the attention runs on (host-only helper)."""
+    import ctypes
+    nwh, nww = ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.load().psw_window_grid(H, W, window, 1 if pano_mode else 0, ctypes.byref(nwh), ctypes.byref(nww)),
+               "psw_window_grid")
+    return nwh.value, nww.value
+
+
+def window_hav_table(uv, window, shift):
+    """fp16 great-circle distance table [nW, window^2, 56] for one image geometry (pano mode, bf16 path).
+    uv [H, W, 2] fp32 (make_uv_hw2).  Depends on (H, W, window, shift) only: build once, reuse every forward."""
+    dev = _chk(uv)
+    H, W, _ = uv.shape
+    nwh, nww = window_grid(H, W, window, True)
+    table = torch.empty((nwh * nww, window * window, 56), dtype=torch.float16, device=uv.device)
+    with torch.cuda.device(dev):
+        _call("psw_window_hav_table", _ptr(_f32(uv, "uv")), _ptr(table), H, W, window, shift, _stream(dev))
+    return table
+
+
 def window_attention(qkv, alpha, beta, qkv_bias, uv, mask, heads, window, shift, pano_mode, scale, out=None,
-                     impl=None):
+                     impl=None, hav_table=None):
     """Fused shift + partition + W-MSA core + reverse + un-shift.  qkv [B, H, W, 3C] -> [B, H, W, C].
-    `impl`: None (product path), 'simt' (CUDA-core kernel on bf16), 'tc0' / 'tc1' (tcgen05 variants)."""
-    dev = _chk(qkv, alpha, beta, qkv_bias, uv, mask, out)
+    fp32 tensors: CUDA-core parity kernel (needs `uv` in pano mode).  bf16 tensors: tcgen05 kernel (needs
+    `hav_table` from window_hav_table() in pano mode; built on the fly from `uv` when omitted).
+    `impl='simt'`: the CUDA-core kernel on bf16 tensors (cross-check)."""
+    dev = _chk(qkv, alpha, beta, qkv_bias, uv, mask, out, hav_table)
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     if out is None:
         out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
-    args = [_ptr(qkv), _ptr(out), _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta")), _ptr(_f32(qkv_bias, "qkv_bias")),
-            _ptr(_f32(uv, "uv")), _ptr(_f32(mask, "mask")), B, H, W, C, heads, window, shift, 1 if pano_mode else 0,
-            float(scale)]
+    if pano_mode and qkv.dtype == torch.bfloat16 and impl is None and hav_table is None and uv is not None:
+        hav_table = window_hav_table(uv, window, shift)
+    head = [_ptr(qkv), _ptr(out), _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta")), _ptr(_f32(qkv_bias, "qkv_bias")),
+            _ptr(_f32(uv, "uv"))]
+    tail = [_ptr(_f32(mask, "mask")), B, H, W, C, heads, window, shift, 1 if pano_mode else 0, float(scale)]
     with torch.cuda.device(dev):
         if impl is None:
-            _call("psw_window_attn_fwd", *args, _dt(qkv), _stream(dev))
+            _call("psw_window_attn_fwd", *head, _ptr(hav_table), *tail, _dt(qkv), _stream(dev))
         elif impl == "simt":
             if qkv.dtype != torch.bfloat16:
                 raise PanoSwinB200Error("impl='simt' is the bf16 cross-check kernel")
-            _call("psw_window_attn_fwd_simt_bf16", *args, _stream(dev))
-        elif impl in ("tc0", "tc1"):
-            _call("psw_window_attn_fwd_tc_variant", *args, int(impl[-1]), _stream(dev))
+            _call("psw_window_attn_fwd_simt_bf16", *head, *tail, _stream(dev))
         else:
             raise PanoSwinB200Error(f"unknown impl {impl!r}")
     return out

@@ -65,4 +65,4 @@ if __name__ == "__main__":
     if what == "linear":
         linear()
     else:
-        attn({"attn0": "tc0", "attn1": "tc1", "attnsimt": "simt"}[what])
+        attn({"attn": None, "attnsimt": "simt"}[what])
