@@ -277,6 +277,7 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         for i_layer in out_indices:
             self.add_module(f"norm{i_layer}", norm_layer(self.num_features[i_layer]))
         self._compute_dtype = torch.bfloat16
+        self._fused_conv_relu = None
         self._const_cache: Dict[tuple, torch.Tensor] = {}
         self._weight_cache: Dict[tuple, tuple] = {}
         DoubleModeModule.__init__(self, pano_mode=pano_mode)
@@ -386,8 +387,20 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             self._weight_cache["stem_key"] = key
         (w1, b1), (w2, b2), (w3, b3) = self._weight_cache["stem"]
         y = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        y = F.relu_(F.conv2d(y, w1, b1, padding=1))
-        y = F.relu_(F.conv2d(y, w2, b2, padding=1))
+        if self._fused_conv_relu is None:                   # cuDNN's fused conv+bias+ReLU, probed once
+            try:
+                t = torch.cudnn_convolution_relu(y[:1, :, :8, :8].contiguous(memory_format=torch.channels_last), w1, b1,
+                                                 (1, 1), (1, 1), (1, 1), 1)
+                ref = F.relu(F.conv2d(y[:1, :, :8, :8], w1, b1, padding=1))
+                self._fused_conv_relu = bool(torch.allclose(t.float(), ref.float(), atol=2e-2, rtol=2e-2))
+            except (RuntimeError, AttributeError):
+                self._fused_conv_relu = False
+        if self._fused_conv_relu:
+            y = torch.cudnn_convolution_relu(y, w1, b1, (1, 1), (1, 1), (1, 1), 1)
+            y = torch.cudnn_convolution_relu(y, w2, b2, (1, 1), (1, 1), (1, 1), 1)
+        else:
+            y = F.relu_(F.conv2d(y, w1, b1, padding=1))
+            y = F.relu_(F.conv2d(y, w2, b2, padding=1))
         y = F.conv2d(y, w3, b3, stride=pe.patch_size)
         return y.permute(0, 2, 3, 1).contiguous()          # no copy when the conv output is channels-last
 

@@ -36,7 +36,8 @@ constexpr int AT_HAV_PITCH = 56;                   // halfs per distance-table r
 constexpr int AT_TMEM_COLS = 128;
 constexpr int AT_P_COL = 0;                        // P (bf16x2 packed): TMEM columns [0, 32)
 constexpr int AT_O_COL = 32;                       // O (fp32): TMEM columns [32, 96)
-constexpr int AT_CTAS_PER_SM = 4;
+constexpr int AT_CTAS_PER_SM = 3;
+constexpr int AT_TAB_PITCH = 23;                   // float2 entries per table row in smem (13 used)
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& r) {
@@ -117,24 +118,25 @@ struct Step {
   int wp;                 // window pair: windows 2*wp, 2*wp + 1
   int e;                  // head
   int el;                 // head index inside the item, 0 .. hc-1
-  int n;                  // running step count of this CTA (parity selects the table slot)
+  int n;                  // running step count of this CTA (parity selects the buffers)
 };
 
-template <int WS>
+template <int WS, bool HAS_MASK>
 __global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
 window_attn_tc_kernel(const AttnParams p) {
   constexpr int N = WS * WS;                     // tokens per window (<= 64)
-  constexpr int TW = 2 * WS - 1;                 // relative-position table width
+  constexpr int TW = 2 * WS - 1;                 // relative-position table width (13)
   constexpr int TAB = TW * TW;
-  constexpr int TABP = (TAB + 1) & ~1;           // padded to an even count
+  constexpr int TP = AT_TAB_PITCH;               // smem row pitch of the table: bank-conflict-free for row-per-lane reads
+  constexpr int TABS = TW * TP;                  // float2 entries per table slot
   static_assert(N <= 64, "window too large for the 64-row unit tile");
+  static_assert(TP >= TW, "table pitch too small");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* buf = smem;                                                   // [3][128 x 64 B]
-  __half* hav_s = reinterpret_cast<__half*>(buf + AT_BUF_BYTES);         // [2 units][N][56]
-  float2* tab = reinterpret_cast<float2*>(hav_s + 2 * N * AT_HAV_PITCH); // [2 slots][TABP] (alpha, beta) * log2(e)
-  int* src = reinterpret_cast<int*>(tab + 2 * TABP);                     // [2 slots][2 units][64]
+  uint8_t* bufs = smem;                                                  // [2 stages][3][128 x 64 B]
+  float2* tab = reinterpret_cast<float2*>(bufs + 2 * AT_BUF_BYTES);      // [2 stages][TABS] (alpha, beta)
+  int* src = reinterpret_cast<int*>(tab + 2 * TABS);                     // [2 slots][2 units][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(src + 2 * 2 * 64);        // [2]: S ready, O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   bf16* bias_bf = reinterpret_cast<bf16*>(tmem_slot + 4);                // [3C] (16 B aligned)
@@ -148,10 +150,8 @@ window_attn_tc_kernel(const AttnParams p) {
   const int n_hc = heads / p.hc;
 
   // ---------------------------------------------------------------- one-time setup
-  for (int i = tid; i < AT_BUF_BYTES / 16; i += AT_THREADS)
-    reinterpret_cast<uint4*>(buf)[i] = make_uint4(0, 0, 0, 0);           // padding rows must stay finite
-  for (int i = tid; i < 2 * N * AT_HAV_PITCH / 2; i += AT_THREADS)
-    reinterpret_cast<uint32_t*>(hav_s)[i] = 0u;                          // planar mode: d == 0
+  for (int i = tid; i < 2 * AT_BUF_BYTES / 16; i += AT_THREADS)
+    reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0, 0, 0, 0);          // padding rows must stay finite
   for (int i = tid; i < C3; i += AT_THREADS) bias_bf[i] = __float2bfloat16_rn(p.qkv_bias ? p.qkv_bias[i] : 0.f);
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -176,6 +176,9 @@ window_attn_tc_kernel(const AttnParams p) {
   const int ti = tid & 63;
   const int ic = ti < N ? ti : 0;
   const int ri = ic / WS, ci = ic - ri * WS;
+  // loader role of this thread: 16-byte chunk c of tokens lt0 and lt0 + 32
+  const int lc = tid & 3;
+  const int lt0 = tid >> 2;
 
   auto first_step = [&](int item) {
     Step s;
@@ -194,92 +197,93 @@ window_attn_tc_kernel(const AttnParams p) {
     if (s.e + 1 < heads) { ++s.e; } else { s.e = 0; ++s.wp; }
     return s;
   };
-  // token maps of both windows of pair `wp` -> src[slot] (thread = (unit, token))
+  // token maps of both windows of pair `wp` -> src[slot] (thread = (unit, token)); entry = element offset of the
+  // token's qkv row inside the whole qkv tensor divided by 8 (16-byte units), or -1 for a padding cell
   auto prep_src = [&](int wp) {
     const int w = 2 * wp + unit;
     int s = -1;
     if (ti < N && w < p.n_windows) {
-      const int wi = w % wpi;
+      const int b = w / wpi;
+      const int wi = w - b * wpi;
       const int wr = wi / g.nWw, wc = wi - wr * g.nWw;
-      s = source_token(g, wr * WS + ri, wc * WS + ci);
+      const int t = source_token(g, wr * WS + ri, wc * WS + ci);
+      if (t >= 0) s = b * (int)HW + t;                     // global token index (< 2^31, checked by the host)
     }
     src[(wp & 1) * 128 + tid] = s;
   };
-  // gather rows of `parts` (bit 0: Q, bit 1: K, bit 2: V) of step `st`; also its per-head tables with Q/K
-  auto issue_loads = [&](const Step& st, int parts) {
-    const int c = tid & 3;
+  // gather all q/k/v rows and the per-head tables of step `st` into stage (st.n & 1)
+  auto issue_loads = [&](const Step& st) {
+    uint8_t* base = bufs + (st.n & 1) * AT_BUF_BYTES;
+    const int* smap = src + (st.wp & 1) * 128;
+    const bf16* gq = p.qkv + st.e * 32 + lc * 8;
+    const bf16* bq = bias_bf + st.e * 32 + lc * 8;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int w = 2 * st.wp + u;
-      if (w >= p.n_windows) continue;
-      const int b = w / wpi;
-      const bf16* base = p.qkv + ((int64_t)b * HW) * C3 + st.e * 32 + c * 8;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int t = (tid >> 2) + 32 * k;
-        if (t >= N) continue;
-        const int s = src[(st.wp & 1) * 128 + u * 64 + t];
-        const int row = u * 64 + t;
-        uint8_t* dst = buf + row * 64 + ((c ^ ((row >> 1) & 3)) << 4);
-        const bf16* g_row = base + (int64_t)s * C3;
-        const bf16* b_row = bias_bf + st.e * 32 + c * 8;
-#pragma unroll
-        for (int part = 0; part < 3; ++part) {
-          if (!(parts & (1 << part))) continue;
-          if (s >= 0) cp_async16(dst + part * AT_PART_BYTES, g_row + part * C);
-          else *reinterpret_cast<uint4*>(dst + part * AT_PART_BYTES) = *reinterpret_cast<const uint4*>(b_row + part * C);
+    for (int k = 0; k < 4; ++k) {                          // rows lt0, lt0+32 of unit 0, then of unit 1
+      const int t = lt0 + 32 * (k & 1);
+      const int row = (k >> 1) * 64 + t;
+      if (t < N) {
+        const int s = smap[row];
+        uint8_t* dst = base + row * 64 + ((lc ^ ((row >> 1) & 3)) << 4);
+        if (s >= 0) {
+          const bf16* grow = gq + (int64_t)s * C3;
+          cp_async16(dst, grow);
+          cp_async16(dst + AT_PART_BYTES, grow + C);
+          cp_async16(dst + 2 * AT_PART_BYTES, grow + 2 * C);
+        } else if (2 * st.wp + (k >> 1) < p.n_windows) {   // padding cell of a real window: q/k/v = bias
+          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(bq);
+          *reinterpret_cast<uint4*>(dst + AT_PART_BYTES) = *reinterpret_cast<const uint4*>(bq + C);
+          *reinterpret_cast<uint4*>(dst + 2 * AT_PART_BYTES) = *reinterpret_cast<const uint4*>(bq + 2 * C);
         }
       }
     }
-    if (parts & 1) {
-      float* trow = reinterpret_cast<float*>(tab + (st.n & 1) * TABP);
-      for (int k = tid; k < TAB; k += AT_THREADS) {
-        cp_async4(trow + 2 * k, p.alpha + k * heads + st.e);
-        cp_async4(trow + 2 * k + 1, p.beta + k * heads + st.e);
-      }
+    float* trow = reinterpret_cast<float*>(tab + (st.n & 1) * TABS);
+    for (int k = tid; k < TAB; k += AT_THREADS) {
+      const int o = 2 * ((k / TW) * TP + (k % TW));
+      cp_async4(trow + o, p.alpha + k * heads + st.e);
+      cp_async4(trow + o + 1, p.beta + k * heads + st.e);
     }
-  };
-  // my own distance-table row of pair `wp` (no other thread reads it: no barrier needed, only my wait_group)
-  auto issue_hav = [&](int wp) {
-    const int w = 2 * wp + unit;
-    if (p.hav == nullptr || ti >= N || w >= p.n_windows) return;
-    const __half* grow = p.hav + ((size_t)(w % wpi) * N + ti) * AT_HAV_PITCH;
-    __half* srow = hav_s + (unit * N + ti) * AT_HAV_PITCH;
-#pragma unroll
-    for (int k = 0; k < AT_HAV_PITCH / 8; ++k) cp_async16(srow + 8 * k, grow + 8 * k);
   };
 
   Step cur = first_step(item_begin);
   if (item_begin < item_end) {
     prep_src(cur.wp);
     __syncthreads();
-    issue_loads(cur, 3);
+    issue_loads(cur);
   }
-  cp_async_commit();                                       // group A: Q, K, tables
-  if (item_begin < item_end) issue_loads(cur, 4);
-  cp_async_commit();                                       // group B: V
-  if (item_begin < item_end) issue_hav(cur.wp);
-  cp_async_commit();                                       // group C: distance rows
+  cp_async_commit();
+
+  uint4 hreg[AT_HAV_PITCH / 8];                            // my distance-table row (fp16), kept across the item's heads
+#pragma unroll
+  for (int k = 0; k < AT_HAV_PITCH / 8; ++k) hreg[k] = make_uint4(0, 0, 0, 0);
+  int hav_wp = -1;
 
   uint32_t par = 0;
   while (cur.item < item_end) {
     const Step nxt = next_step(cur);
     const bool has_next = nxt.item < item_end;
-    // ---- 0. token maps of the next window pair (other slot)
-    __syncthreads();         // everyone is done with the previous step's token maps / tables / TMEM rows
+    const int my_w = 2 * cur.wp + unit;
+    const bool row_valid = (ti < N) && (my_w < p.n_windows);
+    // ---- 0. token maps of the next window pair (other slot); my distance row of this pair
+    __syncthreads();         // everyone is done with the previous step's buffers / token maps / TMEM rows
     if (has_next && nxt.wp != cur.wp) prep_src(nxt.wp);
-
-    // ---- 1. Q, K and the tables of this step have landed (groups B, C may still be in flight)
-    cp_async_wait<2>();
-    {
-      float2* t2 = tab + (cur.n & 1) * TABP;              // scale my own entries (the ones I copied) by log2(e)
-      for (int k = tid; k < TAB; k += AT_THREADS) t2[k] = make_float2(t2[k].x * LOG2E, t2[k].y * LOG2E);
+    if (p.hav != nullptr && hav_wp != cur.wp) {
+      hav_wp = cur.wp;
+      if (row_valid) {
+        const uint4* grow = reinterpret_cast<const uint4*>(p.hav + ((size_t)(my_w % wpi) * N + ti) * AT_HAV_PITCH);
+#pragma unroll
+        for (int k = 0; k < AT_HAV_PITCH / 8; ++k) hreg[k] = __ldg(grow + k);
+      }
     }
+    __syncthreads();         // next pair's token maps are visible
+    // ---- 1. prefetch the WHOLE next step into the other stage, then wait for this step's data
+    if (has_next) issue_loads(nxt);
+    cp_async_commit();
+    cp_async_wait<1>();
     fence_async_shared();
     __syncthreads();
 
     // ---- 2. S = Q . K^T (both units at once, block diagonal)
-    const uint32_t sq = smem_u32(buf);
+    const uint32_t sq = smem_u32(bufs + (cur.n & 1) * AT_BUF_BYTES);
     if (tid == 0) {
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
@@ -292,15 +296,7 @@ window_attn_tc_kernel(const AttnParams p) {
     mbar_wait(&bars[0], par);
     tc_fence_after();
 
-    // ---- 3. Q/K buffers are free: prefetch the next step's Q, K, tables
-    if (has_next) issue_loads(nxt, 3);
-    cp_async_commit();                                     // group A'
-
-    // ---- 4. bias + softmax on my row (needs groups B, C of this step: everything but A')
-    cp_async_wait<1>();
-    fence_async_shared();                                  // my V rows -> visible to the PV MMA after the barrier
-    const int my_w = 2 * cur.wp + unit;
-    const bool row_valid = (ti < N) && (my_w < p.n_windows);
+    // ---- 3. bias + softmax on my row
     float sum = 1.f;
     {
       uint32_t sr[N];
@@ -328,37 +324,36 @@ window_attn_tc_kernel(const AttnParams p) {
           sr[k] = t1;
         }
       }
-      const uint4* h8 = reinterpret_cast<const uint4*>(hav_s + (unit * N + ic) * AT_HAV_PITCH);   // 8 halfs per load
-      const float2* trow = tab + (cur.n & 1) * TABP + (ri + WS - 1) * TW + (ci + WS - 1);
-      const float* mrow = p.mask ? p.mask + ((int64_t)((my_w < p.n_windows ? my_w : 0) % wpi) * N + ic) * N : nullptr;
-      const float sc = p.scale * LOG2E;
+      const float2* trow = tab + (cur.n & 1) * TABS + (ri + WS - 1) * TP + (ci + WS - 1);
+      const float* mrow = nullptr;
+      if constexpr (HAS_MASK) mrow = p.mask + ((int64_t)((my_w < p.n_windows ? my_w : 0) % wpi) * N + ic) * N;
       float t[N];
       float mx = -INFINITY;
 #pragma unroll
       for (int jc = 0; jc < (N + 7) / 8; ++jc) {
-        const uint4 hq = h8[jc];
-        const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+        const uint32_t hw[4] = {hreg[jc].x, hreg[jc].y, hreg[jc].z, hreg[jc].w};
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int j = 8 * jc + q;
           if (j < N) {
             const __half2 hh = *reinterpret_cast<const __half2*>(&hw[q >> 1]);
             const float hv = (q & 1) ? __high2float(hh) : __low2float(hh);
-            const float2 ab = trow[-((j / WS) * TW + (j % WS))];
+            const float2 ab = trow[-((j / WS) * TP + (j % WS))];
             float bia = fmaf(hv, ab.x, ab.y);
-            if (mrow) bia = fmaf(__ldg(mrow + j), LOG2E, bia);
-            t[j] = fmaf(__uint_as_float(sr[j]), sc, bia);
+            if constexpr (HAS_MASK) bia += __ldg(mrow + j);
+            t[j] = fmaf(__uint_as_float(sr[j]), p.scale, bia);
             mx = fmaxf(mx, t[j]);
           }
         }
       }
+      const float mneg = -mx * LOG2E;
       sum = 0.f;
       uint32_t pk[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
         float p0 = 0.f, p1 = 0.f;
-        if (2 * k < N) { p0 = fast_exp2(t[2 * k] - mx); sum += p0; }
-        if (2 * k + 1 < N) { p1 = fast_exp2(t[2 * k + 1] - mx); sum += p1; }
+        if (2 * k < N) { p0 = fast_exp2(fmaf(t[2 * k], LOG2E, mneg)); sum += p0; }
+        if (2 * k + 1 < N) { p1 = fast_exp2(fmaf(t[2 * k + 1], LOG2E, mneg)); sum += p1; }
         pk[k] = row_valid ? pack_bf16x2(p0, p1) : 0u;
       }
       tmem_st_x32(tmem_base + lane_base + AT_P_COL, pk);
@@ -367,7 +362,7 @@ window_attn_tc_kernel(const AttnParams p) {
     tc_fence_before();
     __syncthreads();
 
-    // ---- 5. O = P . [V_u0 | V_u1]
+    // ---- 4. O = P . [V_u0 | V_u1]
     if (tid == 0) {
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);     // B (V) is MN-major: [key][dim] rows
@@ -382,13 +377,7 @@ window_attn_tc_kernel(const AttnParams p) {
     mbar_wait(&bars[1], par);
     tc_fence_after();
 
-    // ---- 6. V buffer and (at the end of an item) the distance rows are free: prefetch
-    if (has_next) issue_loads(nxt, 4);
-    cp_async_commit();                                     // group B'
-    if (has_next && nxt.wp != cur.wp) issue_hav(nxt.wp);
-    cp_async_commit();                                     // group C'
-
-    // ---- 7. normalise and store my output row at the token's un-shifted position
+    // ---- 5. normalise and store my output row at the token's un-shifted position
     {
       uint32_t orow[32];
       tmem_ld_x32(tmem_base + lane_base + AT_O_COL + (uint32_t)(unit * 32), orow);
@@ -396,8 +385,7 @@ window_attn_tc_kernel(const AttnParams p) {
       const int s = src[(cur.wp & 1) * 128 + unit * 64 + ic];
       if (row_valid && s >= 0) {
         const float inv = 1.0f / sum;
-        const int b = my_w / wpi;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)b * HW + s) * C + cur.e * 32);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (int64_t)s * C + cur.e * 32);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 v;
@@ -424,16 +412,15 @@ window_attn_tc_kernel(const AttnParams p) {
 }
 
 static size_t attn_tc_smem_bytes(int ws, int C) {
-  const int N = ws * ws, TAB = (2 * ws - 1) * (2 * ws - 1), TABP = (TAB + 1) & ~1;
+  const int TW = 2 * ws - 1;
   size_t b = 1024;                                   // alignment slack
-  b += AT_BUF_BYTES;
-  b += (size_t)2 * N * AT_HAV_PITCH * 2;
-  b += (size_t)2 * TABP * 8;
+  b += 2 * AT_BUF_BYTES;
+  b += (size_t)2 * TW * AT_TAB_PITCH * 8;
   b += 2 * 2 * 64 * 4;
   b += 2 * 8 + 16;
   b += (size_t)3 * C * 2;
-  // at least 46 KiB so that no more than 4 CTAs (4 x 128 TMEM columns) ever share an SM
-  return b < 46 * 1024 ? 46 * 1024 : b;
+  // at least 58 KiB so that no more than 3 CTAs ever share an SM (register budget: 170 per thread)
+  return b < 58 * 1024 ? 58 * 1024 : b;
 }
 
 int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const float* qkv_bias,
@@ -455,8 +442,10 @@ int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* 
   p.n_items = ((p.n_windows + 1) / 2) * (heads / p.hc);
   const size_t smem = attn_tc_smem_bytes(window, C);
   PSW_REQUIRE(smem <= 220 * 1024, PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd(bf16): C=%d too large", C);
-  auto kern = window_attn_tc_kernel<7>;
+  PSW_REQUIRE((int64_t)B * H * W < (1ll << 31) / 1, PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd(bf16): too many tokens");
+  auto kern = mask ? window_attn_tc_kernel<7, true> : window_attn_tc_kernel<7, false>;
   PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int grid = num_sms() * AT_CTAS_PER_SM;
   if (grid > p.n_items) grid = p.n_items;
   kern<<<grid, AT_THREADS, smem, st>>>(p);

@@ -1,11 +1,11 @@
 // K2 (throughput path): y = act(x . w^T + bias) (+ residual) with bf16 operands on the 5th-generation
 // tensor cores (tcgen05.mma, fp32 accumulators in TMEM), every global access a TMA transfer.
 //
-// Persistent, warp-specialised CTA (one per SM, 320 threads):
+// Persistent, warp-specialised CTA (one per SM, 320 or 448 threads):
 //   warp 0      TMA producer : [128 x 64] x-tile and [BLOCK_N x 64] w-tile per stage, SWIZZLE_128B, mbarrier ring
 //   warp 1      MMA issuer   : one thread issues 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) per stage; commits free
 //                              the smem slot and, per tile, publish the accumulator
-//   warps 2..9  epilogue     : two warps per TMEM lane quadrant, alternating 64-byte-wide column chunks:
+//   warps 2..   epilogue     : 8 or 12 warps, two or three per TMEM lane quadrant, interleaving 64-byte-wide chunks:
 //                              tcgen05.ld 32 rows x CW columns -> +bias -> [GELU] -> [+residual] -> swizzled smem
 //                              tile -> TMA store (coalesced, clipped at M / N).  Residual tiles are TMA-loaded two
 //                              chunks ahead into a per-warp ring, so no thread ever issues a strided global access.
@@ -23,8 +23,7 @@ namespace psw {
 constexpr int TC_BM = 128;         // UMMA M
 constexpr int TC_BK = 64;          // one 128-byte swizzle row of bf16
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_MAX_EPI_WARPS = 12;
 constexpr int TC_TILE_BYTES = 32 * 64;      // epilogue staging tile: 32 rows x 64 B, SWIZZLE_64B
 
 struct TcSmemTail {
@@ -32,7 +31,7 @@ struct TcSmemTail {
   uint64_t empty[TC_MAX_STAGES];
   uint64_t tfull[2];
   uint64_t tempty[2];
-  uint64_t res_bar[TC_EPI_WARPS][2];
+  uint64_t res_bar[TC_MAX_EPI_WARPS][2];
   uint32_t tmem_base;
 };
 
@@ -44,11 +43,10 @@ __device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float xc = fminf(fmaxf(x, -9.0f), 9.0f);
-  const float x2 = xc * xc;
+  const float x2 = fminf(x * x, 64.0f);           // the fitted polynomial is used on |x| <= 8; beyond, tanh saturates
   const float p = fmaf(fmaf(-3.20974528e-04f, x2, 3.68320430e-02f), x2, 7.97686932e-01f);
   float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xc * p));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
@@ -57,12 +55,17 @@ template <typename TO> struct Chunk;             // CW output columns = one 64-b
 template <> struct Chunk<float> { static constexpr int CW = 16; };
 template <> struct Chunk<bf16> { static constexpr int CW = 32; };
 
+// EW epilogue warps: 12 (three per TMEM lane quadrant) when there is no residual ring to stage, else 8
+template <bool RES> struct EpiCfg { static constexpr int EW = RES ? 8 : 12; static constexpr int THREADS = 64 + 32 * EW; };
+
 template <bool GELU, bool RES, typename TO>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(EpiCfg<RES>::THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r,
                  const float* __restrict__ bias, int64_t M, int N, int K, int block_n, int stages) {
   constexpr int CW = Chunk<TO>::CW;
+  constexpr int TC_EPI_WARPS = EpiCfg<RES>::EW;
+  constexpr int PER_QUAD = TC_EPI_WARPS / 4;                  // warps sharing one TMEM lane quadrant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = TC_BM * TC_BK * 2;                 // 16 KiB
@@ -155,7 +158,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // ------------------------------- epilogue (8 warps) --------------------------
     const int ew = warp - 2;
     const int quad = warp & 3;                                // TMEM lane quadrant this warp may access
-    const int half = ew >> 2;                                 // the two warps of a quadrant alternate chunks
+    const int part = ew >> 2;                                 // the PER_QUAD warps of a quadrant interleave chunks
     uint8_t* my_smem = epi_smem + ew * EPI_PER_WARP;
     uint8_t* out_buf[2] = {my_smem, my_smem + TC_TILE_BYTES};
     uint8_t* res_buf[2] = {my_smem + 2 * TC_TILE_BYTES, my_smem + 3 * TC_TILE_BYTES};
@@ -174,15 +177,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       const int n_t = (int)(tile - m_t * n_tiles);
       const int row0 = (int)(m_t * TC_BM) + quad * 32;
       const int col0 = n_t * block_n;
-      // chunks of this warp in this tile: c = first, first + 2, ... (first alternates with the tile parity so an
-      // odd chunk count still balances the two warps of a quadrant)
-      const int first = (half + (int)(tile_iter & 1u) * (n_chunks & 1)) & 1;
+      // chunks of this warp in this tile: c = first, first + PER_QUAD, ... (first rotates with the tile count so a
+      // chunk count that is not a multiple of PER_QUAD still balances the warps of a quadrant)
+      const int first = (part + (int)(tile_iter % PER_QUAD) * (n_chunks % PER_QUAD)) % PER_QUAD;
       if (RES) {
         // prefetch the first two residual chunks of this tile before waiting for the accumulator
         if (lane == 0) {
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const int c = first + 2 * j;
+            const int c = first + PER_QUAD * j;
             if (c < n_chunks) {
               const uint32_t b = res_issued & 1;
               mbar_expect_tx(&res_bar[b], TC_TILE_BYTES);
@@ -195,7 +198,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       mbar_wait(&tail->tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * acc_stride;
-      for (int c = first; c < n_chunks; c += 2) {
+      for (int c = first; c < n_chunks; c += PER_QUAD) {
         float v[CW];
         if constexpr (CW == 32) {
           uint32_t r[32];
@@ -245,10 +248,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           }
           ++res_used;
           __syncwarp();                                       // every lane has read the tile: the slot is free
-          if (lane == 0 && c + 4 < n_chunks) {                // keep the ring two chunks ahead
+          if (lane == 0 && c + 2 * PER_QUAD < n_chunks) {     // keep the ring two chunks ahead
             const uint32_t nb = res_issued & 1;
             mbar_expect_tx(&res_bar[nb], TC_TILE_BYTES);
-            tma_load_2d(res_buf[nb], &map_r, &res_bar[nb], col0 + (c + 4) * CW, row0);
+            tma_load_2d(res_buf[nb], &map_r, &res_bar[nb], col0 + (c + 2 * PER_QUAD) * CW, row0);
             ++res_issued;
           }
         }
@@ -317,7 +320,7 @@ static int launch_tc(const void* x, const void* w, const float* bias, const void
   rc = make_tensor_map_2d(&mr, RES ? residual : y, (uint64_t)M, (uint64_t)N, 32, CW, (int)sizeof(TO), CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)block_n * TC_BK * 2;
-  const size_t epi_bytes = (size_t)TC_EPI_WARPS * (RES ? 4 : 2) * TC_TILE_BYTES;
+  const size_t epi_bytes = (size_t)EpiCfg<RES>::EW * (RES ? 4 : 2) * TC_TILE_BYTES;
   const size_t fixed = 1024 + epi_bytes + sizeof(TcSmemTail);
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -327,7 +330,7 @@ static int launch_tc(const void* x, const void* w, const float* bias, const void
   int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   auto kern = linear_tc_kernel<GELU, RES, TO>;
   PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, TC_THREADS, smem, st>>>(mx, mw, my, mr, bias, M, N, K, block_n, stages);
+  kern<<<grid, EpiCfg<RES>::THREADS, smem, st>>>(mx, mw, my, mr, bias, M, N, K, block_n, stages);
   return launch_status("linear_tc_kernel");
 }
 

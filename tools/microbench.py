@@ -1,0 +1,86 @@
+"""Micro-benchmarks of single ops at the bench shapes (CUDA events, L2 flushed between iterations by cycling
+through enough distinct buffers).  usage: python tools/microbench.py {attn|linear|ln|all} [iters]"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from panoswintransformerobjectdetection_b200 import ops  # noqa: E402
+from panoswintransformerobjectdetection_b200.backbone import make_uv_hw2  # noqa: E402
+
+DEV = "cuda:0"
+B = int(os.environ.get("MB_BATCH", "32"))
+
+
+def time_op(fn, n_bufs, iters):
+    for i in range(3):
+        fn(i % n_bufs)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i % n_bufs)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3      # us
+
+
+def attn(iters):
+    for (H, W, C, heads) in [(128, 256, 96, 3), (64, 128, 192, 6), (32, 64, 384, 12), (16, 32, 768, 24)]:
+        nb = max(2, int(400e6 // (B * H * W * 4 * C * 2)) + 1)
+        qkv = [torch.randn(B, H, W, 3 * C, device=DEV).bfloat16() for _ in range(nb)]
+        out = [torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
+        alpha = torch.randn(169, heads, device=DEV) * 0.1
+        beta = torch.randn(169, heads, device=DEV) * 0.1
+        qb = torch.randn(3 * C, device=DEV) * 0.1
+        uv = make_uv_hw2(H, W).to(DEV)
+        for shift in (0, 3):
+            hav = ops.window_hav_table(uv, 7, shift)
+            us = time_op(lambda i: ops.window_attention(qkv[i], alpha, beta, qb, uv, None, heads, 7, shift, True, 32 ** -0.5,
+                                                        out=out[i], hav_table=hav), nb, iters)
+            byt = B * H * W * C * 8
+            print(f"attn B{B} {H}x{W} C{C} h{heads} s{shift}: {us:8.1f} us  {byt / us / 1e3:7.0f} GB/s", flush=True)
+
+
+def linear(iters):
+    shapes = [(32768, 288, 96, 0, 0, "bf16"), (32768, 96, 96, 0, 1, "f32"), (32768, 384, 96, 1, 0, "bf16"), (32768, 96, 384, 0, 1, "f32"),
+              (8192, 576, 192, 0, 0, "bf16"), (8192, 768, 192, 1, 0, "bf16"), (8192, 192, 768, 0, 1, "f32"),
+              (2048, 1152, 384, 0, 0, "bf16"), (2048, 1536, 384, 1, 0, "bf16"), (2048, 384, 1536, 0, 1, "f32"),
+              (512, 2304, 768, 0, 0, "bf16"), (512, 3072, 768, 1, 0, "bf16"), (512, 768, 3072, 0, 1, "f32")]
+    for (tok, N, K, gelu, res, odt) in shapes:
+        M = tok * B
+        od = torch.bfloat16 if odt == "bf16" else torch.float32
+        nb = max(2, int(400e6 // (M * (K * 2 + N * od.itemsize))) + 1)
+        x = [torch.randn(M, K, device=DEV).bfloat16() for _ in range(nb)]
+        y = [torch.randn(M, N, device=DEV).to(od) for _ in range(nb)]
+        w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+        b = torch.randn(N, device=DEV)
+        us = time_op(lambda i: ops.linear(x[i], w, b, residual=y[i] if res else None, gelu=bool(gelu), out=y[i], out_dtype=od),
+                     nb, iters)
+        byt = M * K * 2 + N * K * 2 + M * N * od.itemsize * (2 if res else 1)
+        fl = 2.0 * M * N * K
+        print(f"linear M{M} N{N} K{K} gelu{gelu} res{res} {odt}: {us:8.1f} us  {byt / us / 1e3:7.0f} GB/s  {fl / us / 1e6:7.1f} TF/s", flush=True)
+
+
+def ln(iters):
+    for (tok, C) in [(32768, 96), (8192, 192), (2048, 384), (512, 768)]:
+        rows = tok * B
+        nb = max(2, int(400e6 // (rows * C * 6)) + 1)
+        x = [torch.randn(rows, C, device=DEV) for _ in range(nb)]
+        y = [torch.empty(rows, C, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
+        g, bb = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+        us = time_op(lambda i: ops.layernorm(x[i], g, bb, 1e-5, torch.bfloat16, out=y[i]), nb, iters)
+        print(f"layernorm rows{rows} C{C}: {us:8.1f} us  {rows * C * 6 / us / 1e3:7.0f} GB/s", flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    if what in ("attn", "all"):
+        attn(iters)
+    if what in ("linear", "all"):
+        linear(iters)
+    if what in ("ln", "all"):
+        ln(iters)
