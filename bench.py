@@ -348,7 +348,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
-    ap.add_argument("--chunk", type=int, default=8, help="images per pipelined chunk on the end-to-end path")
+    ap.add_argument("--chunk", type=int, default=4, help="images per pipelined chunk on the end-to-end path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", default=None, help="write the per-shape kernel table to this JSON file")
     args = ap.parse_args()

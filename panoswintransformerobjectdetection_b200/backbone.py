@@ -277,6 +277,7 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         for i_layer in out_indices:
             self.add_module(f"norm{i_layer}", norm_layer(self.num_features[i_layer]))
         self._compute_dtype = torch.bfloat16
+        self._residual_dtype = torch.float32
         self._fused_conv_relu = None
         self._const_cache: Dict[tuple, torch.Tensor] = {}
         self._weight_cache: Dict[tuple, tuple] = {}
@@ -323,6 +324,15 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
     @property
     def compute_dtype(self):
         return self._compute_dtype
+
+    def set_residual_dtype(self, dtype):
+        """Storage type of the residual stream in bf16 mode: 'fp32' (default, what the reference keeps under
+        autocast) or 'bf16' (halves the residual traffic; measured accuracy in profiles/)."""
+        table = {"bf16": torch.bfloat16, "fp32": torch.float32}
+        if dtype not in table:
+            raise ValueError("residual dtype must be 'bf16' or 'fp32'")
+        self._residual_dtype = table[dtype]
+        return self
 
     # ---- cached constants / converted weights -------------------------------------------------
     def _const(self, key, builder, device):
@@ -426,6 +436,18 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         if self.pano_mode and x_bchw.shape[3] != x_bchw.shape[2] * 2:
             warnings.warn("PanoSwin is configured in Pano mode, expecting channel3 == 2 * channel2, but get {} and {}, "
                           "probably cause an error".format(x_bchw.shape[3], x_bchw.shape[2]))
+        self._check_forward(x_bchw)
+        with torch.no_grad():
+            return self._forward_tokens(x_bchw.float())
+
+    def forward_streamed(self, x_bchw, on_output):
+        """forward() that additionally calls `on_output(k, feature_map)` as soon as the k-th output map has been
+        enqueued, so a caller can start consuming (e.g. copying out) early stages while later ones still run."""
+        self._check_forward(x_bchw)
+        with torch.no_grad():
+            return self._forward_tokens(x_bchw.float(), on_output)
+
+    def _check_forward(self, x_bchw):
         if not x_bchw.is_cuda:
             raise ops.PanoSwinB200Error("SimplePanoSwinTransformer (B200) needs a CUDA input; there is no CPU fallback")
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
@@ -434,11 +456,10 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         if self.pano_mode and not self.ape:
             raise AttributeError("pano_mode=True requires ape=True: the reference builds abs_encoder only when ape is set "
                                  "(simple_panoswin_transformer.py:841-842) and always calls it in pano mode (:934)")
-        with torch.no_grad():
-            return self._forward_tokens(x_bchw.float())
 
-    def _forward_tokens(self, img: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+    def _forward_tokens(self, img: torch.Tensor, on_output=None) -> Tuple[torch.Tensor, ...]:
         cd = self._compute_dtype
+        rd = torch.float32 if cd == torch.float32 else self._residual_dtype      # residual-stream storage
         dev = img.device
         ws = self.window_size
         tok = self._stem(img)                                     # [B, Hs, Ws, E] in the compute dtype
@@ -446,11 +467,12 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         pos = self._abs_position(Hs, Ws, dev) if (self.pano_mode and self.ape) else None
         if self.patch_embed.norm is not None:
             n = self.patch_embed.norm
-            x = ops.layernorm(tok.view(B, Hs * Ws, E), self._f(n.weight), self._f(n.bias), n.eps, torch.float32, pos)
+            x = ops.layernorm(tok.view(B, Hs * Ws, E), self._f(n.weight), self._f(n.bias), n.eps, rd, pos)
         else:
             x = tok.view(B, Hs * Ws, E).float()
             if pos is not None:
                 x = x + pos[None]
+            x = x.to(rd).contiguous()
         H, W = Hs, Ws
         outs = []
         for i, layer in enumerate(self.layers):
@@ -477,10 +499,12 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             if i in self.out_indices:
                 n = getattr(self, f"norm{i}")
                 outs.append(ops.layernorm_nchw(x, self._f(n.weight), self._f(n.bias), H, W, n.eps))
+                if on_output is not None:
+                    on_output(len(outs) - 1, outs[-1])
             if layer.downsample is not None:
                 d = layer.downsample
                 xm = ops.patch_merge_layernorm(x, self._f(d.norm.weight), self._f(d.norm.bias), H, W, d.norm.eps, cd)
-                x = ops.linear(xm, self._w(d.reduction.weight, cd), None, out_dtype=torch.float32)
+                x = ops.linear(xm, self._w(d.reduction.weight, cd), None, out_dtype=rd)
                 H, W = (H + 1) // 2, (W + 1) // 2
         return tuple(outs)
 

@@ -39,59 +39,83 @@ struct MergeRows {
   }
 };
 
-template <int VPL, typename TI, typename TO, typename Rows>
+template <int VPL, int R, typename TI, typename TO, typename Rows>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_rows_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ pos, int64_t pos_rows,
                       Rows rows, int Cout, float eps) {
+  // R rows per warp iteration: all loads of the R rows are issued before any reduction, so a warp keeps
+  // R * VPL 16-byte (fp32) / 8-byte (bf16) requests in flight instead of VPL.
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nvec = Cout >> 2;
   const int64_t nrows = rows.num_rows();
   const float inv_c = 1.0f / (float)Cout;
-  for (int64_t r = (int64_t)blockIdx.x * LN_WARPS + warp; r < nrows; r += (int64_t)gridDim.x * LN_WARPS) {
-    float v[VPL][4];
-    float s = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * LN_WARPS * R;
+  for (int64_t r0 = ((int64_t)blockIdx.x * LN_WARPS + warp) * R; r0 < nrows; r0 += stride) {
+    float v[R][VPL][4];
+    float s[R];
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      int vec = lane + 32 * k;
-      v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
-      if (vec < nvec) {
-        int64_t off = rows.offset(r, vec);
-        if (off >= 0) load4(x + off, v[k]);
-      }
-      s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
-    }
-    const float mean = warp_sum(s) * inv_c;
-    float q = 0.f;
+    for (int j = 0; j < R; ++j) {
+      s[j] = 0.f;
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      if (lane + 32 * k < nvec) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float d = v[k][e] - mean;
-          q += d * d;
+      for (int k = 0; k < VPL; ++k) {
+        const int vec = lane + 32 * k;
+        v[j][k][0] = v[j][k][1] = v[j][k][2] = v[j][k][3] = 0.f;
+        if (vec < nvec && r0 + j < nrows) {
+          const int64_t off = rows.offset(r0 + j, vec);
+          if (off >= 0) load4(x + off, v[j][k]);
         }
       }
     }
-    const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
-    const float* prow = pos ? pos + (r % pos_rows) * Cout : nullptr;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) s[j] += (v[j][k][0] + v[j][k][1]) + (v[j][k][2] + v[j][k][3]);
+    }
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) mean[j] = warp_sum(s[j]) * inv_c;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        if (lane + 32 * k < nvec) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float d = v[j][k][e] - mean[j];
+            q += d * d;
+          }
+        }
+      }
+      s[j] = q;
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) rstd[j] = rsqrtf(warp_sum(s[j]) * inv_c + eps);
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      int vec = lane + 32 * k;
+      const int vec = lane + 32 * k;
       if (vec < nvec) {
-        float g[4], b[4], o[4];
+        float g[4], b[4];
         load4(gamma + vec * 4, g);
         load4(beta + vec * 4, b);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = (v[k][e] - mean) * rstd * g[e] + b[e];
-        if (prow) {
-          float pp[4];
-          load4(prow + vec * 4, pp);
+        for (int j = 0; j < R; ++j) {
+          const int64_t r = r0 + j;
+          if (r < nrows) {
+            float o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] += pp[e];
+            for (int e = 0; e < 4; ++e) o[e] = (v[j][k][e] - mean[j]) * rstd[j] * g[e] + b[e];
+            if (pos) {
+              float pp[4];
+              load4(pos + (r % pos_rows) * Cout + vec * 4, pp);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] += pp[e];
+            }
+            store4(y + r * Cout + (int64_t)vec * 4, o);
+          }
         }
-        store4(y + r * Cout + (int64_t)vec * 4, o);
       }
     }
   }
@@ -102,24 +126,26 @@ static int launch_ln(const TI* x, TO* y, const float* gamma, const float* beta, 
                      Rows rows, int64_t nrows, int Cout, float eps, cudaStream_t st) {
   int nvec = Cout / 4;
   int vpl = (nvec + 31) / 32;
-  int64_t want = (nrows + LN_WARPS - 1) / LN_WARPS;
-  int64_t cap = (int64_t)num_sms() * 16;
-  int blocks = (int)(want < cap ? want : cap);
-  if (blocks < 1) blocks = 1;
   static const int kInst[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};   // instantiated vectors-per-lane
   int inst = 32;
   for (int k = 9; k >= 0; --k)
     if (kInst[k] >= vpl) inst = kInst[k];
-#define PSW_LN_CASE(V)                                                                                     \
-  case V:                                                                                                  \
-    layernorm_rows_kernel<V, TI, TO, Rows><<<blocks, LN_WARPS * 32, 0, st>>>(x, y, gamma, beta, pos, pos_rows, \
-                                                                             rows, Cout, eps);             \
+  const int R = inst <= 2 ? 4 : (inst <= 6 ? 2 : 1);               // rows per warp iteration
+  int64_t want = (nrows + (int64_t)LN_WARPS * R - 1) / ((int64_t)LN_WARPS * R);
+  int64_t cap = (int64_t)num_sms() * 16;
+  int blocks = (int)(want < cap ? want : cap);
+  if (blocks < 1) blocks = 1;
+#define PSW_LN_CASE(V, RR)                                                                                       \
+  case V:                                                                                                        \
+    layernorm_rows_kernel<V, RR, TI, TO, Rows><<<blocks, LN_WARPS * 32, 0, st>>>(x, y, gamma, beta, pos, pos_rows, \
+                                                                                 rows, Cout, eps);               \
     break;
   switch (inst) {
-    PSW_LN_CASE(1) PSW_LN_CASE(2) PSW_LN_CASE(3) PSW_LN_CASE(4) PSW_LN_CASE(6) PSW_LN_CASE(8) PSW_LN_CASE(12)
-    PSW_LN_CASE(16) PSW_LN_CASE(24) PSW_LN_CASE(32)
+    PSW_LN_CASE(1, 4) PSW_LN_CASE(2, 4) PSW_LN_CASE(3, 2) PSW_LN_CASE(4, 2) PSW_LN_CASE(6, 2) PSW_LN_CASE(8, 1)
+    PSW_LN_CASE(12, 1) PSW_LN_CASE(16, 1) PSW_LN_CASE(24, 1) PSW_LN_CASE(32, 1)
   }
 #undef PSW_LN_CASE
+  (void)R;
   return launch_status("layernorm_rows_kernel");
 }
 
@@ -140,39 +166,67 @@ static int dispatch_ln(const void* x, void* y, const float* gamma, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// LayerNorm + NHWC -> NCHW (fp32 out).  A CTA owns 32 consecutive tokens of one image: 8 warps normalise
-// 4 rows each into a [C][33] shared tile, then every warp streams whole channels out as 128-byte rows.
+// LayerNorm + NHWC -> NCHW (fp32 out).  A CTA owns TT consecutive tokens of one image: each warp reads whole rows
+// once (CPL channels per lane in registers, 128-byte coalesced requests), normalises them into a [C][TT+1] shared
+// tile, then every warp streams whole channels out as TT*4-byte contiguous runs.
 // ---------------------------------------------------------------------------------------------------
-template <typename TI>
+template <typename TI, int CPL>
 __global__ void __launch_bounds__(256)
 layernorm_nchw_kernel(const TI* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
-                      const float* __restrict__ beta, int64_t HW, int C, float eps) {
-  extern __shared__ float tile[];                 // [C][33]
+                      const float* __restrict__ beta, int64_t HW, int C, int TT, float eps) {
+  extern __shared__ float tile[];                 // [C][TT + 1]
+  const int P = TT + 1;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int64_t tiles_per_img = (HW + 31) / 32;
+  const int64_t tiles_per_img = (HW + TT - 1) / TT;
   const int b = (int)(blockIdx.x / tiles_per_img);
-  const int64_t t0 = (blockIdx.x % tiles_per_img) * 32;
+  const int64_t t0 = (blockIdx.x % tiles_per_img) * TT;
   const float inv_c = 1.0f / (float)C;
-  for (int rr = warp; rr < 32; rr += 8) {
-    int64_t t = t0 + rr;
-    if (t >= HW) break;
-    const TI* row = x + ((int64_t)b * HW + t) * C;
-    float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += to_f32(row[c]);
-    float mean = warp_sum(s) * inv_c;
-    float q = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      float d = to_f32(row[c]) - mean;
-      q += d * d;
+  float g[CPL], bt[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    const int c = lane + 32 * k;
+    g[k] = c < C ? gamma[c] : 0.f;
+    bt[k] = c < C ? beta[c] : 0.f;
+  }
+  for (int rr = warp; rr < TT; rr += 16) {        // two rows in flight per warp
+    float v[2][CPL];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int64_t t = t0 + rr + 8 * j;
+      const TI* row = x + ((int64_t)b * HW + t) * C;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const int c = lane + 32 * k;
+        v[j][k] = (rr + 8 * j < TT && t < HW && c < C) ? to_f32(row[c]) : 0.f;
+      }
     }
-    float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
-    for (int c = lane; c < C; c += 32) tile[c * 33 + rr] = (to_f32(row[c]) - mean) * rstd * gamma[c] + beta[c];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (rr + 8 * j >= TT || t0 + rr + 8 * j >= HW) continue;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) s += v[j][k];
+      const float mean = warp_sum(s) * inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const float d = (lane + 32 * k < C) ? v[j][k] - mean : 0.f;
+        q += d * d;
+      }
+      const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const int c = lane + 32 * k;
+        if (c < C) tile[c * P + rr + 8 * j] = (v[j][k] - mean) * rstd * g[k] + bt[k];
+      }
+    }
   }
   __syncthreads();
-  int64_t t = t0 + lane;
-  if (t < HW) {
-    for (int c = warp; c < C; c += 8) y[((int64_t)b * C + c) * HW + t] = tile[c * 33 + lane];
+  for (int c = warp; c < C; c += 8) {
+    float* dst = y + ((int64_t)b * C + c) * HW + t0;
+    for (int seg = lane; seg < TT; seg += 32)
+      if (t0 + seg < HW) dst[seg] = tile[c * P + seg];
   }
 }
 
@@ -206,23 +260,40 @@ extern "C" PSW_API int psw_patch_merge_ln_fwd(const void* x, void* y, const floa
   return dispatch_ln(x, y, gamma, beta, nullptr, 1, mr, nrows, 4 * C, eps, in_dtype, out_dtype, (cudaStream_t)stream);
 }
 
+template <typename TI>
+static int launch_nchw(const TI* x, float* y, const float* gamma, const float* beta, int B, int64_t HW, int C, float eps,
+                       cudaStream_t st) {
+  const int cpl = (C + 31) / 32;
+  // tokens per tile: as wide as ~48 KiB of shared memory allows, 32..128
+  int TT = 128;
+  while (TT > 32 && (size_t)C * (TT + 1) * sizeof(float) > 56 * 1024) TT >>= 1;
+  const size_t smem = (size_t)C * (TT + 1) * sizeof(float);
+  PSW_REQUIRE(smem <= 200 * 1024 && cpl <= 32, PSW_ERR_UNSUPPORTED, "psw_layernorm_nchw_fwd: C=%d too large", C);
+  const int64_t blocks = (int64_t)B * ((HW + TT - 1) / TT);
+  PSW_REQUIRE(blocks < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_layernorm_nchw_fwd: too many tiles");
+#define PSW_NCHW_CASE(V)                                                                                          \
+  case V: {                                                                                                       \
+    auto kern = layernorm_nchw_kernel<TI, V>;                                                                     \
+    PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+    kern<<<(unsigned)blocks, 256, smem, st>>>(x, y, gamma, beta, HW, C, TT, eps);                                \
+    break;                                                                                                        \
+  }
+  int inst = cpl <= 1 ? 1 : cpl <= 2 ? 2 : cpl <= 3 ? 3 : cpl <= 4 ? 4 : cpl <= 6 ? 6 : cpl <= 8 ? 8 : cpl <= 12 ? 12 : cpl <= 16 ? 16 : cpl <= 24 ? 24 : 32;
+  switch (inst) {
+    PSW_NCHW_CASE(1) PSW_NCHW_CASE(2) PSW_NCHW_CASE(3) PSW_NCHW_CASE(4) PSW_NCHW_CASE(6) PSW_NCHW_CASE(8)
+    PSW_NCHW_CASE(12) PSW_NCHW_CASE(16) PSW_NCHW_CASE(24) PSW_NCHW_CASE(32)
+  }
+#undef PSW_NCHW_CASE
+  return launch_status("layernorm_nchw_kernel");
+}
+
 extern "C" PSW_API int psw_layernorm_nchw_fwd(const void* x, float* y, const float* gamma, const float* beta, int B,
                                       int64_t HW, int C, float eps, int in_dtype, void* stream) {
   PSW_REQUIRE(x && y && gamma && beta, PSW_ERR_BAD_ARG, "psw_layernorm_nchw_fwd: null pointer");
   PSW_REQUIRE(B > 0 && HW > 0 && C > 0, PSW_ERR_BAD_ARG, "psw_layernorm_nchw_fwd: bad dims");
-  size_t smem = (size_t)C * 33 * sizeof(float);
-  PSW_REQUIRE(smem <= 200 * 1024, PSW_ERR_UNSUPPORTED, "psw_layernorm_nchw_fwd: C=%d too large", C);
-  int64_t blocks = (int64_t)B * ((HW + 31) / 32);
-  PSW_REQUIRE(blocks < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_layernorm_nchw_fwd: too many tiles");
   cudaStream_t st = (cudaStream_t)stream;
-  if (in_dtype == PSW_F32) {
-    PSW_CUDA(cudaFuncSetAttribute(layernorm_nchw_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layernorm_nchw_kernel<float><<<(unsigned)blocks, 256, smem, st>>>((const float*)x, y, gamma, beta, HW, C, eps);
-  } else if (in_dtype == PSW_BF16) {
-    PSW_CUDA(cudaFuncSetAttribute(layernorm_nchw_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    layernorm_nchw_kernel<bf16><<<(unsigned)blocks, 256, smem, st>>>((const bf16*)x, y, gamma, beta, HW, C, eps);
-  } else {
-    PSW_REQUIRE(false, PSW_ERR_BAD_ARG, "psw_layernorm_nchw_fwd: unknown dtype %d", in_dtype);
-  }
-  return launch_status("layernorm_nchw_kernel");
+  if (in_dtype == PSW_F32) return launch_nchw((const float*)x, y, gamma, beta, B, HW, C, eps, st);
+  if (in_dtype == PSW_BF16) return launch_nchw((const bf16*)x, y, gamma, beta, B, HW, C, eps, st);
+  PSW_REQUIRE(false, PSW_ERR_BAD_ARG, "psw_layernorm_nchw_fwd: unknown dtype %d", in_dtype);
+  return 0;
 }

@@ -115,3 +115,30 @@ def test_api_surface_on_gpu():
     assert m(img)[0].shape == (1, 64, 8, 13)
     m.switch_pano_mode()
     assert m.pano_mode is True and all(b.pano_mode for l in m.layers for b in l.blocks)
+
+
+def test_host_pipeline_matches_direct_forward():
+    """HostPipeline (pinned host in / pinned host out, chunked, three streams) returns what forward() returns."""
+    from panoswintransformerobjectdetection_b200.runtime import HostPipeline
+    cfg = O.make_config(embed_dim=32, depths=(2, 2, 2), num_heads=(1, 2, 4), out_indices=(0, 1, 2))
+    m = _build(cfg, O.make_state_dict(cfg, 2), "bf16")
+    img = O.make_image((5, 3, 64, 128), 3)
+    direct = [o.cpu() for o in m(img.to(DEV))]
+    for chunk in (2, 5, 8):
+        got = HostPipeline(m, chunk=chunk)(img.pin_memory())
+        assert len(got) == len(direct)
+        for g, d in zip(got, direct):
+            assert g.is_pinned() and g.shape == d.shape
+            assert rel_l2(g, d) <= 5e-3          # cuDNN may choose another stem algorithm per chunk size
+
+
+def test_bf16_residual_stream_option():
+    cfg = O.make_config(embed_dim=32, depths=(2, 2, 2), num_heads=(1, 2, 4), out_indices=(0, 1, 2))
+    sd = O.make_state_dict(cfg, 2)
+    img = O.make_image((2, 3, 128, 256), 3)
+    want = O.backbone_forward(sd, cfg, img)
+    m = _build(cfg, sd, "bf16")
+    m.set_residual_dtype("bf16")
+    outs = m(img.to(DEV))
+    for o, w in zip(outs, want):
+        assert o.dtype == torch.float32 and rel_l2(o, w) <= 3e-2
