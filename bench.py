@@ -153,7 +153,7 @@ class Tracer:
 
 
 # ------------------------------------------------------------------------------------------------
-def build_model(device):
+def build_model(device, residual="fp32"):
     import torch
     from oracle import panoswin_oracle as O
     import panoswintransformerobjectdetection_b200 as P
@@ -163,6 +163,7 @@ def build_model(device):
     m.to(device)
     m.eval()
     m.set_compute_dtype("bf16")
+    m.set_residual_dtype(residual)
     return m
 
 
@@ -224,7 +225,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    model = build_model(dev)
+    model = build_model(dev, args.residual)
     g = torch.Generator().manual_seed(1234 + rank)
     host_img = torch.rand(B, 3, IMG_H, IMG_W, generator=g).pin_memory()
     dev_img = host_img.to(dev)
@@ -318,7 +319,7 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"PanoSwin-T backbone inference (BASELINE.json configs[1]), batch {B}x3x{IMG_H}x{IMG_W} per GPU, "
-                               "bf16 activations / fp32 residual stream, random-init weights",
+                               f"bf16 activations / {args.residual} residual stream, random-init weights",
                    "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective in the forward",
                    "l2": "inputs (201 MB of images, >=400 MB activations per layer) exceed the 126 MB L2; no explicit flush",
                    "stem": "conv stem runs on cuDNN (torch), everything after it on libpanoswin_b200"},
@@ -348,7 +349,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
-    ap.add_argument("--chunk", type=int, default=4, help="images per pipelined chunk on the end-to-end path")
+    ap.add_argument("--chunk", type=int, default=8, help="images per pipelined chunk on the end-to-end path")
+    ap.add_argument("--residual", default="fp32", choices=["fp32", "bf16"], help="residual-stream storage in bf16 mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--detail", default=None, help="write the per-shape kernel table to this JSON file")
     args = ap.parse_args()

@@ -40,23 +40,49 @@ def gather_features(local_outs: Sequence[torch.Tensor], world: int, group=None) 
     return outs
 
 
+class GraphedForward:
+    """The backbone forward for one fixed input shape captured into a CUDA graph: one `replay()` re-issues the
+    ~100 kernel launches of a forward without any Python / ctypes work (small chunks are launch-bound otherwise).
+    `static_in` is the graph's input buffer, `static_out` its tuple of output maps."""
+
+    def __init__(self, model, shape, device):
+        self.static_in = torch.zeros(shape, device=device)
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side), torch.no_grad():      # warm-up: builds every cached constant / bf16 weight copy
+            for _ in range(2):
+                model(self.static_in)
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = model(self.static_in)
+
+    def replay(self):
+        self.graph.replay()
+        return self.static_out
+
+
 class HostPipeline:
     """model(images on the host) -> feature maps on the host, chunked and overlapped.
 
-    Three streams: copy-in (H2D of chunk i+1), compute (forward of chunk i), copy-out.  Every stage's feature map
-    is copied out as soon as that stage has been computed (`forward_streamed`), so the D2H traffic — 3.75x the
-    H2D bytes for this backbone — runs underneath the remaining stages and the following chunks.
-    Input must be a pinned fp32 [B, 3, H, W] tensor; outputs are pinned fp32 NCHW maps reused across calls."""
+    Three streams: copy-in (H2D of chunk i+1), compute (forward of chunk i), copy-out (D2H of chunk i-1; the
+    feature maps are 3.75x the input bytes, so the D2H stream is the critical resource).  With `graphs=True`
+    (default) each of the two chunk slots owns a CUDA graph of the forward, so chunks can be small (early first
+    D2H, short tail) without becoming launch-bound.  Input must be a pinned fp32 [B, 3, H, W] tensor; outputs are
+    pinned fp32 NCHW maps reused across calls."""
 
-    def __init__(self, model, chunk: int = 4):
+    def __init__(self, model, chunk: int = 8, graphs: bool = True):
         self.model = model
         self.chunk = int(chunk)
+        self.graphs = graphs
         self.dev = next(model.parameters()).device
         self.s_in = torch.cuda.Stream(self.dev)
         self.s_cmp = torch.cuda.Stream(self.dev)
         self.s_out = torch.cuda.Stream(self.dev)
         self._host_out = None
-        self._dev_in = None
+        self._host_out_batch = None
+        self._slots = {}                              # (slot, chunk shape) -> GraphedForward / input buffer
 
     def _ensure_host_out(self, B, k, o):
         if self._host_out is None or self._host_out_batch != B:
@@ -67,46 +93,79 @@ class HostPipeline:
             self._host_out[k] = h
         return h
 
+    def _schedule(self, B):
+        """Chunk boundaries: a half-size first chunk (the copy-out stream starts early) and a half-size last chunk
+        (short tail after the last forward), full chunks in between."""
+        c = self.chunk
+        sizes = []
+        left = B
+        if B > 2 * c and c >= 2:
+            sizes.append(c // 2)
+            left -= c // 2
+            while left > c + c // 2:
+                sizes.append(c)
+                left -= c
+            if left > c // 2:
+                sizes.append(left - c // 2)
+                left = c // 2
+            sizes.append(left)
+        else:
+            while left > 0:
+                sizes.append(min(c, left))
+                left -= sizes[-1]
+        bounds, b0 = [], 0
+        for n in sizes:
+            bounds.append((b0, b0 + n))
+            b0 += n
+        return bounds
+
+    def _slot(self, k, shape):
+        key = (k, tuple(shape))
+        s = self._slots.get(key)
+        if s is None:
+            s = GraphedForward(self.model, shape, self.dev) if self.graphs else torch.empty(shape, device=self.dev)
+            self._slots[key] = s
+        return s
+
     @torch.no_grad()
     def __call__(self, host_img: torch.Tensor):
         if host_img.is_cuda or not host_img.is_pinned():
             raise ValueError("HostPipeline wants a pinned host tensor")
         B = host_img.shape[0]
+        bounds = self._schedule(B)
+        slots = [self._slot(ci & 1, (b1 - b0,) + tuple(host_img.shape[1:])) for ci, (b0, b1) in enumerate(bounds)]
         cur = torch.cuda.current_stream(self.dev)
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_stream(cur)
-        n_in = min(self.chunk, B)
-        if self._dev_in is None or self._dev_in[0].shape[1:] != host_img.shape[1:] or self._dev_in[0].shape[0] < n_in:
-            self._dev_in = [torch.empty((n_in,) + tuple(host_img.shape[1:]), device=self.dev) for _ in range(2)]
-        in_free = [None, None]                      # event: compute finished reading input buffer k
-        live = []                                   # keeps device outputs alive until the final sync
-        for ci, b0 in enumerate(range(0, B, self.chunk)):
-            b1 = min(B, b0 + self.chunk)
-            k = ci & 1
+        in_free, out_free = {}, {}                    # per slot object: input consumed / outputs copied out
+        live = []
+        n_out = 0
+        for (b0, b1), slot in zip(bounds, slots):
+            xin = slot.static_in if self.graphs else slot
             with torch.cuda.stream(self.s_in):
-                if in_free[k] is not None:
-                    self.s_in.wait_event(in_free[k])
-                xin = self._dev_in[k][: b1 - b0]
+                if id(slot) in in_free:
+                    self.s_in.wait_event(in_free[id(slot)])
                 xin.copy_(host_img[b0:b1], non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(self.s_in)
-
-            def on_output(idx, o, b0=b0, b1=b1):
-                done = torch.cuda.Event()
-                done.record(self.s_cmp)
-                h = self._ensure_host_out(B, idx, o)
-                with torch.cuda.stream(self.s_out):
-                    self.s_out.wait_event(done)
-                    h[b0:b1].copy_(o, non_blocking=True)
-
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(ready)
-                outs = self.model.forward_streamed(xin, on_output)
-                done_in = torch.cuda.Event()
-                done_in.record(self.s_cmp)
-                in_free[k] = done_in
+                if id(slot) in out_free:              # the graph's static outputs are still being copied out
+                    self.s_cmp.wait_event(out_free[id(slot)])
+                outs = slot.replay() if self.graphs else self.model(xin)
+                done = torch.cuda.Event()
+                done.record(self.s_cmp)
+                in_free[id(slot)] = done
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(done)
+                for idx, o in enumerate(outs):
+                    self._ensure_host_out(B, idx, o)[b0:b1].copy_(o, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(self.s_out)
+                out_free[id(slot)] = copied
             live.append(outs)
+            n_out = len(outs)
         cur.wait_stream(self.s_out)
         cur.wait_stream(self.s_cmp)
         cur.synchronize()
-        return [self._host_out[i] for i in range(len(live[0]))]
+        return [self._host_out[i] for i in range(n_out)]

@@ -124,8 +124,8 @@ def test_host_pipeline_matches_direct_forward():
     m = _build(cfg, O.make_state_dict(cfg, 2), "bf16")
     img = O.make_image((5, 3, 64, 128), 3)
     direct = [o.cpu() for o in m(img.to(DEV))]
-    for chunk in (2, 5, 8):
-        got = HostPipeline(m, chunk=chunk)(img.pin_memory())
+    for chunk, graphs in ((2, True), (5, True), (8, False), (2, False)):
+        got = HostPipeline(m, chunk=chunk, graphs=graphs)(img.pin_memory())
         assert len(got) == len(direct)
         for g, d in zip(got, direct):
             assert g.is_pinned() and g.shape == d.shape

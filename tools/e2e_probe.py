@@ -1,0 +1,42 @@
+"""PCIe copy rates and the end-to-end pipeline at several chunk sizes."""
+import os, sys, time
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench
+from panoswintransformerobjectdetection_b200.runtime import HostPipeline
+
+dev = torch.device("cuda", 0)
+def t(fn, n=5):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+print("H2D GB/s", 0.268435456 / (t(lambda: d.copy_(h, non_blocking=True)) * 1e-3))
+print("D2H GB/s", 0.268435456 / (t(lambda: h.copy_(d, non_blocking=True)) * 1e-3))
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+h2 = torch.empty(256 << 20, dtype=torch.uint8).pin_memory(); d2 = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+def both():
+    s1.wait_stream(torch.cuda.current_stream()); s2.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s1): d.copy_(h, non_blocking=True)
+    with torch.cuda.stream(s2): h2.copy_(d2, non_blocking=True)
+    torch.cuda.current_stream().wait_stream(s1); torch.cuda.current_stream().wait_stream(s2)
+print("duplex: ms for 256MiB each way", t(both))
+model = bench.build_model(dev)
+img = torch.rand(32, 3, 512, 1024).pin_memory()
+dimg = img.to(dev)
+for bs in (32, 16, 8, 4, 2):
+    x = dimg[:bs]
+    ms = t(lambda: model(x), 5)
+    print(f"device-resident forward batch {bs}: {ms:.2f} ms -> {bs / ms * 1e3:.0f} img/s")
+for graphs in (False, True):
+    for chunk in (16, 8, 4, 2):
+        pipe = HostPipeline(model, chunk=chunk, graphs=graphs)
+        ms = t(lambda: pipe(img), 5)
+        print(f"pipeline graphs={graphs} chunk {chunk}: {ms:.2f} ms -> {32 / ms * 1e3:.0f} img/s", flush=True)
+        del pipe
+        torch.cuda.empty_cache()
