@@ -95,14 +95,14 @@ class ClockSampler:
 def launch_work(fn, a):
     sz = {0: 4, 1: 2}
     if fn == "psw_window_attn_fwd":
-        B, H, W, C = a[8], a[9], a[10], a[11]
-        heads, ws = a[12], a[13]
+        B, H, W, C = a[9], a[10], a[11], a[12]
+        heads, ws = a[13], a[14]
         tok = B * H * W
-        es = sz[a[17]]
-        nwin_h = -(-(2 * H if a[15] else H) // ws)
-        nwin_w = -(-(((W + 1) // 2) if a[15] else W) // ws)
+        es = sz[a[18]]
+        nwin_h = -(-(2 * H if a[16] else H) // ws)
+        nwin_w = -(-(((W + 1) // 2) if a[16] else W) // ws)
         flops = 4.0 * (ws * ws) ** 2 * (C // heads) * B * nwin_h * nwin_w * heads
-        return dict(kind="window_attn", shape=f"B{B} {H}x{W} C{C} h{heads} s{a[14]}", bytes=4.0 * tok * C * es, flops=flops)
+        return dict(kind="window_attn", shape=f"B{B} {H}x{W} C{C} h{heads} s{a[15]}", bytes=4.0 * tok * C * es, flops=flops)
     if fn == "psw_linear_fwd":
         M, N, K = a[5], a[6], a[7]
         es, eo = sz[a[9]], sz[a[10]]

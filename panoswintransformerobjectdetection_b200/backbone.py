@@ -355,6 +355,17 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         self._weight_cache[k] = (p._version, p.data_ptr(), conv)
         return conv
 
+    def _bias_tables(self, attn, ws):
+        """Per-head (alpha, beta) layout for the bf16 attention kernel, cached until either table changes."""
+        al, be = attn.sphere_position_alpha_table_Te, attn.sphere_position_beta_table_Te
+        k = ("btab", id(attn))
+        ver = (al._version, be._version, al.data_ptr(), be.data_ptr())
+        hit = self._weight_cache.get(k)
+        if hit is None or hit[0] != ver:
+            hit = (ver, ops.window_bias_tables(al.detach().contiguous(), be.detach().contiguous(), ws))
+            self._weight_cache[k] = hit
+        return hit[1]
+
     @staticmethod
     def _f(p: Optional[torch.Tensor]):
         return None if p is None else p.detach().contiguous()
@@ -484,14 +495,17 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                 mask = None
                 if not self.pano_mode and shift > 0:
                     mask = self._const(("mask", H, W, ws, shift), lambda: planar_attention_mask(H, W, ws, shift), dev)
-                hav = None
-                if self.pano_mode and cd == torch.bfloat16:
-                    hav = self._const(("hav", H, W, ws, shift), lambda: ops.window_hav_table(uv, ws, shift), dev)
+                hav = btab = None
+                if cd == torch.bfloat16:
+                    if self.pano_mode:
+                        hav = self._const(("hav", H, W, ws, shift), lambda: ops.window_hav_table(uv, ws, shift), dev)
+                    btab = self._bias_tables(a, ws)
                 xn = ops.layernorm(x, self._f(blk.norm1.weight), self._f(blk.norm1.bias), blk.norm1.eps, cd)
                 qkv = ops.linear(xn, self._w(a.qkv.weight, cd), self._f(a.qkv.bias))
                 att = ops.window_attention(qkv.view(B, H, W, 3 * C), self._f(a.sphere_position_alpha_table_Te),
                                            self._f(a.sphere_position_beta_table_Te), self._f(a.qkv.bias), uv, mask,
-                                           a.num_heads, ws, shift, self.pano_mode, a.scale, hav_table=hav)
+                                           a.num_heads, ws, shift, self.pano_mode, a.scale, hav_table=hav,
+                                           bias_tables=btab)
                 x = ops.linear(att.view(B, H * W, C), self._w(a.proj.weight, cd), self._f(a.proj.bias), residual=x, out=x)
                 xn = ops.layernorm(x, self._f(blk.norm2.weight), self._f(blk.norm2.bias), blk.norm2.eps, cd)
                 hid = ops.linear(xn, self._w(blk.mlp.fc1.weight, cd), self._f(blk.mlp.fc1.bias), gelu=True)

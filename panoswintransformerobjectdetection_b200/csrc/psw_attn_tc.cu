@@ -29,16 +29,15 @@
 
 namespace psw {
 
-constexpr int AT_THREADS = 256;                   // two threads per tile row
+constexpr int AT_THREADS = 128;
 constexpr int AT_PART_BYTES = 128 * 64;            // 128 rows x 64 B (32 bf16), SWIZZLE_64B
 constexpr int AT_BUF_BYTES = 3 * AT_PART_BYTES;    // q, k, v
 constexpr int AT_HAV_PITCH = 56;                   // halfs per distance-table row (112 B = 7 x 16 B)
 constexpr int AT_TMEM_COLS = 128;
 constexpr int AT_P_COL = 0;                        // P (bf16x2 packed): TMEM columns [0, 32)
 constexpr int AT_O_COL = 32;                       // O (fp32): TMEM columns [32, 96)
-constexpr int AT_CTAS_PER_SM = 2;
-constexpr int AT_STAGES = 4;                      // q/k/v ring: 3 steps of prefetch
-constexpr int AT_TAB_PITCH = 23;                   // float2 entries per table row in smem (13 used)
+constexpr int AT_CTAS_PER_SM = 3;                 // measured: 4 CTAs/SM (128 regs, no spills) is not faster
+constexpr int AT_TAB_PITCH = 24;                   // float2 entries per table row (13 used; 192 B rows = 12 x 16 B)
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& r) {
@@ -102,6 +101,7 @@ struct AttnParams {
   bf16* out;
   const float* alpha;
   const float* beta;
+  const float2* tables;   // [heads][2w-1][AT_TAB_PITCH] (alpha, beta) from psw_window_bias_tables, or nullptr
   const float* qkv_bias;
   const __half* hav;      // [wpi][N][56] or nullptr (planar mode: d == 0)
   const float* mask;
@@ -111,6 +111,7 @@ struct AttnParams {
   int n_windows;          // B * windows per image
   int n_items;            // ceil(n_windows / 2) * (heads / hc)
   float scale;
+  long long* dbg;         // diagnostics: per-phase cycle totals of CTA 0 (nullptr in production)
 };
 
 // One pipeline step = one head of one window pair.
@@ -119,94 +120,8 @@ struct Step {
   int wp;                 // window pair: windows 2*wp, 2*wp + 1
   int e;                  // head
   int el;                 // head index inside the item, 0 .. hc-1
-  int n;                  // running step count of this CTA (selects the ring stage)
+  int n;                  // running step count of this CTA (parity selects the buffers)
 };
-
-// TMEM column loads of arbitrary compile-time length (multiples handled with x16 / x8 / x1 pieces)
-__device__ __forceinline__ void tmem_ld_x8v(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_x16v(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st_x4v(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
-               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_x8v(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_st_x16v(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
-}
-__device__ __forceinline__ void pair_barrier(int q) {      // the two warps that share TMEM lane quadrant q
-  asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-}
-
-// Bias + softmax of one half of a tile row.  HALF 0: keys [0, 24); HALF 1: keys [24, 49) (+ zero padding to 64).
-// Returns this half's partial sum of exp; the un-normalised bf16 probabilities go to the P columns of TMEM.
-template <int WS, int HALF, bool HAS_MASK>
-__device__ __forceinline__ float softmax_half(uint32_t s_addr, uint32_t p_addr, const uint4 (&hreg)[4], const float2* trow,
-                                              const float* mrow, float scale, bool row_valid, float* xch_max, int q) {
-  constexpr int N = WS * WS;
-  constexpr int TP = AT_TAB_PITCH;
-  constexpr int J0 = HALF == 0 ? 0 : 24;
-  constexpr int J1 = HALF == 0 ? 24 : N;
-  constexpr int NJ = J1 - J0;                               // 24 or 25
-  uint32_t sr[NJ > 24 ? 25 : 24];
-  tmem_ld_x16v(s_addr + J0, sr);
-  tmem_ld_x8v(s_addr + J0 + 16, sr + 16);
-  if constexpr (NJ > 24) tmem_ld_x1(s_addr + J0 + 24, sr[24]);
-  tmem_ld_wait();
-  float t[NJ];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int jj = 0; jj < NJ; ++jj) {
-    const int j = J0 + jj;
-    const uint32_t hw = reinterpret_cast<const uint32_t*>(hreg)[jj >> 1];
-    const __half2 hh = *reinterpret_cast<const __half2*>(&hw);
-    const float hv = (jj & 1) ? __high2float(hh) : __low2float(hh);
-    const float2 ab = trow[-((j / WS) * TP + (j % WS))];
-    float bia = fmaf(hv, ab.x, ab.y);
-    if constexpr (HAS_MASK) bia += __ldg(mrow + j);
-    t[jj] = fmaf(__uint_as_float(sr[jj]), scale, bia);
-    mx = fmaxf(mx, t[jj]);
-  }
-  // exchange the half-row maxima with the partner warp (same TMEM lanes, other key half)
-  xch_max[0] = mx;
-  pair_barrier(q);
-  mx = fmaxf(mx, xch_max[HALF == 0 ? 128 : -128]);
-  const float mneg = -mx * LOG2E;
-  float sum = 0.f;
-  constexpr int NP = HALF == 0 ? 12 : 20;                   // packed bf16x2 columns: keys [0,24) / [24,64)
-  uint32_t pk[NP];
-#pragma unroll
-  for (int k = 0; k < NP; ++k) {
-    float p0 = 0.f, p1 = 0.f;
-    if (2 * k < NJ) { p0 = fast_exp2(fmaf(t[2 * k], LOG2E, mneg)); sum += p0; }
-    if (2 * k + 1 < NJ) { p1 = fast_exp2(fmaf(t[2 * k + 1], LOG2E, mneg)); sum += p1; }
-    pk[k] = row_valid ? pack_bf16x2(p0, p1) : 0u;
-  }
-  if constexpr (HALF == 0) {
-    tmem_st_x8v(p_addr, pk);
-    tmem_st_x4v(p_addr + 8, pk + 8);
-  } else {
-    tmem_st_x16v(p_addr + 12, pk);
-    tmem_st_x4v(p_addr + 28, pk + 16);
-  }
-  tmem_st_wait();
-  return sum;
-}
 
 template <int WS, bool HAS_MASK>
 __global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
@@ -216,24 +131,20 @@ window_attn_tc_kernel(const AttnParams p) {
   constexpr int TAB = TW * TW;
   constexpr int TP = AT_TAB_PITCH;               // smem row pitch of the table: bank-conflict-free for row-per-lane reads
   constexpr int TABS = TW * TP;                  // float2 entries per table slot
-  constexpr int NS = AT_STAGES;
-  static_assert(N == 49, "row split below is written for window 7");
+  static_assert(N <= 64, "window too large for the 64-row unit tile");
   static_assert(TP >= TW, "table pitch too small");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* bufs = smem;                                                  // [NS stages][3][128 x 64 B]
-  float2* tab = reinterpret_cast<float2*>(bufs + NS * AT_BUF_BYTES);     // [NS stages][TABS] (alpha, beta)
-  int* src = reinterpret_cast<int*>(tab + NS * TABS);                    // [NS slots][2 units][64]
-  float* xch = reinterpret_cast<float*>(src + NS * 128);                 // [2 halves][128]: row max, then [2][128] row sum
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 4 * 128);           // [2]: S ready, O ready
+  // align to 1024 B by OFFSETTING the __shared__ array (keeps the shared address space: LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* bufs = smem;                                                  // [2 stages][3][128 x 64 B]
+  float2* tab = reinterpret_cast<float2*>(bufs + 2 * AT_BUF_BYTES);      // [2 stages][TABS] (alpha, beta)
+  int* src = reinterpret_cast<int*>(tab + 2 * TABS);                     // [3 slots][2 units][64]: this, next, next-next pair
+  uint64_t* bars = reinterpret_cast<uint64_t*>(src + 3 * 2 * 64);        // [2]: S ready, O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int lane = tid & 31;
-  const int q = warp & 3;                                  // TMEM lane quadrant of this warp
-  const int half = warp >> 2;                              // which half of the keys / output dims this thread owns
   const int C = p.C, heads = p.heads, C3 = 3 * p.C;
   const WinGeom g = p.g;
   const int wpi = g.nWh * g.nWw;
@@ -241,7 +152,7 @@ window_attn_tc_kernel(const AttnParams p) {
   const int n_hc = heads / p.hc;
 
   // ---------------------------------------------------------------- one-time setup
-  for (int i = tid; i < NS * AT_BUF_BYTES / 16; i += AT_THREADS)
+  for (int i = tid; i < 2 * AT_BUF_BYTES / 16; i += AT_THREADS)
     reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0, 0, 0, 0);          // padding rows must stay finite
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -256,7 +167,7 @@ window_attn_tc_kernel(const AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
   // 8 bias values (one 16-byte chunk of a padding token's q / k / v row) as bf16; padding cells are rare
   auto bias_chunk = [&](int ch) {
     uint4 r = make_uint4(0, 0, 0, 0);
@@ -271,16 +182,14 @@ window_attn_tc_kernel(const AttnParams p) {
   const int item_begin = (int)((int64_t)p.n_items * blockIdx.x / gridDim.x);
   const int item_end = (int)((int64_t)p.n_items * (blockIdx.x + 1) / gridDim.x);
 
-  // this thread's tile row (shared with the partner thread of warp q + 4 * (1 - half))
-  const int row = q * 32 + lane;
-  const int unit = row >> 6;                               // warp-uniform
-  const int ti = row & 63;
+  // this thread's tile row
+  const int unit = tid >> 6;                               // warp-uniform
+  const int ti = tid & 63;
   const int ic = ti < N ? ti : 0;
   const int ri = ic / WS, ci = ic - ri * WS;
-  // loader role of this thread: 16-byte chunk lc of token lt of both units; token-map role: (unit lu, token lt2)
+  // loader role of this thread: 16-byte chunk c of tokens lt0 and lt0 + 32
   const int lc = tid & 3;
-  const int lt = tid >> 2;                                 // 0 .. 63
-  const int lu = tid >> 7, lt2 = tid & 63;                 // threads 0..63 and 128..191 compute the token maps
+  const int lt0 = tid >> 2;
 
   auto first_step = [&](int item) {
     Step s;
@@ -299,105 +208,107 @@ window_attn_tc_kernel(const AttnParams p) {
     if (s.e + 1 < heads) { ++s.e; } else { s.e = 0; ++s.wp; }
     return s;
   };
-  // token maps of both windows of pair `wp` -> src[wp % NS]; entry = global token index b*H*W + h*W + w, or -1
+  // token maps of both windows of pair `wp` -> src[wp & 3] (thread = (unit, token)); entry = global token index
+  // b*H*W + h*W + w of the cell's source token, or -1 for a padding cell
   auto prep_src = [&](int wp) {
-    if ((tid & 64) == 0) {
-      const int w = 2 * wp + lu;
-      int s = -1;
-      if (lt2 < N && w < p.n_windows) {
-        const int b = w / wpi;
-        const int wi = w - b * wpi;
-        const int wr = wi / g.nWw, wc = wi - wr * g.nWw;
-        const int r = lt2 / WS, c = lt2 - r * WS;
-        const int t = source_token(g, wr * WS + r, wc * WS + c);
-        if (t >= 0) s = b * (int)HW + t;
-      }
-      src[(wp % NS) * 128 + lu * 64 + lt2] = s;
+    const int w = 2 * wp + unit;
+    int s = -1;
+    if (ti < N && w < p.n_windows) {
+      const int b = w / wpi;
+      const int wi = w - b * wpi;
+      const int wr = wi / g.nWw, wc = wi - wr * g.nWw;
+      const int t = source_token(g, wr * WS + ri, wc * WS + ci);
+      if (t >= 0) s = b * (int)HW + t;                     // global token index (< 2^31, checked by the host)
     }
+    src[(wp % 3) * 128 + tid] = s;
   };
-  // gather all q/k/v rows and the per-head tables of step `st` into ring stage st.n % NS
+  // per-thread constants of the loader role: rows lt0, lt0+32 of unit 0 and unit 1, chunk lc
+  int ld_row[4], ld_dst[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int t = lt0 + 32 * (k & 1);
+    ld_row[k] = t < N ? (k >> 1) * 64 + t : -1;
+    const int row = (k >> 1) * 64 + t;
+    ld_dst[k] = row * 64 + ((lc ^ ((row >> 1) & 3)) << 4);
+  }
+  const int tab_o0 = 2 * ((tid / TW) * TP + (tid % TW));                           // table entries tid and tid + 128
+  const int tab_o1 = 2 * (((tid + AT_THREADS) / TW) * TP + ((tid + AT_THREADS) % TW));
+  // gather all q/k/v rows and the per-head tables of step `st` into stage (st.n & 1)
   auto issue_loads = [&](const Step& st) {
-    uint8_t* base = bufs + (st.n % NS) * AT_BUF_BYTES;
-    const int* smap = src + (st.wp % NS) * 128;
+    uint8_t* base = bufs + (st.n & 1) * AT_BUF_BYTES;
+    const int* smap = src + (st.wp % 3) * 128;
     const bf16* gq = p.qkv + st.e * 32 + lc * 8;
     const int bch = st.e * 32 + lc * 8;
-    if (lt < N) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int r = u * 64 + lt;
-        const int s = smap[r];
-        uint8_t* dst = base + r * 64 + ((lc ^ ((r >> 1) & 3)) << 4);
+    for (int k = 0; k < 4; ++k) {
+      if (ld_row[k] >= 0) {
+        const int s = smap[ld_row[k]];
+        uint8_t* dst = base + ld_dst[k];
         if (s >= 0) {
           const bf16* grow = gq + (int64_t)s * C3;
           cp_async16(dst, grow);
           cp_async16(dst + AT_PART_BYTES, grow + C);
           cp_async16(dst + 2 * AT_PART_BYTES, grow + 2 * C);
-        } else if (2 * st.wp + u < p.n_windows) {          // padding cell of a real window: q/k/v = bias
+        } else if (2 * st.wp + (k >> 1) < p.n_windows) {   // padding cell of a real window: q/k/v = bias
           *reinterpret_cast<uint4*>(dst) = bias_chunk(bch);
           *reinterpret_cast<uint4*>(dst + AT_PART_BYTES) = bias_chunk(bch + C);
           *reinterpret_cast<uint4*>(dst + 2 * AT_PART_BYTES) = bias_chunk(bch + 2 * C);
         }
       }
     }
-    if (tid < TAB) {
-      float* trow = reinterpret_cast<float*>(tab + (st.n % NS) * TABS);
-      const int o = 2 * ((tid / TW) * TP + (tid % TW));
-      cp_async4(trow + o, p.alpha + tid * heads + st.e);
-      cp_async4(trow + o + 1, p.beta + tid * heads + st.e);
+    float* trow = reinterpret_cast<float*>(tab + (st.n & 1) * TABS);
+    if (p.tables != nullptr) {
+      // pre-transposed tables: 7 x 16 B (14 entries, 13 used) per table row, one cp.async per thread
+      if (tid < TW * 7) {
+        const int o = (tid / 7) * TP + (tid % 7) * 2;                  // float2 index inside the head's table
+        cp_async16(tab + (st.n & 1) * TABS + o, p.tables + (size_t)st.e * TABS + o);
+      }
+    } else {
+      cp_async4(trow + tab_o0, p.alpha + tid * heads + st.e);
+      cp_async4(trow + tab_o0 + 1, p.beta + tid * heads + st.e);
+      if (tid + AT_THREADS < TAB) {
+        cp_async4(trow + tab_o1, p.alpha + (tid + AT_THREADS) * heads + st.e);
+        cp_async4(trow + tab_o1 + 1, p.beta + (tid + AT_THREADS) * heads + st.e);
+      }
     }
   };
 
-  // ---------------------------------------------------------------- prologue: fill NS-1 ring stages
   Step cur = first_step(item_begin);
-  Step pre = cur;                                          // next step to be prefetched
   int src_wp = -1;                                         // highest window pair whose token maps are in smem
-  {
-    Step s = cur;
-    for (int k = 0; k < NS - 1; ++k) {
-      if (s.item < item_end && s.wp > src_wp) { prep_src(s.wp); src_wp = s.wp; }
-      s = next_step(s);
-    }
+  if (item_begin < item_end) {
+    prep_src(cur.wp);
+    src_wp = cur.wp;
+    const Step n1 = next_step(cur);
+    if (n1.item < item_end && n1.wp > src_wp) { prep_src(n1.wp); src_wp = n1.wp; }
+    __syncthreads();
+    issue_loads(cur);
   }
-  __syncthreads();
-  for (int k = 0; k < NS - 1; ++k) {
-    if (pre.item < item_end) issue_loads(pre);
-    cp_async_commit();
-    pre = next_step(pre);
-  }
+  cp_async_commit();
 
-  uint4 hreg[4];                                           // my half of my distance-table row (fp16), kept per item
+  uint4 hreg[AT_HAV_PITCH / 8];                            // my distance-table row (fp16), kept across the item's heads
 #pragma unroll
-  for (int k = 0; k < 4; ++k) hreg[k] = make_uint4(0, 0, 0, 0);
+  for (int k = 0; k < AT_HAV_PITCH / 8; ++k) hreg[k] = make_uint4(0, 0, 0, 0);
   int hav_wp = -1;
 
   uint32_t par = 0;
+  long long ph[6] = {0, 0, 0, 0, 0, 0};
+  const bool prof = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
   while (cur.item < item_end) {
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+    if (prof) c0 = clock64();
+    const Step nxt = next_step(cur);
+    const bool has_next = nxt.item < item_end;
     const int my_w = 2 * cur.wp + unit;
     const bool row_valid = (ti < N) && (my_w < p.n_windows);
-    // ---- 0. token maps of the step about to be prefetched; my distance half-row of this pair
-    __syncthreads();         // everyone is done with the previous step's buffers / token maps / TMEM rows
-    const bool pre_ok = pre.item < item_end;
-    if (pre_ok && pre.wp > src_wp) { prep_src(pre.wp); src_wp = pre.wp; }
-    if (p.hav != nullptr && hav_wp != cur.wp) {
-      hav_wp = cur.wp;
-      if (row_valid) {
-        const uint4* grow = reinterpret_cast<const uint4*>(p.hav + ((size_t)(my_w % wpi) * N + ti) * AT_HAV_PITCH) + 3 * half;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < 3 + half) hreg[k] = __ldg(grow + k);
-      }
-    }
-    __syncthreads();         // the token maps are visible
-    // ---- 1. prefetch step cur + NS - 1 into the stage that the previous step just released; wait for this step
-    if (pre_ok) issue_loads(pre);
-    cp_async_commit();
-    pre = next_step(pre);
-    cp_async_wait<NS - 1>();
+    // ---- 1. this step's q/k/v + tables (requested one step ago) have landed; one barrier orders them, the
+    //         previous step's TMEM reads and the token maps prepared during the previous step
+    cp_async_wait<0>();
     fence_async_shared();
     __syncthreads();
 
+    if (prof) c1 = clock64();
     // ---- 2. S = Q . K^T (both units at once, block diagonal)
-    const uint32_t sq = smem_u32(bufs + (cur.n % NS) * AT_BUF_BYTES);
+    const uint32_t sq = smem_u32(bufs + (cur.n & 1) * AT_BUF_BYTES);
     if (tid == 0) {
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
@@ -407,26 +318,79 @@ window_attn_tc_kernel(const AttnParams p) {
       umma_ss(tmem_base, dq + 2, dk + 2, idesc, 1);        // head_dim 16..31: +32 B inside the swizzle row
       umma_commit(&bars[0]);
     }
+    // while the MMA runs: prefetch the WHOLE next step into the other stage (released by the previous step's PV
+    // MMA, which every thread has waited for) and fetch my distance row when the window pair changed
+    if (has_next) issue_loads(nxt);
+    cp_async_commit();
+    if (p.hav != nullptr && hav_wp != cur.wp) {
+      hav_wp = cur.wp;
+      if (row_valid) {
+        const uint4* grow = reinterpret_cast<const uint4*>(p.hav + ((size_t)(my_w % wpi) * N + ti) * AT_HAV_PITCH);
+#pragma unroll
+        for (int k = 0; k < AT_HAV_PITCH / 8; ++k) hreg[k] = __ldg(grow + k);
+      }
+    }
     mbar_wait(&bars[0], par);
     tc_fence_after();
 
-    // ---- 3. bias + softmax: two threads per row, 24 / 25 keys each
+    if (prof) c2 = clock64();
+    // ---- 3. bias + softmax on my row
+    float sum = 1.f;
     {
+      uint32_t sr[N];
       const uint32_t s_addr = tmem_base + lane_base + (uint32_t)(unit * 64);
-      const uint32_t p_addr = tmem_base + lane_base + AT_P_COL;
-      const float2* trow = tab + (cur.n % NS) * TABS + (ri + WS - 1) * TP + (ci + WS - 1);
+      {
+        static_assert(N == 49, "TMEM row load below is written for 49 logits");
+        uint32_t t32[32], t16[16], t1;
+        tmem_ld_x32(s_addr, t32);
+        tmem_ld_x16(s_addr + 32, t16);
+        tmem_ld_x1(s_addr + 48, t1);
+        tmem_ld_wait();                                    // one wait for the three loads
+#pragma unroll
+        for (int k = 0; k < 32; ++k) sr[k] = t32[k];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sr[32 + k] = t16[k];
+        sr[48] = t1;
+      }
+      const float2* trow = tab + (cur.n & 1) * TABS + (ri + WS - 1) * TP + (ci + WS - 1);
       const float* mrow = nullptr;
       if constexpr (HAS_MASK) mrow = p.mask + ((int64_t)((my_w < p.n_windows ? my_w : 0) % wpi) * N + ic) * N;
-      float part;
-      if (half == 0)
-        part = softmax_half<WS, 0, HAS_MASK>(s_addr, p_addr, hreg, trow, mrow, p.scale, row_valid, xch + row, q);
-      else
-        part = softmax_half<WS, 1, HAS_MASK>(s_addr, p_addr, hreg, trow, mrow, p.scale, row_valid, xch + 128 + row, q);
-      xch[256 + half * 128 + row] = part;
+      float t[N];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int jc = 0; jc < (N + 7) / 8; ++jc) {
+        const uint32_t hw[4] = {hreg[jc].x, hreg[jc].y, hreg[jc].z, hreg[jc].w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int j = 8 * jc + q;
+          if (j < N) {
+            const __half2 hh = *reinterpret_cast<const __half2*>(&hw[q >> 1]);
+            const float hv = (q & 1) ? __high2float(hh) : __low2float(hh);
+            const float2 ab = trow[-((j / WS) * TP + (j % WS))];
+            float bia = fmaf(hv, ab.x, ab.y);
+            if constexpr (HAS_MASK) bia += __ldg(mrow + j);
+            t[j] = fmaf(__uint_as_float(sr[j]), p.scale, bia);
+            mx = fmaxf(mx, t[j]);
+          }
+        }
+      }
+      const float mneg = -mx * LOG2E;
+      sum = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        float p0 = 0.f, p1 = 0.f;
+        if (2 * k < N) { p0 = fast_exp2(fmaf(t[2 * k], LOG2E, mneg)); sum += p0; }
+        if (2 * k + 1 < N) { p1 = fast_exp2(fmaf(t[2 * k + 1], LOG2E, mneg)); sum += p1; }
+        pk[k] = row_valid ? pack_bf16x2(p0, p1) : 0u;
+      }
+      tmem_st_x32(tmem_base + lane_base + AT_P_COL, pk);
+      tmem_st_wait();
     }
     tc_fence_before();
     __syncthreads();
 
+    if (prof) c3 = clock64();
     // ---- 4. O = P . [V_u0 | V_u1]
     if (tid == 0) {
       tc_fence_after();
@@ -439,20 +403,26 @@ window_attn_tc_kernel(const AttnParams p) {
       }
       umma_commit(&bars[1]);
     }
+    // while the MMA runs: token maps of the step after next (visible to its loader after the next barriers)
+    if (has_next) {
+      const Step nn = next_step(nxt);
+      if (nn.item < item_end && nn.wp > src_wp) { prep_src(nn.wp); src_wp = nn.wp; }
+    }
     mbar_wait(&bars[1], par);
     tc_fence_after();
 
-    // ---- 5. normalise and store my 16 output dims of the row at the token's un-shifted position
+    if (prof) c4 = clock64();
+    // ---- 5. normalise and store my output row at the token's un-shifted position
     {
-      uint32_t orow[16];
-      tmem_ld_x16v(tmem_base + lane_base + AT_O_COL + (uint32_t)(unit * 32 + half * 16), orow);
+      uint32_t orow[32];
+      tmem_ld_x32(tmem_base + lane_base + AT_O_COL + (uint32_t)(unit * 32), orow);
       tmem_ld_wait();
-      const int s = src[(cur.wp % NS) * 128 + unit * 64 + ic];
+      const int s = src[(cur.wp % 3) * 128 + unit * 64 + ic];
       if (row_valid && s >= 0) {
-        const float inv = 1.0f / (xch[256 + row] + xch[256 + 128 + row]);
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (int64_t)s * C + cur.e * 32 + half * 16);
+        const float inv = 1.0f / sum;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (int64_t)s * C + cur.e * 32);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint4 v;
           v.x = pack_bf16x2(__uint_as_float(orow[8 * c + 0]) * inv, __uint_as_float(orow[8 * c + 1]) * inv);
           v.y = pack_bf16x2(__uint_as_float(orow[8 * c + 2]) * inv, __uint_as_float(orow[8 * c + 3]) * inv);
@@ -463,9 +433,15 @@ window_attn_tc_kernel(const AttnParams p) {
       }
     }
     tc_fence_before();       // the next iteration's barrier orders these TMEM reads before the next S MMA
+    if (prof) {
+      const long long c5 = clock64();
+      ph[0] += c1 - c0; ph[1] += c2 - c1; ph[2] += c3 - c2; ph[3] += c4 - c3; ph[4] += c5 - c4; ph[5] += 1;
+    }
     par ^= 1;
-    cur = next_step(cur);
+    cur = nxt;
   }
+  if (prof)
+    for (int k = 0; k < 6; ++k) p.dbg[k] = ph[k];
 
   cp_async_wait<0>();
   tc_fence_before();
@@ -479,18 +455,40 @@ window_attn_tc_kernel(const AttnParams p) {
 static size_t attn_tc_smem_bytes(int ws, int C) {
   const int TW = 2 * ws - 1;
   size_t b = 1024;                                   // alignment slack
-  b += (size_t)AT_STAGES * AT_BUF_BYTES;
-  b += (size_t)AT_STAGES * TW * AT_TAB_PITCH * 8;
-  b += (size_t)AT_STAGES * 128 * 4;
-  b += 4 * 128 * 4;
+  b += 2 * AT_BUF_BYTES;
+  b += (size_t)2 * TW * AT_TAB_PITCH * 8;
+  b += 3 * 2 * 64 * 4;
   b += 2 * 8 + 16;
   (void)C;
-  return b;
+  // keep the CTA count per SM at AT_CTAS_PER_SM (register budget 65536 / (3 * 128) = 170 per thread)
+  const size_t floor_bytes = (size_t)(233472 / (AT_CTAS_PER_SM + 1)) - 1024 + 16;
+  return b < floor_bytes ? floor_bytes : b;
 }
 
-int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const float* qkv_bias,
-                   const void* hav_table, const float* mask, int B, int H, int W, int C, int heads, int window,
-                   int shift, int pano, float scale, cudaStream_t st) {
+// (alpha, beta)[idx][head] -> tables[head][row][AT_TAB_PITCH] float2, the shared-memory layout of the attention kernel
+__global__ void bias_tables_kernel(const float* __restrict__ alpha, const float* __restrict__ beta,
+                                   float2* __restrict__ out, int heads, int tw) {
+  const int n = heads * tw * AT_TAB_PITCH;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = i % AT_TAB_PITCH;
+    const int r = (i / AT_TAB_PITCH) % tw;
+    const int e = i / (AT_TAB_PITCH * tw);
+    float2 v = make_float2(0.f, 0.f);
+    if (c < tw) v = make_float2(alpha[(r * tw + c) * heads + e], beta[(r * tw + c) * heads + e]);
+    out[i] = v;
+  }
+}
+
+int window_bias_tables(const float* alpha, const float* beta, void* tables, int heads, int window, cudaStream_t st) {
+  const int tw = 2 * window - 1;
+  const int n = heads * tw * AT_TAB_PITCH;
+  bias_tables_kernel<<<(n + 255) / 256, 256, 0, st>>>(alpha, beta, (float2*)tables, heads, tw);
+  return launch_status("bias_tables_kernel");
+}
+
+int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const void* tables,
+                   const float* qkv_bias, const void* hav_table, const float* mask, int B, int H, int W, int C,
+                   int heads, int window, int shift, int pano, float scale, long long* dbg, cudaStream_t st) {
   PSW_REQUIRE(window == 7, PSW_ERR_UNSUPPORTED,
               "psw_window_attn_fwd(bf16): the tcgen05 kernel is instantiated for window 7 (every shipped PanoSwin config); got %d",
               window);
@@ -498,10 +496,11 @@ int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* 
               "psw_window_attn_fwd(bf16): pano mode needs the great-circle table (psw_window_hav_table)");
   AttnParams p;
   p.qkv = qkv; p.out = out; p.alpha = alpha; p.beta = beta; p.qkv_bias = qkv_bias;
+  p.tables = (const float2*)tables;
   p.hav = pano ? (const __half*)hav_table : nullptr;
   p.mask = mask;
   p.g = make_geom(H, W, window, shift, pano);
-  p.B = B; p.C = C; p.heads = heads; p.scale = scale;
+  p.B = B; p.C = C; p.heads = heads; p.scale = scale; p.dbg = dbg;
   p.hc = heads % 3 == 0 ? 3 : (heads % 4 == 0 ? 4 : (heads % 2 == 0 ? 2 : 1));
   p.n_windows = B * p.g.nWh * p.g.nWw;
   p.n_items = ((p.n_windows + 1) / 2) * (heads / p.hc);

@@ -67,7 +67,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   constexpr int TC_EPI_WARPS = EpiCfg<RES>::EW;
   constexpr int PER_QUAD = TC_EPI_WARPS / 4;                  // warps sharing one TMEM lane quadrant
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // align to 1024 B by OFFSETTING the __shared__ array (keeps the shared address space: LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t a_bytes = TC_BM * TC_BK * 2;                 // 16 KiB
   const uint32_t b_bytes = (uint32_t)block_n * TC_BK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;

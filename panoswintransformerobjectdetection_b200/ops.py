@@ -140,29 +140,41 @@ def window_hav_table(uv, window, shift):
     return table
 
 
+def window_bias_tables(alpha, beta, window):
+    """Per-head re-layout of the alpha/beta tables for the bf16 attention kernel: fp32 [heads, 2w-1, 24, 2]."""
+    dev = _chk(alpha, beta)
+    heads = alpha.shape[1]
+    out = torch.empty((heads, 2 * window - 1, 24, 2), dtype=torch.float32, device=alpha.device)
+    with torch.cuda.device(dev):
+        _call("psw_window_bias_tables", _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta")), _ptr(out), heads, window,
+              _stream(dev))
+    return out
+
+
 def window_attention(qkv, alpha, beta, qkv_bias, uv, mask, heads, window, shift, pano_mode, scale, out=None,
-                     impl=None, hav_table=None):
+                     impl=None, hav_table=None, bias_tables=None):
     """Fused shift + partition + W-MSA core + reverse + un-shift.  qkv [B, H, W, 3C] -> [B, H, W, C].
     fp32 tensors: CUDA-core parity kernel (needs `uv` in pano mode).  bf16 tensors: tcgen05 kernel (needs
     `hav_table` from window_hav_table() in pano mode; built on the fly from `uv` when omitted).
     `impl='simt'`: the CUDA-core kernel on bf16 tensors (cross-check)."""
-    dev = _chk(qkv, alpha, beta, qkv_bias, uv, mask, out, hav_table)
+    dev = _chk(qkv, alpha, beta, qkv_bias, uv, mask, out, hav_table, bias_tables)
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     if out is None:
         out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
     if pano_mode and qkv.dtype == torch.bfloat16 and impl is None and hav_table is None and uv is not None:
         hav_table = window_hav_table(uv, window, shift)
-    head = [_ptr(qkv), _ptr(out), _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta")), _ptr(_f32(qkv_bias, "qkv_bias")),
-            _ptr(_f32(uv, "uv"))]
+    head = [_ptr(qkv), _ptr(out), _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta"))]
+    mid = [_ptr(_f32(qkv_bias, "qkv_bias")), _ptr(_f32(uv, "uv"))]
     tail = [_ptr(_f32(mask, "mask")), B, H, W, C, heads, window, shift, 1 if pano_mode else 0, float(scale)]
     with torch.cuda.device(dev):
         if impl is None:
-            _call("psw_window_attn_fwd", *head, _ptr(hav_table), *tail, _dt(qkv), _stream(dev))
+            _call("psw_window_attn_fwd", *head, _ptr(_f32(bias_tables, "bias_tables")), *mid, _ptr(hav_table), *tail,
+                  _dt(qkv), _stream(dev))
         elif impl == "simt":
             if qkv.dtype != torch.bfloat16:
                 raise PanoSwinB200Error("impl='simt' is the bf16 cross-check kernel")
-            _call("psw_window_attn_fwd_simt_bf16", *head, *tail, _stream(dev))
+            _call("psw_window_attn_fwd_simt_bf16", *head, *mid, *tail, _stream(dev))
         else:
             raise PanoSwinB200Error(f"unknown impl {impl!r}")
     return out

@@ -150,7 +150,7 @@ def test_window_attention_fp32(ops, case, hd):
 
 
 @pytest.mark.parametrize("case", ATTN_CASES)
-@pytest.mark.parametrize("impl", [None, "simt"])
+@pytest.mark.parametrize("impl", [None, "tables", "simt"])
 def test_window_attention_bf16(ops, case, impl):
     H, W, heads, shift, pano = case
     qkv, alpha, beta, qb, uv, C = _attn_case(H, W, heads, 32, shift, pano, seed=5)
@@ -160,8 +160,9 @@ def test_window_attention_bf16(ops, case, impl):
     want = attention_core(qkv.float(), alpha, beta, qb.bfloat16().float() if impl != "simt" else qb, uv, H, W, heads, 7,
                           shift, pano, scale)
     mask = O.planar_shift_mask(H, W, 7, shift).to(DEV) if (not pano and shift) else None
+    bt = ops.window_bias_tables(alpha.to(DEV), beta.to(DEV), 7) if impl == "tables" else None
     got = ops.window_attention(qkv.to(DEV), alpha.to(DEV), beta.to(DEV), qb.to(DEV), uv.to(DEV) if pano else None, mask,
-                               heads, 7, shift, pano, scale, impl=impl)
+                               heads, 7, shift, pano, scale, impl="simt" if impl == "simt" else None, bias_tables=bt)
     torch.cuda.synchronize()
     assert got.dtype == torch.bfloat16 and torch.isfinite(got.float()).all()
     assert rel_l2(got.float(), want) <= 1e-2

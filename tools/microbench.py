@@ -38,8 +38,9 @@ def attn(iters):
         uv = make_uv_hw2(H, W).to(DEV)
         for shift in (0, 3):
             hav = ops.window_hav_table(uv, 7, shift)
+            bt = ops.window_bias_tables(alpha, beta, 7)
             us = time_op(lambda i: ops.window_attention(qkv[i], alpha, beta, qb, uv, None, heads, 7, shift, True, 32 ** -0.5,
-                                                        out=out[i], hav_table=hav), nb, iters)
+                                                        out=out[i], hav_table=hav, bias_tables=bt), nb, iters)
             byt = B * H * W * C * 8
             print(f"attn B{B} {H}x{W} C{C} h{heads} s{shift}: {us:8.1f} us  {byt / us / 1e3:7.0f} GB/s", flush=True)
 
@@ -84,3 +85,33 @@ if __name__ == "__main__":
         linear(iters)
     if what in ("ln", "all"):
         ln(iters)
+
+
+def attn_phases():
+    """Per-phase cycle breakdown of one CTA of the tcgen05 attention kernel (psw_window_attn_fwd_profile)."""
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    for (H, W, C, heads) in [(128, 256, 96, 3), (32, 64, 384, 12)]:
+        qkv = torch.randn(B, H, W, 3 * C, device=DEV).bfloat16()
+        out = torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16)
+        alpha = torch.randn(169, heads, device=DEV) * 0.1
+        beta = torch.randn(169, heads, device=DEV) * 0.1
+        qb = torch.randn(3 * C, device=DEV) * 0.1
+        uv = make_uv_hw2(H, W).to(DEV)
+        hav = ops.window_hav_table(uv, 7, 3)
+        ph = torch.zeros(6, dtype=torch.int64, device=DEV)
+        for _ in range(2):
+            rc = lib.psw_window_attn_fwd_profile(qkv.data_ptr(), out.data_ptr(), alpha.data_ptr(), beta.data_ptr(), qb.data_ptr(),
+                                                 hav.data_ptr(), B, H, W, C, heads, 7, 3, 32 ** -0.5, ph.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc, "profile")
+        torch.cuda.synchronize()
+        v = ph.tolist()
+        n = max(v[5], 1)
+        names = ["wait-loads", "S-mma", "softmax", "PV-mma", "store"]
+        print(f"attn phases {H}x{W} C{C}: steps {v[5]}  " + "  ".join(f"{nm} {v[i] / n:.0f}" for i, nm in enumerate(names)) +
+              f"  total/step {sum(v[:5]) / n:.0f} cyc", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "phases":
+    attn_phases()
