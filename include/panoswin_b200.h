@@ -85,9 +85,9 @@ PSW_API int psw_linear_fwd(const void* x, const void* w, const float* bias, cons
  *   qkv      [B, H, W, 3C]  output of the qkv linear on UN-shifted tokens, channel order (3, heads, hd)
  *   out      [B, H, W, C]   attention output (before proj), un-shifted token order
  *   alpha, beta [(2*window-1)^2, heads] fp32 tables (sphere_position_{alpha,beta}_table_Te)
- *   bias_tables optional (NULL allowed): alpha/beta re-laid-out per head by psw_window_bias_tables(); lets the
- *            PSW_BF16 kernel fetch a head's tables with contiguous 16-byte copies (weights are static at inference,
- *            so callers cache it per block)
+ *   bias_tables alpha/beta packed per head by psw_window_bias_tables() — required by the PSW_BF16 path (one
+ *            contiguous 2 KB block per head, fp16 pairs); weights are static at inference, so callers cache it
+ *            per block.  Ignored (may be NULL) on the PSW_F32 path, which reads alpha / beta directly
  *   qkv_bias [3C] fp32 or NULL — q/k/v of a zero (padding) token: padded cells take part as keys/values
  *   uv       [H, W, 2] fp32 token coordinates (make_uv_hw2 :153-189); used by the PSW_F32 path in pano mode
  *   hav_table fp16 great-circle distances of every window of one image, from psw_window_hav_table(); used by
@@ -115,8 +115,9 @@ PSW_API int psw_window_grid(int H, int W, int window, int pano_mode, int* nwh, i
  * Depends on (H, W, window, shift) only — not on batch, heads or weights (uv carries no gradient).
  */
 /*
- * (alpha, beta) [(2w-1)^2, heads] -> tables [heads][2w-1][24] float2 (alpha, beta), zero padded: the per-head
- * layout the PSW_BF16 attention kernel keeps in shared memory.  (2w-1)*24*8 bytes per head.
+ * (alpha, beta) [(2w-1)^2, heads] fp32 -> tables [heads][508] fp16x2 words (alpha, beta): entry (r, c) of the
+ * (2w-1) x (2w-1) table at word r*39 + c, zero padded — the per-head shared-memory image of the PSW_BF16 attention
+ * kernel.  2032 bytes per head.
  */
 PSW_API int psw_window_bias_tables(const float* alpha, const float* beta, void* tables, int heads, int window,
                                    void* stream);
@@ -146,11 +147,13 @@ PSW_API int psw_cast(const void* src, void* dst, int64_t n, int src_dtype, int d
  *   _simt_bf16  : the CUDA-core kernel on bf16 tensors (cross-check of the tensor-core kernel).
  */
 /* The bf16 pano kernel with per-phase SM-cycle totals of CTA 0 in phase_cycles[6] (device, int64):
- * {wait-for-loads, S MMA, softmax, P.V MMA, store, steps}. */
+ * {wait-for-loads, S MMA, softmax, P.V MMA, store, steps} (NULL allowed).  mode 1 = memory skeleton only: the same
+ * gathers and stores without MMA / softmax (output = q rows), to measure what the access pattern alone sustains. */
 PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, const float* alpha, const float* beta,
-                                        const float* qkv_bias, const void* hav_table, int B, int H, int W,
+                                        const void* bias_tables, const float* qkv_bias, const void* hav_table,
+                                        int B, int H, int W,
                                         int C, int heads, int window, int shift, float scale,
-                                        long long* phase_cycles, void* stream);
+                                        long long* phase_cycles, int mode, void* stream);
 /* Host-only: dump the kernels' window geometry (see psw_api.cu); map may be NULL to query hp / wp. */
 PSW_API int psw_debug_source_map(int H, int W, int window, int shift, int pano_mode, int* map, int capacity,
                                  int* hp, int* wp);

@@ -9,7 +9,7 @@ int window_attn_simt(const T* qkv, T* out, const float* alpha, const float* beta
                      int pano, float scale, cudaStream_t st);
 int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const void* tables,
                    const float* qkv_bias, const void* hav_table, const float* mask, int B, int H, int W, int C,
-                   int heads, int window, int shift, int pano, float scale, long long* dbg, cudaStream_t st);
+                   int heads, int window, int shift, int pano, float scale, long long* dbg, int mode, cudaStream_t st);
 int window_bias_tables(const float* alpha, const float* beta, void* tables, int heads, int window, cudaStream_t st);
 int window_hav_table(const float* uv, void* table, int H, int W, int window, int shift, cudaStream_t st);
 }  // namespace psw
@@ -47,7 +47,7 @@ extern "C" PSW_API int psw_window_attn_fwd(const void* qkv, void* out, const flo
   PSW_REQUIRE(aligned16(hav_table), PSW_ERR_BAD_ARG, "psw_window_attn_fwd(bf16): great-circle table must be 16-byte aligned");
   PSW_REQUIRE(aligned16(bias_tables), PSW_ERR_BAD_ARG, "psw_window_attn_fwd(bf16): bias tables must be 16-byte aligned");
   return window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, mask, B, H, W, C,
-                        heads, window, shift, pano_mode, scale, nullptr, st);
+                        heads, window, shift, pano_mode, scale, nullptr, 0, st);
 }
 
 extern "C" PSW_API int psw_window_bias_tables(const float* alpha, const float* beta, void* tables, int heads, int window,
@@ -58,16 +58,18 @@ extern "C" PSW_API int psw_window_bias_tables(const float* alpha, const float* b
 }
 
 // Diagnostics: same as the PSW_BF16 path of psw_window_attn_fwd, plus per-phase SM-cycle totals of CTA 0 written to
-// phase_cycles[6] (device memory): {wait-for-loads, S MMA, softmax, P.V MMA, store, steps}.
+// phase_cycles[6] (device memory, may be NULL): {wait-for-loads, S MMA, softmax, P.V MMA, store, steps}.
+// mode 1 runs the memory skeleton only (same gathers and stores, no MMA / softmax; output = q rows).
 extern "C" PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, const float* alpha, const float* beta,
-                                                   const float* qkv_bias, const void* hav_table, int B, int H, int W,
+                                                   const void* bias_tables, const float* qkv_bias,
+                                                   const void* hav_table, int B, int H, int W,
                                                    int C, int heads, int window, int shift, float scale,
-                                                   long long* phase_cycles, void* stream) {
+                                                   long long* phase_cycles, int mode, void* stream) {
   int rc = check_attn_args(qkv, out, alpha, beta, hav_table, B, H, W, C, heads, window, shift, 1);
   if (rc) return rc;
-  PSW_REQUIRE(phase_cycles != nullptr && C / heads == 32, PSW_ERR_BAD_ARG, "psw_window_attn_fwd_profile: bad arguments");
-  return window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, nullptr, qkv_bias, hav_table, nullptr, B, H, W, C, heads,
-                        window, shift, 1, scale, phase_cycles, (cudaStream_t)stream);
+  PSW_REQUIRE(C / heads == 32 && (mode == 0 || mode == 1), PSW_ERR_BAD_ARG, "psw_window_attn_fwd_profile: bad arguments");
+  return window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, nullptr, B, H, W, C,
+                        heads, window, shift, 1, scale, phase_cycles, mode, (cudaStream_t)stream);
 }
 
 extern "C" PSW_API int psw_window_grid(int H, int W, int window, int pano_mode, int* nwh, int* nww) {

@@ -18,9 +18,10 @@
 // stores at the token's UN-shifted position.  q/k/v rows are gathered with cp.async (16 B) straight from the
 // un-shifted [B,H,W,3C] qkv tensor into the 64B-swizzled UMMA layout: pano shift with longitude wrap-around,
 // the odd-W zero column, window padding (padding tokens = qkv bias) and partition are address arithmetic
-// (psw::source_token).  One q/k/v buffer per CTA: Q/K of the next step are prefetched as soon as the S MMA
-// has retired, V as soon as the PV MMA has retired; 4 CTAs per SM (TMEM 4 x 128 columns) overlap each
-// other's MMA / softmax / store phases.
+// (psw::source_token).  q/k/v
+// buffers are double-buffered per CTA: the whole next step is prefetched while the S MMA of the current one runs,
+// the row's bias is computed in the same window; 4 CTAs per SM (TMEM 4 x 128 columns) overlap each other's
+// MMA / softmax / store phases.
 //
 // Algorithmic HBM bytes per unit: 49 * 32 * 2 B * 4 (q, k, v read + o written) = 12,544 B.
 #include <cuda_fp16.h>
@@ -36,8 +37,10 @@ constexpr int AT_HAV_PITCH = 56;                   // halfs per distance-table r
 constexpr int AT_TMEM_COLS = 128;
 constexpr int AT_P_COL = 0;                        // P (bf16x2 packed): TMEM columns [0, 32)
 constexpr int AT_O_COL = 32;                       // O (fp32): TMEM columns [32, 96)
-constexpr int AT_CTAS_PER_SM = 3;                 // measured: 4 CTAs/SM (128 regs, no spills) is not faster
-constexpr int AT_TAB_PITCH = 24;                   // float2 entries per table row (13 used; 192 B rows = 12 x 16 B)
+constexpr int AT_CTAS_PER_SM = 4;                 // 128 registers per thread (no spills), 4 x 128 TMEM columns
+constexpr int AT_TAB_PITCH = 39;                   // half2 (alpha, beta) words per table row: 13 used; 39 = 7 mod 32 makes
+                                                   // the row-per-lane lookups bank-conflict-free
+constexpr int AT_TAB_WORDS = 508;                  // 13 * 39 = 507 words per head, padded to a multiple of 4 (16 B)
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& r) {
@@ -101,7 +104,7 @@ struct AttnParams {
   bf16* out;
   const float* alpha;
   const float* beta;
-  const float2* tables;   // [heads][2w-1][AT_TAB_PITCH] (alpha, beta) from psw_window_bias_tables, or nullptr
+  const __half2* tables;  // [heads][AT_TAB_WORDS] packed (alpha, beta) from psw_window_bias_tables
   const float* qkv_bias;
   const __half* hav;      // [wpi][N][56] or nullptr (planar mode: d == 0)
   const float* mask;
@@ -112,6 +115,7 @@ struct AttnParams {
   int n_items;            // ceil(n_windows / 2) * (heads / hc)
   float scale;
   long long* dbg;         // diagnostics: per-phase cycle totals of CTA 0 (nullptr in production)
+  int mode;               // diagnostics: 0 = normal, 1 = memory skeleton (same gathers and stores, no MMA / softmax)
 };
 
 // One pipeline step = one head of one window pair.
@@ -130,7 +134,7 @@ window_attn_tc_kernel(const AttnParams p) {
   constexpr int TW = 2 * WS - 1;                 // relative-position table width (13)
   constexpr int TAB = TW * TW;
   constexpr int TP = AT_TAB_PITCH;               // smem row pitch of the table: bank-conflict-free for row-per-lane reads
-  constexpr int TABS = TW * TP;                  // float2 entries per table slot
+  constexpr int TABS = AT_TAB_WORDS;             // half2 words per table slot
   static_assert(N <= 64, "window too large for the 64-row unit tile");
   static_assert(TP >= TW, "table pitch too small");
 
@@ -138,7 +142,7 @@ window_attn_tc_kernel(const AttnParams p) {
   // align to 1024 B by OFFSETTING the __shared__ array (keeps the shared address space: LDS/STS, not generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* bufs = smem;                                                  // [2 stages][3][128 x 64 B]
-  float2* tab = reinterpret_cast<float2*>(bufs + 2 * AT_BUF_BYTES);      // [2 stages][TABS] (alpha, beta)
+  __half2* tab = reinterpret_cast<__half2*>(bufs + 2 * AT_BUF_BYTES);    // [2 stages][TABS] packed (alpha, beta)
   int* src = reinterpret_cast<int*>(tab + 2 * TABS);                     // [3 slots][2 units][64]: this, next, next-next pair
   uint64_t* bars = reinterpret_cast<uint64_t*>(src + 3 * 2 * 64);        // [2]: S ready, O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
@@ -231,8 +235,6 @@ window_attn_tc_kernel(const AttnParams p) {
     const int row = (k >> 1) * 64 + t;
     ld_dst[k] = row * 64 + ((lc ^ ((row >> 1) & 3)) << 4);
   }
-  const int tab_o0 = 2 * ((tid / TW) * TP + (tid % TW));                           // table entries tid and tid + 128
-  const int tab_o1 = 2 * (((tid + AT_THREADS) / TW) * TP + ((tid + AT_THREADS) % TW));
   // gather all q/k/v rows and the per-head tables of step `st` into stage (st.n & 1)
   auto issue_loads = [&](const Step& st) {
     uint8_t* base = bufs + (st.n & 1) * AT_BUF_BYTES;
@@ -256,21 +258,8 @@ window_attn_tc_kernel(const AttnParams p) {
         }
       }
     }
-    float* trow = reinterpret_cast<float*>(tab + (st.n & 1) * TABS);
-    if (p.tables != nullptr) {
-      // pre-transposed tables: 7 x 16 B (14 entries, 13 used) per table row, one cp.async per thread
-      if (tid < TW * 7) {
-        const int o = (tid / 7) * TP + (tid % 7) * 2;                  // float2 index inside the head's table
-        cp_async16(tab + (st.n & 1) * TABS + o, p.tables + (size_t)st.e * TABS + o);
-      }
-    } else {
-      cp_async4(trow + tab_o0, p.alpha + tid * heads + st.e);
-      cp_async4(trow + tab_o0 + 1, p.beta + tid * heads + st.e);
-      if (tid + AT_THREADS < TAB) {
-        cp_async4(trow + tab_o1, p.alpha + (tid + AT_THREADS) * heads + st.e);
-        cp_async4(trow + tab_o1 + 1, p.beta + (tid + AT_THREADS) * heads + st.e);
-      }
-    }
+    // per-head tables: one contiguous 2032-byte block, 127 x 16 B
+    if (tid < TABS / 4) cp_async16(tab + (st.n & 1) * TABS + 4 * tid, p.tables + (size_t)st.e * TABS + 4 * tid);
   };
 
   Step cur = first_step(item_begin);
@@ -307,6 +296,25 @@ window_attn_tc_kernel(const AttnParams p) {
     __syncthreads();
 
     if (prof) c1 = clock64();
+    if (p.mode == 1) {
+      // memory skeleton: prefetch as usual, then copy my row's q chunk to the output position (64 B per row)
+      if (has_next) issue_loads(nxt);
+      cp_async_commit();
+      if (has_next) {
+        const Step nn = next_step(nxt);
+        if (nn.item < item_end && nn.wp > src_wp) { prep_src(nn.wp); src_wp = nn.wp; }
+      }
+      const int s = src[(cur.wp % 3) * 128 + unit * 64 + ic];
+      if (row_valid && s >= 0) {
+        const uint8_t* qrow = bufs + (cur.n & 1) * AT_BUF_BYTES + tid * 64;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (int64_t)s * C + cur.e * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[c] = *reinterpret_cast<const uint4*>(qrow + 16 * c);
+      }
+      __syncthreads();
+      cur = nxt;
+      continue;
+    }
     // ---- 2. S = Q . K^T (both units at once, block diagonal)
     const uint32_t sq = smem_u32(bufs + (cur.n & 1) * AT_BUF_BYTES);
     if (tid == 0) {
@@ -328,6 +336,29 @@ window_attn_tc_kernel(const AttnParams p) {
         const uint4* grow = reinterpret_cast<const uint4*>(p.hav + ((size_t)(my_w % wpi) * N + ti) * AT_HAV_PITCH);
 #pragma unroll
         for (int k = 0; k < AT_HAV_PITCH / 8; ++k) hreg[k] = __ldg(grow + k);
+      }
+    }
+    // still inside the MMA window: my row's bias d(i,j) * alpha[idx] + beta[idx] (+ mask) — independent of S.
+    // Table entries of one key row are fetched as a batch of 7 before they are consumed (LDS latency overlaps).
+    float bia[N];
+    {
+      const __half2* trow = tab + (cur.n & 1) * TABS + (ri + WS - 1) * TP + (ci + WS - 1);
+      const float* mrow = nullptr;
+      if constexpr (HAS_MASK) mrow = p.mask + ((int64_t)((my_w < p.n_windows ? my_w : 0) % wpi) * N + ic) * N;
+      const uint32_t* hw = reinterpret_cast<const uint32_t*>(hreg);
+#pragma unroll
+      for (int rj = 0; rj < WS; ++rj) {
+        __half2 ab[WS];
+#pragma unroll
+        for (int cj = 0; cj < WS; ++cj) ab[cj] = trow[-(rj * TP + cj)];
+#pragma unroll
+        for (int cj = 0; cj < WS; ++cj) {
+          const int j = rj * WS + cj;
+          const __half2 hh = *reinterpret_cast<const __half2*>(&hw[j >> 1]);
+          const float hv = (j & 1) ? __high2float(hh) : __low2float(hh);
+          bia[j] = fmaf(hv, __low2float(ab[cj]), __high2float(ab[cj]));
+          if constexpr (HAS_MASK) bia[j] += __ldg(mrow + j);
+        }
       }
     }
     mbar_wait(&bars[0], par);
@@ -352,27 +383,12 @@ window_attn_tc_kernel(const AttnParams p) {
         for (int k = 0; k < 16; ++k) sr[32 + k] = t16[k];
         sr[48] = t1;
       }
-      const float2* trow = tab + (cur.n & 1) * TABS + (ri + WS - 1) * TP + (ci + WS - 1);
-      const float* mrow = nullptr;
-      if constexpr (HAS_MASK) mrow = p.mask + ((int64_t)((my_w < p.n_windows ? my_w : 0) % wpi) * N + ic) * N;
       float t[N];
       float mx = -INFINITY;
 #pragma unroll
-      for (int jc = 0; jc < (N + 7) / 8; ++jc) {
-        const uint32_t hw[4] = {hreg[jc].x, hreg[jc].y, hreg[jc].z, hreg[jc].w};
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int j = 8 * jc + q;
-          if (j < N) {
-            const __half2 hh = *reinterpret_cast<const __half2*>(&hw[q >> 1]);
-            const float hv = (q & 1) ? __high2float(hh) : __low2float(hh);
-            const float2 ab = trow[-((j / WS) * TP + (j % WS))];
-            float bia = fmaf(hv, ab.x, ab.y);
-            if constexpr (HAS_MASK) bia += __ldg(mrow + j);
-            t[j] = fmaf(__uint_as_float(sr[j]), p.scale, bia);
-            mx = fmaxf(mx, t[j]);
-          }
-        }
+      for (int j = 0; j < N; ++j) {
+        t[j] = fmaf(__uint_as_float(sr[j]), p.scale, bia[j]);
+        mx = fmaxf(mx, t[j]);
       }
       const float mneg = -mx * LOG2E;
       sum = 0.f;
@@ -456,7 +472,8 @@ static size_t attn_tc_smem_bytes(int ws, int C) {
   const int TW = 2 * ws - 1;
   size_t b = 1024;                                   // alignment slack
   b += 2 * AT_BUF_BYTES;
-  b += (size_t)2 * TW * AT_TAB_PITCH * 8;
+  b += (size_t)2 * AT_TAB_WORDS * 4;
+  (void)TW;
   b += 3 * 2 * 64 * 4;
   b += 2 * 8 + 16;
   (void)C;
@@ -465,42 +482,46 @@ static size_t attn_tc_smem_bytes(int ws, int C) {
   return b < floor_bytes ? floor_bytes : b;
 }
 
-// (alpha, beta)[idx][head] -> tables[head][row][AT_TAB_PITCH] float2, the shared-memory layout of the attention kernel
+// (alpha, beta)[idx][head] fp32 -> tables[head][AT_TAB_WORDS] half2 (alpha, beta): entry (r, c) of the (2w-1)^2
+// table sits at word r * AT_TAB_PITCH + c — exactly the shared-memory image the attention kernel copies per head
 __global__ void bias_tables_kernel(const float* __restrict__ alpha, const float* __restrict__ beta,
-                                   float2* __restrict__ out, int heads, int tw) {
-  const int n = heads * tw * AT_TAB_PITCH;
+                                   __half2* __restrict__ out, int heads, int tw) {
+  const int n = heads * AT_TAB_WORDS;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int c = i % AT_TAB_PITCH;
-    const int r = (i / AT_TAB_PITCH) % tw;
-    const int e = i / (AT_TAB_PITCH * tw);
-    float2 v = make_float2(0.f, 0.f);
-    if (c < tw) v = make_float2(alpha[(r * tw + c) * heads + e], beta[(r * tw + c) * heads + e]);
-    out[i] = v;
+    const int e = i / AT_TAB_WORDS;
+    const int o = i - e * AT_TAB_WORDS;
+    const int r = o / AT_TAB_PITCH, c = o - r * AT_TAB_PITCH;
+    float a = 0.f, b = 0.f;
+    if (r < tw && c < tw) { a = alpha[(r * tw + c) * heads + e]; b = beta[(r * tw + c) * heads + e]; }
+    out[i] = __floats2half2_rn(a, b);
   }
 }
 
 int window_bias_tables(const float* alpha, const float* beta, void* tables, int heads, int window, cudaStream_t st) {
   const int tw = 2 * window - 1;
-  const int n = heads * tw * AT_TAB_PITCH;
-  bias_tables_kernel<<<(n + 255) / 256, 256, 0, st>>>(alpha, beta, (float2*)tables, heads, tw);
+  PSW_REQUIRE(tw * AT_TAB_PITCH <= AT_TAB_WORDS, PSW_ERR_UNSUPPORTED, "psw_window_bias_tables: window %d too large", window);
+  const int n = heads * AT_TAB_WORDS;
+  bias_tables_kernel<<<(n + 255) / 256, 256, 0, st>>>(alpha, beta, (__half2*)tables, heads, tw);
   return launch_status("bias_tables_kernel");
 }
 
 int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const void* tables,
                    const float* qkv_bias, const void* hav_table, const float* mask, int B, int H, int W, int C,
-                   int heads, int window, int shift, int pano, float scale, long long* dbg, cudaStream_t st) {
+                   int heads, int window, int shift, int pano, float scale, long long* dbg, int mode, cudaStream_t st) {
   PSW_REQUIRE(window == 7, PSW_ERR_UNSUPPORTED,
               "psw_window_attn_fwd(bf16): the tcgen05 kernel is instantiated for window 7 (every shipped PanoSwin config); got %d",
               window);
+  PSW_REQUIRE(tables != nullptr, PSW_ERR_BAD_ARG,
+              "psw_window_attn_fwd(bf16): needs the per-head bias tables (psw_window_bias_tables)");
   PSW_REQUIRE(!pano || hav_table, PSW_ERR_BAD_ARG,
               "psw_window_attn_fwd(bf16): pano mode needs the great-circle table (psw_window_hav_table)");
   AttnParams p;
   p.qkv = qkv; p.out = out; p.alpha = alpha; p.beta = beta; p.qkv_bias = qkv_bias;
-  p.tables = (const float2*)tables;
+  p.tables = (const __half2*)tables;
   p.hav = pano ? (const __half*)hav_table : nullptr;
   p.mask = mask;
   p.g = make_geom(H, W, window, shift, pano);
-  p.B = B; p.C = C; p.heads = heads; p.scale = scale; p.dbg = dbg;
+  p.B = B; p.C = C; p.heads = heads; p.scale = scale; p.dbg = dbg; p.mode = mode;
   p.hc = heads % 3 == 0 ? 3 : (heads % 4 == 0 ? 4 : (heads % 2 == 0 ? 2 : 1));
   p.n_windows = B * p.g.nWh * p.g.nWw;
   p.n_items = ((p.n_windows + 1) / 2) * (heads / p.hc);

@@ -141,10 +141,10 @@ def window_hav_table(uv, window, shift):
 
 
 def window_bias_tables(alpha, beta, window):
-    """Per-head re-layout of the alpha/beta tables for the bf16 attention kernel: fp32 [heads, 2w-1, 24, 2]."""
+    """Per-head packing of the alpha/beta tables for the bf16 attention kernel: fp16 [heads, 508, 2]."""
     dev = _chk(alpha, beta)
     heads = alpha.shape[1]
-    out = torch.empty((heads, 2 * window - 1, 24, 2), dtype=torch.float32, device=alpha.device)
+    out = torch.empty((heads, 508, 2), dtype=torch.float16, device=alpha.device)
     with torch.cuda.device(dev):
         _call("psw_window_bias_tables", _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta")), _ptr(out), heads, window,
               _stream(dev))
@@ -162,14 +162,17 @@ def window_attention(qkv, alpha, beta, qkv_bias, uv, mask, heads, window, shift,
     C = C3 // 3
     if out is None:
         out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
-    if pano_mode and qkv.dtype == torch.bfloat16 and impl is None and hav_table is None and uv is not None:
-        hav_table = window_hav_table(uv, window, shift)
+    if qkv.dtype == torch.bfloat16 and impl is None:
+        if pano_mode and hav_table is None and uv is not None:
+            hav_table = window_hav_table(uv, window, shift)
+        if bias_tables is None:
+            bias_tables = window_bias_tables(alpha, beta, window)
     head = [_ptr(qkv), _ptr(out), _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta"))]
     mid = [_ptr(_f32(qkv_bias, "qkv_bias")), _ptr(_f32(uv, "uv"))]
     tail = [_ptr(_f32(mask, "mask")), B, H, W, C, heads, window, shift, 1 if pano_mode else 0, float(scale)]
     with torch.cuda.device(dev):
         if impl is None:
-            _call("psw_window_attn_fwd", *head, _ptr(_f32(bias_tables, "bias_tables")), *mid, _ptr(hav_table), *tail,
+            _call("psw_window_attn_fwd", *head, _ptr(bias_tables), *mid, _ptr(hav_table), *tail,
                   _dt(qkv), _stream(dev))
         elif impl == "simt":
             if qkv.dtype != torch.bfloat16:

@@ -99,10 +99,11 @@ def attn_phases():
         qb = torch.randn(3 * C, device=DEV) * 0.1
         uv = make_uv_hw2(H, W).to(DEV)
         hav = ops.window_hav_table(uv, 7, 3)
+        bt = ops.window_bias_tables(alpha, beta, 7)
         ph = torch.zeros(6, dtype=torch.int64, device=DEV)
         for _ in range(2):
-            rc = lib.psw_window_attn_fwd_profile(qkv.data_ptr(), out.data_ptr(), alpha.data_ptr(), beta.data_ptr(), qb.data_ptr(),
-                                                 hav.data_ptr(), B, H, W, C, heads, 7, 3, 32 ** -0.5, ph.data_ptr(),
+            rc = lib.psw_window_attn_fwd_profile(qkv.data_ptr(), out.data_ptr(), alpha.data_ptr(), beta.data_ptr(), bt.data_ptr(), qb.data_ptr(),
+                                                 hav.data_ptr(), B, H, W, C, heads, 7, 3, 32 ** -0.5, ph.data_ptr(), 0,
                                                  torch.cuda.current_stream().cuda_stream)
             _lib.check(rc, "profile")
         torch.cuda.synchronize()
@@ -113,5 +114,30 @@ def attn_phases():
               f"  total/step {sum(v[:5]) / n:.0f} cyc", flush=True)
 
 
+def attn_skeleton(iters=20):
+    """The attention kernel's memory skeleton (gathers + stores only) vs the full kernel."""
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    for (H, W, C, heads) in [(128, 256, 96, 3), (64, 128, 192, 6), (32, 64, 384, 12)]:
+        nb = max(2, int(400e6 // (B * H * W * 4 * C * 2)) + 1)
+        qkv = [torch.randn(B, H, W, 3 * C, device=DEV).bfloat16() for _ in range(nb)]
+        out = [torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
+        alpha = torch.randn(169, heads, device=DEV) * 0.1
+        beta = torch.randn(169, heads, device=DEV) * 0.1
+        qb = torch.randn(3 * C, device=DEV) * 0.1
+        hav = ops.window_hav_table(make_uv_hw2(H, W).to(DEV), 7, 3)
+        bt = ops.window_bias_tables(alpha, beta, 7)
+        for mode in (1, 0):
+            def run(i):
+                rc = lib.psw_window_attn_fwd_profile(qkv[i].data_ptr(), out[i].data_ptr(), alpha.data_ptr(), beta.data_ptr(),
+                                                     bt.data_ptr(), qb.data_ptr(), hav.data_ptr(), B, H, W, C, heads, 7, 3, 32 ** -0.5, None,
+                                                     mode, torch.cuda.current_stream().cuda_stream)
+                _lib.check(rc, "profile")
+            us = time_op(run, nb, iters)
+            print(f"attn {'skeleton' if mode else 'full    '} {H}x{W} C{C}: {us:8.1f} us  {B * H * W * C * 8 / us / 1e3:7.0f} GB/s", flush=True)
+
+
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "phases":
     attn_phases()
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "skeleton":
+    attn_skeleton()
