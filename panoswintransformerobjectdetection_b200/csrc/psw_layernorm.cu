@@ -39,74 +39,81 @@ struct MergeRows {
   }
 };
 
-template <int VPL, int R, typename TI, typename TO, typename Rows>
+// LPR lanes cooperate on one row (LPR = 8, 16 or 32), each lane owns VPL 4-element vectors at vector indices
+// lane + LPR * k, so a group reads LPR * 16 B contiguous per request and every lane of the warp is busy even for
+// C = 96 (24 vectors: 8 lanes x 3).  A warp works on (32 / LPR) * U rows per iteration; all loads are issued before
+// the reductions (memory-level parallelism), statistics are two-pass in fp32 from registers.
+template <int LPR, int VPL, int U, typename TI, typename TO, typename Rows>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_rows_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ pos, int64_t pos_rows,
                       Rows rows, int Cout, float eps) {
-  // R rows per warp iteration: all loads of the R rows are issued before any reduction, so a warp keeps
-  // R * VPL 16-byte (fp32) / 8-byte (bf16) requests in flight instead of VPL.
+  constexpr int GROUPS = 32 / LPR;                 // rows per warp pass
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int sub = lane % LPR;                      // lane inside the row group
+  const int grp = lane / LPR;
   const int nvec = Cout >> 2;
   const int64_t nrows = rows.num_rows();
   const float inv_c = 1.0f / (float)Cout;
-  const int64_t stride = (int64_t)gridDim.x * LN_WARPS * R;
-  for (int64_t r0 = ((int64_t)blockIdx.x * LN_WARPS + warp) * R; r0 < nrows; r0 += stride) {
-    float v[R][VPL][4];
-    float s[R];
+  const int64_t rows_per_iter = (int64_t)GROUPS * U;
+  const int64_t stride = (int64_t)gridDim.x * LN_WARPS * rows_per_iter;
+  for (int64_t r0 = ((int64_t)blockIdx.x * LN_WARPS + warp) * rows_per_iter; r0 < nrows; r0 += stride) {
+    float v[U][VPL][4];
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      s[j] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * GROUPS + grp;
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
-        const int vec = lane + 32 * k;
-        v[j][k][0] = v[j][k][1] = v[j][k][2] = v[j][k][3] = 0.f;
-        if (vec < nvec && r0 + j < nrows) {
-          const int64_t off = rows.offset(r0 + j, vec);
-          if (off >= 0) load4(x + off, v[j][k]);
+        const int vec = sub + LPR * k;
+        v[u][k][0] = v[u][k][1] = v[u][k][2] = v[u][k][3] = 0.f;
+        if (vec < nvec && r < nrows) {
+          const int64_t off = rows.offset(r, vec);
+          if (off >= 0) load4(x + off, v[u][k]);
         }
       }
     }
+    float mean[U], rstd[U];
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
+    for (int u = 0; u < U; ++u) {
+      float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < VPL; ++k) s[j] += (v[j][k][0] + v[j][k][1]) + (v[j][k][2] + v[j][k][3]);
+      for (int k = 0; k < VPL; ++k) s += (v[u][k][0] + v[u][k][1]) + (v[u][k][2] + v[u][k][3]);
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      mean[u] = s * inv_c;
     }
-    float mean[R], rstd[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) mean[j] = warp_sum(s[j]) * inv_c;
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
+    for (int u = 0; u < U; ++u) {
       float q = 0.f;
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
-        if (lane + 32 * k < nvec) {
+        if (sub + LPR * k < nvec) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float d = v[j][k][e] - mean[j];
+            const float d = v[u][k][e] - mean[u];
             q += d * d;
           }
         }
       }
-      s[j] = q;
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      rstd[u] = rsqrtf(q * inv_c + eps);
     }
 #pragma unroll
-    for (int j = 0; j < R; ++j) rstd[j] = rsqrtf(warp_sum(s[j]) * inv_c + eps);
-#pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      const int vec = lane + 32 * k;
+      const int vec = sub + LPR * k;
       if (vec < nvec) {
         float g[4], b[4];
         load4(gamma + vec * 4, g);
         load4(beta + vec * 4, b);
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int64_t r = r0 + j;
+        for (int u = 0; u < U; ++u) {
+          const int64_t r = r0 + u * GROUPS + grp;
           if (r < nrows) {
             float o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = (v[j][k][e] - mean[j]) * rstd[j] * g[e] + b[e];
+            for (int e = 0; e < 4; ++e) o[e] = (v[u][k][e] - mean[u]) * rstd[u] * g[e] + b[e];
             if (pos) {
               float pp[4];
               load4(pos + (r % pos_rows) * Cout + vec * 4, pp);
@@ -124,28 +131,40 @@ layernorm_rows_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float*
 template <typename TI, typename TO, typename Rows>
 static int launch_ln(const TI* x, TO* y, const float* gamma, const float* beta, const float* pos, int64_t pos_rows,
                      Rows rows, int64_t nrows, int Cout, float eps, cudaStream_t st) {
-  int nvec = Cout / 4;
-  int vpl = (nvec + 31) / 32;
-  static const int kInst[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};   // instantiated vectors-per-lane
+  const int nvec = Cout / 4;
+  // lanes per row: the smallest of 8 / 16 / 32 that keeps at most 4 vectors per lane; wider rows use 32 lanes
+  int lpr = 8;
+  while (lpr < 32 && (nvec + lpr - 1) / lpr > 4) lpr <<= 1;
+  const int vpl = (nvec + lpr - 1) / lpr;
+  static const int kInst[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
   int inst = 32;
   for (int k = 9; k >= 0; --k)
     if (kInst[k] >= vpl) inst = kInst[k];
-  const int R = inst <= 2 ? 4 : (inst <= 6 ? 2 : 1);               // rows per warp iteration
-  int64_t want = (nrows + (int64_t)LN_WARPS * R - 1) / ((int64_t)LN_WARPS * R);
+  const int u = inst <= 4 ? 2 : 1;                               // rows in flight per lane group
+  const int64_t rows_per_block = (int64_t)LN_WARPS * (32 / lpr) * u;
+  int64_t want = (nrows + rows_per_block - 1) / rows_per_block;
   int64_t cap = (int64_t)num_sms() * 16;
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
-#define PSW_LN_CASE(V, RR)                                                                                       \
-  case V:                                                                                                        \
-    layernorm_rows_kernel<V, RR, TI, TO, Rows><<<blocks, LN_WARPS * 32, 0, st>>>(x, y, gamma, beta, pos, pos_rows, \
-                                                                                 rows, Cout, eps);               \
-    break;
-  switch (inst) {
-    PSW_LN_CASE(1, 4) PSW_LN_CASE(2, 4) PSW_LN_CASE(3, 2) PSW_LN_CASE(4, 2) PSW_LN_CASE(6, 2) PSW_LN_CASE(8, 1)
-    PSW_LN_CASE(12, 1) PSW_LN_CASE(16, 1) PSW_LN_CASE(24, 1) PSW_LN_CASE(32, 1)
+#define PSW_LN_LAUNCH(L, V, UU)                                                                                    \
+  layernorm_rows_kernel<L, V, UU, TI, TO, Rows><<<blocks, LN_WARPS * 32, 0, st>>>(x, y, gamma, beta, pos, pos_rows, \
+                                                                                 rows, Cout, eps)
+  if (lpr == 8) {
+    switch (inst) { case 1: PSW_LN_LAUNCH(8, 1, 2); break; case 2: PSW_LN_LAUNCH(8, 2, 2); break;
+                    case 3: PSW_LN_LAUNCH(8, 3, 2); break; default: PSW_LN_LAUNCH(8, 4, 2); break; }
+  } else if (lpr == 16) {
+    switch (inst) { case 1: PSW_LN_LAUNCH(16, 1, 2); break; case 2: PSW_LN_LAUNCH(16, 2, 2); break;
+                    case 3: PSW_LN_LAUNCH(16, 3, 2); break; default: PSW_LN_LAUNCH(16, 4, 2); break; }
+  } else {
+    switch (inst) {
+      case 1: PSW_LN_LAUNCH(32, 1, 2); break; case 2: PSW_LN_LAUNCH(32, 2, 2); break; case 3: PSW_LN_LAUNCH(32, 3, 2); break;
+      case 4: PSW_LN_LAUNCH(32, 4, 2); break; case 6: PSW_LN_LAUNCH(32, 6, 1); break; case 8: PSW_LN_LAUNCH(32, 8, 1); break;
+      case 12: PSW_LN_LAUNCH(32, 12, 1); break; case 16: PSW_LN_LAUNCH(32, 16, 1); break;
+      case 24: PSW_LN_LAUNCH(32, 24, 1); break; default: PSW_LN_LAUNCH(32, 32, 1); break;
+    }
   }
-#undef PSW_LN_CASE
-  (void)R;
+#undef PSW_LN_LAUNCH
+  (void)u;
   return launch_status("layernorm_rows_kernel");
 }
 
