@@ -120,6 +120,10 @@ def launch_work(fn, a):
     if fn == "psw_layernorm_nchw_fwd":
         B, HW, C = a[4], a[5], a[6]
         return dict(kind="layernorm_nchw", shape=f"B{B} HW{HW} C{C}", bytes=float(B * HW * C * (sz[a[8]] + 4)), flops=8.0 * B * HW * C)
+    if fn == "psw_stem_conv3x3_relu_fwd":
+        B, H, W, cin, cout = a[4], a[5], a[6], a[7], a[8]
+        return dict(kind="stem_conv1", shape=f"B{B} {H}x{W} {cin}->{cout}", bytes=float(B * H * W * (cin * 4 + cout * 2)),
+                    flops=2.0 * B * H * W * cin * 9 * cout)
     return dict(kind=fn, shape="", bytes=0.0, flops=0.0)
 
 

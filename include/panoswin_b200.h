@@ -139,6 +139,16 @@ PSW_API int psw_patch_merge_ln_fwd(const void* x, void* y, const float* gamma, c
 PSW_API int psw_layernorm_nchw_fwd(const void* x, float* y, const float* gamma, const float* beta,
                            int B, int64_t HW, int C, float eps, int in_dtype, void* stream);
 
+/*
+ * Stem, first layer: conv3x3(cin -> cout, padding 1) + eval-mode BatchNorm + ReLU (PatchEmbed.proj[0..2], reference
+ * :743-745) on tcgen05.  img [B, cin, H, W] fp32 NCHW -> out [B, H, W, cout] bf16 NHWC.  w_folded [cout, cin*9]
+ * (k = c*9 + ky*3 + kx) and bias_folded [cout] are the fp32 weights / bias with BatchNorm folded in:
+ * w * g/sqrt(var+eps), (b - mean) * g/sqrt(var+eps) + beta.  Built for cin = 3, cout = 32 (embed_dim 96);
+ * other widths return PSW_ERR_UNSUPPORTED and the caller keeps its library convolution.
+ */
+PSW_API int psw_stem_conv3x3_relu_fwd(const float* img, const float* w_folded, const float* bias_folded, void* out,
+                                      int B, int H, int W, int cin, int cout, void* stream);
+
 /* dtype conversion helper for activations entering / leaving the bf16 path: n elements. */
 PSW_API int psw_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
 

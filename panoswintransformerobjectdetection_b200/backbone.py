@@ -402,25 +402,36 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             return w, b
         key = ("stem", tuple(p._version for p in pe.proj.parameters()), bn1.running_mean._version, bn2.running_mean._version)
         if self._weight_cache.get("stem_key") != key:
+            s1 = bn1.weight / torch.sqrt(bn1.running_var + bn1.eps)
             self._weight_cache["stem"] = (folded(conv1, bn1), folded(conv2, bn2),
                                           (conv3.weight.to(torch.bfloat16).contiguous(memory_format=torch.channels_last),
-                                           conv3.bias.to(torch.bfloat16)))
+                                           conv3.bias.to(torch.bfloat16)),
+                                          ((conv1.weight * s1[:, None, None, None]).reshape(conv1.out_channels, -1).float().contiguous(),
+                                           ((conv1.bias - bn1.running_mean) * s1 + bn1.bias).float().contiguous()))
             self._weight_cache["stem_key"] = key
-        (w1, b1), (w2, b2), (w3, b3) = self._weight_cache["stem"]
-        y = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        (w1, b1), (w2, b2), (w3, b3), (w1f, b1f) = self._weight_cache["stem"]
+        own_conv1 = conv1.in_channels == 3 and conv1.out_channels == 32       # libpanoswin_b200 tcgen05 conv (E = 96)
+        if own_conv1:
+            # fp32 NCHW image -> bf16 NHWC, seen by the next convolution as a channels-last NCHW tensor (no copy)
+            y = ops.stem_conv3x3_relu(x.contiguous(), w1f, b1f).permute(0, 3, 1, 2)
+        else:
+            y = x.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         if self._fused_conv_relu is None:                   # cuDNN's fused conv+bias+ReLU, probed once
             try:
-                t = torch.cudnn_convolution_relu(y[:1, :, :8, :8].contiguous(memory_format=torch.channels_last), w1, b1,
+                pw, pb = (w2, b2) if own_conv1 else (w1, b1)
+                t = torch.cudnn_convolution_relu(y[:1, :, :8, :8].contiguous(memory_format=torch.channels_last), pw, pb,
                                                  (1, 1), (1, 1), (1, 1), 1)
-                ref = F.relu(F.conv2d(y[:1, :, :8, :8], w1, b1, padding=1))
+                ref = F.relu(F.conv2d(y[:1, :, :8, :8], pw, pb, padding=1))
                 self._fused_conv_relu = bool(torch.allclose(t.float(), ref.float(), atol=2e-2, rtol=2e-2))
             except (RuntimeError, AttributeError):
                 self._fused_conv_relu = False
         if self._fused_conv_relu:
-            y = torch.cudnn_convolution_relu(y, w1, b1, (1, 1), (1, 1), (1, 1), 1)
+            if not own_conv1:
+                y = torch.cudnn_convolution_relu(y, w1, b1, (1, 1), (1, 1), (1, 1), 1)
             y = torch.cudnn_convolution_relu(y, w2, b2, (1, 1), (1, 1), (1, 1), 1)
         else:
-            y = F.relu_(F.conv2d(y, w1, b1, padding=1))
+            if not own_conv1:
+                y = F.relu_(F.conv2d(y, w1, b1, padding=1))
             y = F.relu_(F.conv2d(y, w2, b2, padding=1))
         y = F.conv2d(y, w3, b3, stride=pe.patch_size)
         return y.permute(0, 2, 3, 1).contiguous()          # no copy when the conv output is channels-last

@@ -46,6 +46,22 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
   return 0;
 }
 
+int make_tensor_map_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, int elem_bytes, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn enc = get_encode_tiled();
+  PSW_REQUIRE(enc != nullptr, PSW_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  PSW_REQUIRE(rank >= 1 && rank <= 5, PSW_ERR_BAD_ARG, "tensor map rank %d", rank);
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];      // strides of dims 1..rank-1
+  CUresult r = enc(map, dt, (cuuint32_t)rank, const_cast<void*>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PSW_REQUIRE(r == CUDA_SUCCESS, PSW_ERR_DRIVER, "cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, (int)r);
+  return 0;
+}
+
 template <typename S, typename D>
 __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n4) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

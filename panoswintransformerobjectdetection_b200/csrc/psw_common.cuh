@@ -322,4 +322,14 @@ EncodeTiledFn get_encode_tiled();
 int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                        uint32_t box_cols, int elem_bytes, CUtensorMapSwizzle swizzle);
 
+// rank-N tiled tensor map: dims / box innermost first; strides_bytes[i] = byte stride of dimension i + 1
+int make_tensor_map_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, int elem_bytes, CUtensorMapSwizzle swizzle);
+
+// TMA: 4-D tiled store shared -> global
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 }  // namespace psw

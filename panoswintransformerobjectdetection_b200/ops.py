@@ -209,6 +209,21 @@ def layernorm_nchw(x, gamma, beta, H, W, eps=1e-5):
     return out
 
 
+def stem_conv3x3_relu(img, w_folded, bias_folded):
+    """conv3x3(pad 1) + folded BatchNorm + ReLU: fp32 NCHW image [B, 3, H, W] -> bf16 NHWC [B, H, W, 32]
+    (reference PatchEmbed.proj[0..2], :743-745).  w_folded [32, 27], bias_folded [32] fp32."""
+    dev = _chk(img, w_folded, bias_folded)
+    B, cin, H, W = img.shape
+    cout = w_folded.shape[0]
+    if img.dtype != torch.float32:
+        raise PanoSwinB200Error("stem_conv3x3_relu wants an fp32 image")
+    out = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=img.device)
+    with torch.cuda.device(dev):
+        _call("psw_stem_conv3x3_relu_fwd", _ptr(img), _ptr(_f32(w_folded, "w_folded")), _ptr(_f32(bias_folded, "bias_folded")),
+              _ptr(out), B, H, W, cin, cout, _stream(dev))
+    return out
+
+
 def cast(x, dtype):
     dev = _chk(x)
     out = torch.empty(x.shape, dtype=dtype, device=x.device)

@@ -191,3 +191,28 @@ def test_errors_are_loud(ops):
         ops.window_attention(qkv, t, t, None, torch.zeros(14, 28, 2, device=DEV), None, 1, 7, 0, True, 1.0)
     with pytest.raises(PanoSwinB200Error):
         ops.window_attention(qkv.float(), t, t, None, torch.zeros(14, 28, 2, device=DEV), None, 1, 7, 7, True, 1.0)   # shift >= window
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 64, 128), (1, 3, 52, 100), (1, 3, 9, 68), (3, 3, 16, 64), (1, 3, 20, 260)])
+def test_stem_conv3x3_relu(ops, shape):
+    """tcgen05 stem conv (3 -> 32) + folded BN + ReLU against fp32 conv on the bf16-rounded operands."""
+    B, _, H, W = shape
+    g = _g(H + W)
+    img = torch.rand(shape, generator=g)
+    w = torch.randn(32, 3, 3, 3, generator=g) / 27 ** 0.5
+    b = torch.randn(32, generator=g) * 0.1
+    wq = w.bfloat16().float()
+    want = F.relu(F.conv2d(img.bfloat16().float(), wq, b, padding=1)).permute(0, 2, 3, 1)
+    got = ops.stem_conv3x3_relu(img.to(DEV), w.reshape(32, 27).to(DEV), b.to(DEV))
+    torch.cuda.synchronize()
+    assert got.shape == (B, H, W, 32) and got.dtype == torch.bfloat16
+    assert rel_l2(got.float(), want) <= 4e-3
+
+
+def test_stem_conv_rejects_unsupported_shapes(ops):
+    from panoswintransformerobjectdetection_b200.ops import PanoSwinB200Error
+    w, b = torch.zeros(32, 27, device=DEV), torch.zeros(32, device=DEV)
+    with pytest.raises(PanoSwinB200Error):                      # W must be a multiple of 4
+        ops.stem_conv3x3_relu(torch.zeros(1, 3, 8, 70, device=DEV), w, b)
+    with pytest.raises(PanoSwinB200Error):                      # built for 3 -> 32 channels
+        ops.stem_conv3x3_relu(torch.zeros(1, 3, 8, 64, device=DEV), torch.zeros(48, 27, device=DEV), torch.zeros(48, device=DEV))
