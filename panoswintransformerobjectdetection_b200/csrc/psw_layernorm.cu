@@ -185,59 +185,64 @@ static int dispatch_ln(const void* x, void* y, const float* gamma, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// LayerNorm + NHWC -> NCHW (fp32 out).  A CTA owns TT consecutive tokens of one image: each warp reads whole rows
-// once (CPL channels per lane in registers, 128-byte coalesced requests), normalises them into a [C][TT+1] shared
-// tile, then every warp streams whole channels out as TT*4-byte contiguous runs.
+// LayerNorm + NHWC -> NCHW (fp32 out).  A CTA owns TT consecutive tokens of one image.  Phase 1 is the row kernel
+// above (LPR lanes per row, 16-byte loads, two-pass fp32 statistics) writing the normalised row into a token-major
+// shared tile [TT][C + 1] (odd pitch: the scalar stores of phase 1 and the column reads of phase 2 are both
+// bank-conflict-free).  Phase 2: every warp streams whole channels out, TT * 4 contiguous bytes per channel.
 // ---------------------------------------------------------------------------------------------------
-template <typename TI, int CPL>
+template <int LPR, int VPL, typename TI>
 __global__ void __launch_bounds__(256)
 layernorm_nchw_kernel(const TI* __restrict__ x, float* __restrict__ y, const float* __restrict__ gamma,
                       const float* __restrict__ beta, int64_t HW, int C, int TT, float eps) {
-  extern __shared__ float tile[];                 // [C][TT + 1]
-  const int P = TT + 1;
+  extern __shared__ float tile[];                 // [TT][C + 1]
+  constexpr int GROUPS = 32 / LPR;
+  const int P = C + 1;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const int nvec = C >> 2;
   const int64_t tiles_per_img = (HW + TT - 1) / TT;
   const int b = (int)(blockIdx.x / tiles_per_img);
   const int64_t t0 = (blockIdx.x % tiles_per_img) * TT;
   const float inv_c = 1.0f / (float)C;
-  float g[CPL], bt[CPL];
+  for (int rr = warp * GROUPS + grp; rr < TT; rr += 8 * GROUPS) {
+    const int64_t t = t0 + rr;
+    float v[VPL][4];
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) {
-    const int c = lane + 32 * k;
-    g[k] = c < C ? gamma[c] : 0.f;
-    bt[k] = c < C ? beta[c] : 0.f;
-  }
-  for (int rr = warp; rr < TT; rr += 16) {        // two rows in flight per warp
-    float v[2][CPL];
+    for (int k = 0; k < VPL; ++k) {
+      const int vec = sub + LPR * k;
+      v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
+      if (vec < nvec && t < HW) load4(x + ((int64_t)b * HW + t) * C + vec * 4, v[k]);
+    }
+    float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int64_t t = t0 + rr + 8 * j;
-      const TI* row = x + ((int64_t)b * HW + t) * C;
+    for (int k = 0; k < VPL; ++k) s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) {
-        const int c = lane + 32 * k;
-        v[j][k] = (rr + 8 * j < TT && t < HW && c < C) ? to_f32(row[c]) : 0.f;
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      if (sub + LPR * k < nvec) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float d = v[k][e] - mean;
+          q += d * d;
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (rr + 8 * j >= TT || t0 + rr + 8 * j >= HW) continue;
-      float s = 0.f;
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_c + eps);
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) s += v[j][k];
-      const float mean = warp_sum(s) * inv_c;
-      float q = 0.f;
+    for (int k = 0; k < VPL; ++k) {
+      const int vec = sub + LPR * k;
+      if (vec < nvec) {
+        float g[4], bt[4];
+        load4(gamma + vec * 4, g);
+        load4(beta + vec * 4, bt);
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) {
-        const float d = (lane + 32 * k < C) ? v[j][k] - mean : 0.f;
-        q += d * d;
-      }
-      const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) {
-        const int c = lane + 32 * k;
-        if (c < C) tile[c * P + rr + 8 * j] = (v[j][k] - mean) * rstd * g[k] + bt[k];
+        for (int e = 0; e < 4; ++e) tile[rr * P + vec * 4 + e] = (v[k][e] - mean) * rstd * g[e] + bt[e];
       }
     }
   }
@@ -245,8 +250,44 @@ layernorm_nchw_kernel(const TI* __restrict__ x, float* __restrict__ y, const flo
   for (int c = warp; c < C; c += 8) {
     float* dst = y + ((int64_t)b * C + c) * HW + t0;
     for (int seg = lane; seg < TT; seg += 32)
-      if (t0 + seg < HW) dst[seg] = tile[c * P + seg];
+      if (t0 + seg < HW) dst[seg] = tile[seg * P + c];
   }
+}
+
+template <typename TI>
+static int launch_nchw(const TI* x, float* y, const float* gamma, const float* beta, int B, int64_t HW, int C, float eps,
+                       cudaStream_t st) {
+  PSW_REQUIRE(C % 4 == 0, PSW_ERR_UNSUPPORTED, "psw_layernorm_nchw_fwd: C=%d must be a multiple of 4", C);
+  const int nvec = C / 4;
+  int lpr = 8;
+  while (lpr < 32 && (nvec + lpr - 1) / lpr > 4) lpr <<= 1;
+  const int vpl = (nvec + lpr - 1) / lpr;
+  // tokens per tile: as wide as ~56 KiB of shared memory allows, 32..128
+  int TT = 128;
+  while (TT > 32 && (size_t)TT * (C + 1) * sizeof(float) > 56 * 1024) TT >>= 1;
+  const size_t smem = (size_t)TT * (C + 1) * sizeof(float);
+  PSW_REQUIRE(smem <= 200 * 1024 && vpl <= 8, PSW_ERR_UNSUPPORTED, "psw_layernorm_nchw_fwd: C=%d too large", C);
+  const int64_t blocks = (int64_t)B * ((HW + TT - 1) / TT);
+  PSW_REQUIRE(blocks < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_layernorm_nchw_fwd: too many tiles");
+#define PSW_NCHW_LAUNCH(L, V)                                                                                    \
+  do {                                                                                                           \
+    auto kern = layernorm_nchw_kernel<L, V, TI>;                                                                 \
+    PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));               \
+    kern<<<(unsigned)blocks, 256, smem, st>>>(x, y, gamma, beta, HW, C, TT, eps);                               \
+  } while (0)
+  if (lpr == 8) {
+    switch (vpl) { case 1: PSW_NCHW_LAUNCH(8, 1); break; case 2: PSW_NCHW_LAUNCH(8, 2); break;
+                   case 3: PSW_NCHW_LAUNCH(8, 3); break; default: PSW_NCHW_LAUNCH(8, 4); break; }
+  } else if (lpr == 16) {
+    switch (vpl) { case 1: PSW_NCHW_LAUNCH(16, 1); break; case 2: PSW_NCHW_LAUNCH(16, 2); break;
+                   case 3: PSW_NCHW_LAUNCH(16, 3); break; default: PSW_NCHW_LAUNCH(16, 4); break; }
+  } else {
+    switch (vpl) { case 1: PSW_NCHW_LAUNCH(32, 1); break; case 2: PSW_NCHW_LAUNCH(32, 2); break;
+                   case 3: PSW_NCHW_LAUNCH(32, 3); break; case 4: PSW_NCHW_LAUNCH(32, 4); break;
+                   case 5: case 6: PSW_NCHW_LAUNCH(32, 6); break; default: PSW_NCHW_LAUNCH(32, 8); break; }
+  }
+#undef PSW_NCHW_LAUNCH
+  return launch_status("layernorm_nchw_kernel");
 }
 
 }  // namespace psw
@@ -277,33 +318,6 @@ extern "C" PSW_API int psw_patch_merge_ln_fwd(const void* x, void* y, const floa
   MergeRows mr{B, H, W, C, (H + 1) / 2, (W + 1) / 2};
   int64_t nrows = (int64_t)B * mr.H2 * mr.W2;
   return dispatch_ln(x, y, gamma, beta, nullptr, 1, mr, nrows, 4 * C, eps, in_dtype, out_dtype, (cudaStream_t)stream);
-}
-
-template <typename TI>
-static int launch_nchw(const TI* x, float* y, const float* gamma, const float* beta, int B, int64_t HW, int C, float eps,
-                       cudaStream_t st) {
-  const int cpl = (C + 31) / 32;
-  // tokens per tile: as wide as ~48 KiB of shared memory allows, 32..128
-  int TT = 128;
-  while (TT > 32 && (size_t)C * (TT + 1) * sizeof(float) > 56 * 1024) TT >>= 1;
-  const size_t smem = (size_t)C * (TT + 1) * sizeof(float);
-  PSW_REQUIRE(smem <= 200 * 1024 && cpl <= 32, PSW_ERR_UNSUPPORTED, "psw_layernorm_nchw_fwd: C=%d too large", C);
-  const int64_t blocks = (int64_t)B * ((HW + TT - 1) / TT);
-  PSW_REQUIRE(blocks < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_layernorm_nchw_fwd: too many tiles");
-#define PSW_NCHW_CASE(V)                                                                                          \
-  case V: {                                                                                                       \
-    auto kern = layernorm_nchw_kernel<TI, V>;                                                                     \
-    PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
-    kern<<<(unsigned)blocks, 256, smem, st>>>(x, y, gamma, beta, HW, C, TT, eps);                                \
-    break;                                                                                                        \
-  }
-  int inst = cpl <= 1 ? 1 : cpl <= 2 ? 2 : cpl <= 3 ? 3 : cpl <= 4 ? 4 : cpl <= 6 ? 6 : cpl <= 8 ? 8 : cpl <= 12 ? 12 : cpl <= 16 ? 16 : cpl <= 24 ? 24 : 32;
-  switch (inst) {
-    PSW_NCHW_CASE(1) PSW_NCHW_CASE(2) PSW_NCHW_CASE(3) PSW_NCHW_CASE(4) PSW_NCHW_CASE(6) PSW_NCHW_CASE(8)
-    PSW_NCHW_CASE(12) PSW_NCHW_CASE(16) PSW_NCHW_CASE(24) PSW_NCHW_CASE(32)
-  }
-#undef PSW_NCHW_CASE
-  return launch_status("layernorm_nchw_kernel");
 }
 
 extern "C" PSW_API int psw_layernorm_nchw_fwd(const void* x, float* y, const float* gamma, const float* beta, int B,

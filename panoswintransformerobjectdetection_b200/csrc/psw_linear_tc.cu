@@ -199,6 +199,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       mbar_wait(&tail->tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * acc_stride;
+      if (first >= n_chunks) {                               // no chunk for this warp in this tile: release at once
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->tempty[acc]);
+      }
       for (int c = first; c < n_chunks; c += PER_QUAD) {
         float v[CW];
         if constexpr (CW == 32) {
@@ -213,6 +218,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        }
+        if (c + PER_QUAD >= n_chunks) {                       // my last read of this accumulator: hand it back to the
+          tc_fence_before();                                  // MMA warp now, the math / stores below no longer need it
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tail->tempty[acc]);
         }
         const int col = col0 + c * CW;
         if (bias) {
@@ -280,9 +290,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
         }
         ++out_cnt;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tail->tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait<0>();                       // all stores of this warp are complete

@@ -142,3 +142,20 @@ def test_bf16_residual_stream_option():
     outs = m(img.to(DEV))
     for o, w in zip(outs, want):
         assert o.dtype == torch.float32 and rel_l2(o, w) <= 3e-2
+
+
+def test_panoswin_b_shaped_config_matches_oracle():
+    """BASELINE.json config 4 family: embed_dim 128, heads (4, 8, 16, 32) — other GEMM tile widths (128 .. 1024
+    channels), four heads per work item in the attention kernel, and the library-conv stem fallback (42 channels)."""
+    cfg = O.make_config(embed_dim=128, depths=(2, 2, 2, 2), num_heads=(4, 8, 16, 32))
+    sd = O.make_state_dict(cfg, 7)
+    img = O.make_image((1, 3, 224, 448), 5)
+    want, want_blocks = O.backbone_forward(sd, cfg, img, return_blocks=True)
+    m = _build(cfg, sd, "fp32")
+    for o, w in zip(m(img.to(DEV)), want):
+        assert rel_l2(o, w) <= fp32_tol(o)
+    m.set_compute_dtype("bf16")
+    outs = m(img.to(DEV))
+    torch.cuda.synchronize()
+    for o, w in zip(outs, want):
+        assert rel_l2(o, w) <= 2e-2
