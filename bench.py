@@ -318,9 +318,9 @@ def run_ours(args):
         hb = k["bound"] == "hbm"
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.isfile(tpath):
+        if os.path.isfile(tpath):                          # ncu dram__bytes_read+write per launch (tools/ncu_traffic.py)
             with open(tpath) as fh:
-                traffic = json.load(fh).get(name)
+                traffic = (json.load(fh).get(name) or {}).get("dram_bytes_per_launch")
         return {"kernel": name, "bound": k["bound"], "achieved": k["gbs"] if hb else k["tflops"],
                 "peak": peaks["hbm_gbs"] if hb else peaks["bf16_tflops"], "unit": "GB/s" if hb else "TFLOP/s",
                 "frac": k["frac"], "traffic": traffic, "ms_per_step": k["ms_per_step"],
