@@ -164,6 +164,15 @@ PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, const float*
                                         int B, int H, int W,
                                         int C, int heads, int window, int shift, float scale,
                                         long long* phase_cycles, int mode, void* stream);
+/* Process-wide diagnostic switch of the bf16 GEMM kernel (profiling only; 0 = normal operation, returns the previous
+ * value): bit0 skip the output stores, bit1 skip the operand loads, bit2 skip the MMAs (results are then garbage);
+ * bit3 skip the proxy fence, bit4 cycle counters;
+ * bits [8,12) cap the pipeline stage count, bits [16,25) force the tile width. */
+PSW_API int psw_debug_linear_mode(int mode);
+/* With mode bit 4 set, CTA 0 of the last bf16 GEMM launch accumulated SM-cycle totals; copies them to the HOST
+ * array host_out16[16] (synchronises): {producer wait-empty, mma wait-tempty, mma wait-full, mma issue, epilogue
+ * wait-tfull, tmem-ld, math+stage, store-issue, tiles}. */
+PSW_API int psw_debug_linear_cycles(long long* host_out16);
 /* Host-only: dump the kernels' window geometry (see psw_api.cu); map may be NULL to query hp / wp. */
 PSW_API int psw_debug_source_map(int H, int W, int window, int shift, int pano_mode, int* map, int capacity,
                                  int* hp, int* wp);

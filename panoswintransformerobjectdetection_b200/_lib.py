@@ -27,6 +27,8 @@ SIGNATURES = {
     "psw_stem_conv3x3_relu_fwd": [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],
     "psw_cast": [_vp, _vp, _i64, _i, _i, _vp],
     "psw_window_attn_fwd_profile": [_vp, _vp, _fp, _fp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp],
+    "psw_debug_linear_mode": [_i],
+    "psw_debug_linear_cycles": [_vp],
     "psw_debug_source_map": [_i, _i, _i, _i, _i, _vp, _i, _vp, _vp],
     "psw_window_attn_fwd_simt_bf16": [_vp, _vp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
 }

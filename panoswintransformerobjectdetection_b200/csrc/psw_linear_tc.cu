@@ -1,21 +1,28 @@
 // K2 (throughput path): y = act(x . w^T + bias) (+ residual) with bf16 operands on the 5th-generation
-// tensor cores (tcgen05.mma, fp32 accumulators in TMEM), every global access a TMA transfer.
+// tensor cores (tcgen05.mma, fp32 accumulators in TMEM), operands staged by TMA.
 //
-// Persistent, warp-specialised CTA (one per SM, 320 or 448 threads):
+// Persistent, warp-specialised CTA (one per SM, 320 or 576 threads):
 //   warp 0      TMA producer : [128 x 64] x-tile and [BLOCK_N x 64] w-tile per stage, SWIZZLE_128B, mbarrier ring
 //   warp 1      MMA issuer   : one thread issues 4 x tcgen05.mma (M=128, N=BLOCK_N, K=16) per stage; commits free
 //                              the smem slot and, per tile, publish the accumulator
-//   warps 2..   epilogue     : 8 or 12 warps, two or three per TMEM lane quadrant, interleaving 64-byte-wide chunks:
-//                              tcgen05.ld 32 rows x CW columns -> +bias -> [GELU] -> [+residual] -> swizzled smem
-//                              tile -> TMA store (coalesced, clipped at M / N).  Residual tiles are TMA-loaded two
-//                              chunks ahead into a per-warp ring, so no thread ever issues a strided global access.
-// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of
-// tile i+1.  Tiles are ordered n-fastest, so CTAs of one wave share the x-tile through L2.
-// Rows beyond M and K beyond the tensor are zero-filled by TMA.
+//   warps 2..   epilogue     : two groups of 4 or 8 warps.  The accumulator is double-buffered in TMEM (2 x 256
+//                              columns); group g drains buffer g, i.e. every second tile of the CTA, so one group's
+//                              math overlaps the other group's stores and the MMAs of the tile after.  Per 64-byte
+//                              wide chunk: tcgen05.ld 32 rows x CW columns -> +bias (shared-memory copy) -> [GELU]
+//                              -> [+residual, TMA-loaded two chunks ahead into a per-warp ring] -> transpose through
+//                              a swizzled smem tile -> 16-byte global stores in which four lanes cover one 64-byte
+//                              row segment (whole sectors; measured faster than TMA stores of such small boxes:
+//                              no proxy fence, no ~300-cycle UTMASTG issue on the critical path).
+// CTA-pair mode (CG = 2, used for deep-K shapes): a cluster of two CTAs owns a 256-row tile; each CTA stages its
+// 128 x-rows and HALF of the w-tile rows, the leader issues tcgen05.mma.cta_group::2 (M=256) which reads both CTAs'
+// shared memory and writes both CTAs' TMEM, tcgen05.commit multicasts the barrier arrivals to both CTAs, and each
+// CTA runs the epilogue of its own 128 rows.  Operand traffic L2 -> SM per output column drops by ~1/3.
+// Tiles are ordered n-fastest, so CTAs of one wave share the x-tile through L2.
+// Rows beyond M and K beyond the tensor are zero-filled by TMA; stores are predicated at M and N.
 //
 // GELU on this path: 0.5 x (1 + tanh(x (c0 + c1 x^2 + c2 x^4))) with a minimax fit of the exact erf GELU
-// (max abs error 5.1e-5 over the real line, below bf16 resolution of the activations) and MUFU.TANH — the
-// fp32 parity path keeps erff.
+// (max abs error 5.1e-5 over the real line, below bf16 resolution of the activations), evaluated two at a time in
+// packed fp16 when the output is bf16 — the fp32 parity path keeps erff.
 #include "psw_common.cuh"
 
 namespace psw {
@@ -23,10 +30,10 @@ namespace psw {
 constexpr int TC_BM = 128;         // UMMA M
 constexpr int TC_BK = 64;          // one 128-byte swizzle row of bf16
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_MAX_EPI_WARPS = 12;
+constexpr int TC_MAX_EPI_WARPS = 16;
 constexpr int TC_TILE_BYTES = 32 * 64;      // epilogue staging tile: 32 rows x 64 B, SWIZZLE_64B
 
-struct TcSmemTail {
+struct alignas(16) TcSmemTail {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
   uint64_t tfull[2];
@@ -42,6 +49,47 @@ __device__ __forceinline__ void tmem_alloc_rt(uint32_t* slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc_rt(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster share one 256-row tile; the leader (cluster rank 0)
+// issues the MMAs, which read A / B from both CTAs' shared memory and write both CTAs' tensor memory.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address -> rank 0
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc2_rt(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2_rt(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// TMA load into this CTA's shared memory whose bytes are counted on the LEADER's mbarrier (same offset)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+}
+// arrive (when all prior MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the leader's barrier at this offset (from either CTA)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+
 __device__ __forceinline__ float gelu_fast(float x) {
   const float x2 = fminf(x * x, 64.0f);           // the fitted polynomial is used on |x| <= 8; beyond, tanh saturates
   const float p = fmaf(fmaf(-3.20974528e-04f, x2, 3.68320430e-02f), x2, 7.97686932e-01f);
@@ -51,43 +99,69 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(hx, t, hx);
 }
 
+// Two GELUs in packed fp16 arithmetic (the result is rounded to bf16 anyway): same fit, 6 instead of 9.5
+// instructions per element.  satfinite keeps |x| > 65504 finite so the tail evaluates to x or 0, not NaN.
+__device__ __forceinline__ uint32_t gelu_pair_bf16(float x0, float x1) {
+  uint32_t h, t;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+  const __half2 x = *reinterpret_cast<const __half2*>(&h);
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(64.0f));
+  const __half2 p = __hfma2(__hfma2(__float2half2_rn(-3.20974528e-04f), x2, __float2half2_rn(3.68320430e-02f)), x2,
+                            __float2half2_rn(7.97686932e-01f));
+  const __half2 u = __hmul2(x, p);
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&u)));
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const float2 f = __half22float2(__hfma2(hx, *reinterpret_cast<const __half2*>(&t), hx));
+  return pack_bf16x2(f.x, f.y);
+}
+
+// diagnostics (mode bit 4): SM-cycle totals of CTA 0 -- {producer wait-empty, mma wait-tempty, mma wait-full, mma issue,
+// epi wait-tfull, epi tmem-ld, epi math+stage, epi store-issue, tiles of CTA 0}
+__device__ long long g_tc_cycles[16];
+
 template <typename TO> struct Chunk;             // CW output columns = one 64-byte row of the staging tile
 template <> struct Chunk<float> { static constexpr int CW = 16; };
 template <> struct Chunk<bf16> { static constexpr int CW = 32; };
 
-// EW epilogue warps: 12 (three per TMEM lane quadrant) when there is no residual ring to stage, else 8
-template <bool RES> struct EpiCfg { static constexpr int EW = RES ? 8 : 12; static constexpr int THREADS = 64 + 32 * EW; };
+// Two groups of GW epilogue warps (GW = 4 or 8: one or two warps per TMEM lane quadrant); group g drains accumulator
+// buffer g, i.e. every second tile of the CTA, so the math of one group overlaps the stores of the other.
+template <int GW> struct EpiCfg { static constexpr int EW = 2 * GW; static constexpr int THREADS = 64 + 32 * EW; };
 
-template <bool GELU, bool RES, typename TO>
-__global__ void __launch_bounds__(EpiCfg<RES>::THREADS, 1)
+template <bool GELU, bool RES, typename TO, int GW, int CG>
+__global__ void __launch_bounds__(EpiCfg<GW>::THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                 const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_r,
-                 const float* __restrict__ bias, int64_t M, int N, int K, int block_n, int stages) {
+                 const __grid_constant__ CUtensorMap map_r,
+                 const float* __restrict__ bias, TO* __restrict__ y, int64_t M, int N, int K, int block_n, int stages, int mode) {
   constexpr int CW = Chunk<TO>::CW;
-  constexpr int TC_EPI_WARPS = EpiCfg<RES>::EW;
-  constexpr int PER_QUAD = TC_EPI_WARPS / 4;                  // warps sharing one TMEM lane quadrant
+  constexpr int TC_EPI_WARPS = EpiCfg<GW>::EW;
+  constexpr int PER_QUAD = GW / 4;                            // warps of one group sharing a TMEM lane quadrant
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B by OFFSETTING the __shared__ array (keeps the shared address space: LDS/STS, not generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t a_bytes = TC_BM * TC_BK * 2;                 // 16 KiB
-  const uint32_t b_bytes = (uint32_t)block_n * TC_BK * 2;
+  const uint32_t b_bytes = (uint32_t)(block_n / CG) * TC_BK * 2;   // pair mode: each CTA stages half of the w-tile rows
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint8_t* epi_smem = smem + (size_t)stages * stage_bytes;    // per warp: 2 out tiles (+ 2 residual tiles)
-  constexpr int EPI_PER_WARP = (RES ? 4 : 2) * TC_TILE_BYTES;
+  uint8_t* epi_smem = smem + (size_t)stages * stage_bytes;    // per warp: 1 out tile (+ 2 residual tiles)
+  constexpr int EPI_PER_WARP = (RES ? 3 : 1) * TC_TILE_BYTES;
   TcSmemTail* tail = reinterpret_cast<TcSmemTail*>(epi_smem + TC_EPI_WARPS * EPI_PER_WARP);
+  float* bias_s = reinterpret_cast<float*>(tail + 1);         // bias of all n_tiles * block_n columns, zero padded
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (N + block_n - 1) / block_n;
-  const int64_t m_tiles = (M + TC_BM - 1) / TC_BM;
+  constexpr int TILE_M = TC_BM * CG;                          // rows per tile (of the CTA or of the CTA pair)
+  const int64_t m_tiles = (M + TILE_M - 1) / TILE_M;
   const int64_t total_tiles = m_tiles * n_tiles;
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int unit = blockIdx.x / CG;                           // index of this CTA (pair) among the tile workers
+  const int n_units = gridDim.x / CG;
   const int k_blocks = (K + TC_BK - 1) / TC_BK;
   const uint32_t acc_stride = 256;
 
+  for (int i = threadIdx.x; i < n_tiles * block_n; i += blockDim.x) bias_s[i] = (bias && i < N) ? bias[i] : 0.0f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
-    tma_prefetch_desc(&map_y);
     if (RES) tma_prefetch_desc(&map_r);
     for (int s = 0; s < stages; ++s) {
       mbar_init(&tail->full[s], 1);
@@ -95,7 +169,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tail->tfull[s], 1);
-      mbar_init(&tail->tempty[s], TC_EPI_WARPS);
+      mbar_init(&tail->tempty[s], GW * CG);
     }
     for (int w = 0; w < TC_EPI_WARPS; ++w) {
       mbar_init(&tail->res_bar[w][0], 1);
@@ -103,7 +177,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc_rt(&tail->tmem_base, 512);
+  if (CG == 2) cluster_sync_all();                            // peer barriers are initialised before anything remote
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc2_rt(&tail->tmem_base, 512);
+    else tmem_alloc_rt(&tail->tmem_base, 512);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -114,69 +192,99 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int64_t m_t = tile / n_tiles;
-        const int n_t = (int)(tile - m_t * n_tiles);
+      const bool prof = (mode & 16) && blockIdx.x == 0;
+      long long c_we = 0;
+      for (int64_t tile = unit; tile < total_tiles; tile += n_units) {
+        const int m_t = (int)((uint32_t)tile / (uint32_t)n_tiles);
+        const int n_t = (int)tile - m_t * n_tiles;
         for (int kb = 0; kb < k_blocks; ++kb) {
+          const long long t0 = prof ? clock64() : 0;
           mbar_wait(&tail->empty[stage], phase ^ 1);
+          if (prof) c_we += clock64() - t0;
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          mbar_expect_tx(&tail->full[stage], stage_bytes);
-          tma_load_2d(sa, &map_x, &tail->full[stage], kb * TC_BK, (int)(m_t * TC_BM));
-          tma_load_2d(sa + a_bytes, &map_w, &tail->full[stage], kb * TC_BK, n_t * block_n);
+          if (CG == 2) {                                      // bytes of both CTAs are counted on the leader's barrier
+            if (cta_rank == 0) mbar_expect_tx(&tail->full[stage], 2 * stage_bytes);
+            tma_load_2d_pair(sa, &map_x, &tail->full[stage], kb * TC_BK, m_t * TILE_M + cta_rank * TC_BM);
+            tma_load_2d_pair(sa + a_bytes, &map_w, &tail->full[stage], kb * TC_BK, n_t * block_n + cta_rank * (block_n / 2));
+          } else if (mode & 2) {                              // diagnostics: no loads
+            mbar_arrive(&tail->full[stage]);
+          } else {
+            mbar_expect_tx(&tail->full[stage], stage_bytes);
+            tma_load_2d(sa, &map_x, &tail->full[stage], kb * TC_BK, m_t * TILE_M);
+            tma_load_2d(sa + a_bytes, &map_w, &tail->full[stage], kb * TC_BK, n_t * block_n);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (prof) g_tc_cycles[0] = c_we;
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(TC_BM, block_n, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TILE_M, block_n, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const bool prof = (mode & 16) && blockIdx.x == 0;
+      long long c_wt = 0, c_wf = 0, c_is = 0, n_t = 0;
+      for (int64_t tile = unit; tile < total_tiles; tile += n_units) {
+        long long t0 = prof ? clock64() : 0;
         mbar_wait(&tail->tempty[acc], acc_phase ^ 1);         // epilogue has drained this accumulator
         tc_fence_after();
+        if (prof) { const long long t1 = clock64(); c_wt += t1 - t0; ++n_t; }
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
         for (int kb = 0; kb < k_blocks; ++kb) {
+          t0 = prof ? clock64() : 0;
           mbar_wait(&tail->full[stage], phase);               // TMA bytes have landed
           tc_fence_after();
+          const long long t1 = prof ? clock64() : 0;
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t da = umma_smem_desc(sa, 16, 1024, UMMA_SWIZZLE_128B);
           const uint64_t db = umma_smem_desc(sa + a_bytes, 16, 1024, UMMA_SWIZZLE_128B);
 #pragma unroll
-          for (int k = 0; k < TC_BK / 16; ++k)                // advance 32 B inside the swizzle row: +2 (>>4)
-            umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&tail->empty[stage]);                   // frees the smem slot when the MMAs retire
+          for (int k = 0; k < TC_BK / 16; ++k) {              // advance 32 B inside the swizzle row: +2 (>>4)
+            if (CG == 2) umma_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else if (!(mode & 4)) umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          if (CG == 2) umma_commit_pair(&tail->empty[stage]);  // frees the smem slot (both CTAs) when the MMAs retire
+          else umma_commit(&tail->empty[stage]);
+          if (prof) { c_wf += t1 - t0; c_is += clock64() - t1; }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tail->tfull[acc]);                       // accumulator complete -> epilogue
+        if (CG == 2) umma_commit_pair(&tail->tfull[acc]);     // accumulator complete -> epilogue (of both CTAs)
+        else umma_commit(&tail->tfull[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (prof) { g_tc_cycles[1] = c_wt; g_tc_cycles[2] = c_wf; g_tc_cycles[3] = c_is; g_tc_cycles[8] = n_t; }
     }
   } else {
-    // ------------------------------- epilogue (8 warps) --------------------------
+    // ------------------------------- epilogue ------------------------------------
     const int ew = warp - 2;
     const int quad = warp & 3;                                // TMEM lane quadrant this warp may access
-    const int part = ew >> 2;                                 // the PER_QUAD warps of a quadrant interleave chunks
+    const int grp = ew / GW;                                  // group = accumulator buffer = tile parity of this CTA
+    const int part = (ew % GW) >> 2;                          // the PER_QUAD warps of a quadrant interleave chunks
     uint8_t* my_smem = epi_smem + ew * EPI_PER_WARP;
-    uint8_t* out_buf[2] = {my_smem, my_smem + TC_TILE_BYTES};
-    uint8_t* res_buf[2] = {my_smem + 2 * TC_TILE_BYTES, my_smem + 3 * TC_TILE_BYTES};
+    uint8_t* out_buf = my_smem;                               // [32 rows][64 B], 16-byte piece index ^= (row >> 1) & 3
+    uint8_t* res_buf0 = my_smem + TC_TILE_BYTES;             // residual ring: slot b at res_buf0 + b * TC_TILE_BYTES
     uint64_t* res_bar = tail->res_bar[ew];
     const int n_chunks = block_n / CW;
-    const int sw = (lane >> 1) & 3;                           // SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
-    uint8_t* my_row_out[2] = {out_buf[0] + lane * 64, out_buf[1] + lane * 64};
-    const uint8_t* my_row_res[2] = {res_buf[0] + lane * 64, res_buf[1] + lane * 64};
-    int acc = 0;
+    const int sw = (lane >> 1) & 3;
+    uint8_t* my_row_out = out_buf + lane * 64;
+    const uint8_t* my_row_res0 = res_buf0 + lane * 64;
+    // read-back for the coalesced store: this lane moves 16-byte piece (lane & 3) of rows (lane >> 2) + 8 j
+    const int t_row = lane >> 2, t_piece = lane & 3;
+    constexpr int PIECE_ELEMS = 16 / (int)sizeof(TO);
+    const int acc = grp;
     uint32_t acc_phase = 0;
-    uint32_t out_cnt = 0;                                     // chunks stored so far (selects the out buffer)
     uint32_t res_issued = 0, res_used = 0;                    // residual ring counters (2 deep)
-    uint32_t tile_iter = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_iter) {
-      const int64_t m_t = tile / n_tiles;
-      const int n_t = (int)(tile - m_t * n_tiles);
-      const int row0 = (int)(m_t * TC_BM) + quad * 32;
+    uint32_t tile_iter = 0;                                   // tiles of this group so far
+    const bool prof = (mode & 16) && blockIdx.x == 0 && ew == 0;
+    long long c_w = 0, c_ld = 0, c_ma = 0, c_st = 0;
+    for (int64_t tile = unit + (int64_t)grp * n_units; tile < total_tiles; tile += 2 * n_units, ++tile_iter) {
+      const int m_t = (int)((uint32_t)tile / (uint32_t)n_tiles);     // total_tiles < 2^31 (checked on the host)
+      const int n_t = (int)tile - m_t * n_tiles;
+      const int row0 = m_t * TILE_M + cta_rank * TC_BM + quad * 32;
       const int col0 = n_t * block_n;
       // chunks of this warp in this tile: c = first, first + PER_QUAD, ... (first rotates with the tile count so a
       // chunk count that is not a multiple of PER_QUAD still balances the warps of a quadrant)
@@ -190,19 +298,21 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             if (c < n_chunks) {
               const uint32_t b = res_issued & 1;
               mbar_expect_tx(&res_bar[b], TC_TILE_BYTES);
-              tma_load_2d(res_buf[b], &map_r, &res_bar[b], col0 + c * CW, row0);
+              tma_load_2d(res_buf0 + b * TC_TILE_BYTES, &map_r, &res_bar[b], col0 + c * CW, row0);
               ++res_issued;
             }
           }
         }
       }
+      long long tp = prof ? clock64() : 0;
       mbar_wait(&tail->tfull[acc], acc_phase);
       tc_fence_after();
+      if (prof) { const long long t1 = clock64(); c_w += t1 - tp; tp = t1; }
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * acc_stride;
       if (first >= n_chunks) {                               // no chunk for this warp in this tile: release at once
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tail->tempty[acc]);
+        if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tail->tempty[acc]); else mbar_arrive(&tail->tempty[acc]); }
       }
       for (int c = first; c < n_chunks; c += PER_QUAD) {
         float v[CW];
@@ -219,93 +329,117 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
         }
+        if (prof) { const long long t1 = clock64(); c_ld += t1 - tp; tp = t1; }
         if (c + PER_QUAD >= n_chunks) {                       // my last read of this accumulator: hand it back to the
           tc_fence_before();                                  // MMA warp now, the math / stores below no longer need it
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tail->tempty[acc]);
+          if (lane == 0) { if (CG == 2) mbar_arrive_leader(&tail->tempty[acc]); else mbar_arrive(&tail->tempty[acc]); }
         }
         const int col = col0 + c * CW;
-        if (bias) {
+        {                                                     // bias (zero-filled copy in shared memory: broadcast reads)
+          const float4* bs = reinterpret_cast<const float4*>(bias_s + col);
 #pragma unroll
           for (int i = 0; i < CW / 4; ++i) {
-            if (col + 4 * i < N) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col) + i);
-              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
-            }
+            const float4 b4 = bs[i];
+            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
           }
         }
-        if (GELU) {
+        uint32_t packed[16];                                  // the 64-byte output row of this lane
+        if constexpr (CW == 32) {
+          if (GELU && !RES) {
 #pragma unroll
-          for (int i = 0; i < CW; ++i) v[i] = gelu_fast(v[i]);
+            for (int i = 0; i < 16; ++i) packed[i] = gelu_pair_bf16(v[2 * i], v[2 * i + 1]);
+          }
         }
-        if (RES) {
-          const uint32_t b = res_used & 1;
-          mbar_wait(&res_bar[b], (res_used >> 1) & 1);
+        if (!(CW == 32 && GELU && !RES)) {
+          if (GELU) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 t = *reinterpret_cast<const uint4*>(my_row_res[b] + ((q ^ sw) << 4));
-            const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
-            if constexpr (CW == 16) {
+            for (int i = 0; i < CW; ++i) v[i] = gelu_fast(v[i]);
+          }
+          if (RES) {
+            const uint32_t b = res_used & 1;
+            mbar_wait(&res_bar[b], (res_used >> 1) & 1);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) v[4 * q + i] += __uint_as_float(w4[i]);
-            } else {
+            for (int q = 0; q < 4; ++q) {
+              const uint4 t = *reinterpret_cast<const uint4*>(my_row_res0 + b * TC_TILE_BYTES + ((q ^ sw) << 4));
+              const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+              if constexpr (CW == 16) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w4[i]);
-                v[8 * q + 2 * i] += __low2float(h);
-                v[8 * q + 2 * i + 1] += __high2float(h);
+                for (int i = 0; i < 4; ++i) v[4 * q + i] += __uint_as_float(w4[i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w4[i]);
+                  v[8 * q + 2 * i] += __low2float(h);
+                  v[8 * q + 2 * i + 1] += __high2float(h);
+                }
               }
             }
+            ++res_used;
+            __syncwarp();                                     // every lane has read the tile: the slot is free
+            if (lane == 0 && c + 2 * PER_QUAD < n_chunks) {   // keep the ring two chunks ahead
+              const uint32_t nb = res_issued & 1;
+              mbar_expect_tx(&res_bar[nb], TC_TILE_BYTES);
+              tma_load_2d(res_buf0 + nb * TC_TILE_BYTES, &map_r, &res_bar[nb], col0 + (c + 2 * PER_QUAD) * CW, row0);
+              ++res_issued;
+            }
           }
-          ++res_used;
-          __syncwarp();                                       // every lane has read the tile: the slot is free
-          if (lane == 0 && c + 2 * PER_QUAD < n_chunks) {     // keep the ring two chunks ahead
-            const uint32_t nb = res_issued & 1;
-            mbar_expect_tx(&res_bar[nb], TC_TILE_BYTES);
-            tma_load_2d(res_buf[nb], &map_r, &res_bar[nb], col0 + (c + 2 * PER_QUAD) * CW, row0);
-            ++res_issued;
-          }
-        }
-        // stage the chunk in shared memory (64-byte rows, 64B swizzle -> conflict-free 16-byte stores)
-        const uint32_t ob = out_cnt & 1;
-        if (lane == 0) tma_store_wait_read<1>();              // the store issued two chunks ago has left this buffer
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 t;
           if constexpr (CW == 16) {
-            t = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
-                           __float_as_uint(v[4 * q + 3]));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) packed[i] = __float_as_uint(v[i]);
           } else {
-            t = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
-                           pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+#pragma unroll
+            for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
           }
-          *reinterpret_cast<uint4*>(my_row_out[ob] + ((q ^ sw) << 4)) = t;
         }
-        fence_async_shared();
+        if (prof) { const long long t1 = clock64(); c_ma += t1 - tp; tp = t1; }
+        // transpose through shared memory (generic proxy only: no fence, no TMA): each lane writes its 64-byte row,
+        // then four lanes move one row, so every 16-byte store of the warp fills whole sectors of 8 output rows
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(my_row_out + ((q ^ sw) << 4)) =
+              make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
         __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&map_y, out_buf[ob], col, row0);       // clipped at M and N by the tensor map
-          tma_store_commit();
+        {
+          uint4 t[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                       // all four reads first: independent registers
+            const int r = t_row + 8 * j;
+            t[j] = *reinterpret_cast<const uint4*>(out_buf + r * 64 + ((t_piece ^ ((r >> 1) & 3)) << 4));
+          }
+          if (!(mode & 1) && col + t_piece * PIECE_ELEMS < N) {
+            uint8_t* gp = reinterpret_cast<uint8_t*>(y + (int64_t)(row0 + t_row) * N + col) + t_piece * 16;
+            const int64_t step = (int64_t)8 * N * (int64_t)sizeof(TO);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (row0 + t_row + 8 * j < M) *reinterpret_cast<uint4*>(gp + j * step) = t[j];
+          }
         }
-        ++out_cnt;
+        __syncwarp();                                         // the staging row may be overwritten by the next chunk
+        if (prof) { const long long t1 = clock64(); c_st += t1 - tp; tp = t1; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      acc_phase ^= 1;
     }
-    if (lane == 0) tma_store_wait<0>();                       // all stores of this warp are complete
+    if (prof && lane == 0) { g_tc_cycles[4] = c_w; g_tc_cycles[5] = c_ld; g_tc_cycles[6] = c_ma; g_tc_cycles[7] = c_st; }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                            // the peer may still read this CTA's smem / signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc_rt(tmem_base, 512);
+    if (CG == 2) tmem_dealloc2_rt(tmem_base, 512);
+    else tmem_dealloc_rt(tmem_base, 512);
   }
 }
 
 // Tile width: a multiple of 32 (epilogue chunks), <= 256 (TMEM double buffer); 192 keeps four pipeline stages
 // next to the epilogue staging, so it is preferred whenever it divides N.
+static int g_tc_mode = 0;   // diagnostics (psw_debug_linear_mode): bit0 no stores, bit1 no loads, bit2 no MMAs,
+                            // bits [8,12) stage-count override, bits [16,25) tile-width override
+
 static int pick_block_n(int N) {
+  if ((g_tc_mode >> 16) & 0x1ff) return (g_tc_mode >> 16) & 0x1ff;
   if (N <= 256) return (N + 31) / 32 * 32;
   const int prefs[] = {192, 256, 224, 160, 128, 96, 64};
   for (int bn : prefs)
@@ -313,33 +447,85 @@ static int pick_block_n(int N) {
   return 192;                                                 // ragged last tile: zero-filled loads, clipped stores
 }
 
+template <bool GELU, bool RES, typename TO, int GW, int CG>
+static int launch_tc_gw(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mr, const float* bias, void* y,
+                        int64_t M, int N, int K, int block_n, int stages, size_t smem, cudaStream_t st) {
+  const int64_t tiles = ((M + TC_BM * CG - 1) / (TC_BM * CG)) * ((N + block_n - 1) / block_n);
+  const int units = num_sms() / CG;
+  const int grid = CG * (int)(tiles < units ? tiles : units);
+  auto kern = linear_tc_kernel<GELU, RES, TO, GW, CG>;
+  PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(EpiCfg<GW>::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  PSW_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mw, mr, bias, (TO*)y, M, N, K, block_n, stages, g_tc_mode & 31));
+  return launch_status("linear_tc_kernel");
+}
+
+// CTA-pair tiles (256 x block_n): worth it when the GEMM is bound by L2 -> SM operand traffic, i.e. deep K, and the
+// pair tiles still fill the machine.
+static bool use_pair(int64_t M, int N, int K, int* block_n) {
+  if ((g_tc_mode >> 26) & 1) return false;
+  const bool force = (g_tc_mode >> 27) & 1;
+  if (N % 32 != 0) return false;
+  int bn = 0;
+  const int prefs[] = {256, 192, 128, 64};
+  for (int c : prefs)
+    if (N % c == 0) { bn = c; break; }
+  if (!bn) return false;
+  if ((g_tc_mode >> 16) & 0x1ff) bn = (g_tc_mode >> 16) & 0x1ff;
+  const int64_t tiles = ((M + 255) / 256) * (N / bn);
+  if (!force && (K < 768 || tiles < 2 * (num_sms() / 2))) return false;   // measured: profitable from K = 768 up
+  *block_n = bn;
+  return true;
+}
+
 template <bool GELU, bool RES, typename TO>
 static int launch_tc(const void* x, const void* w, const float* bias, const void* residual, void* y, int64_t M, int N,
                      int K, cudaStream_t st) {
   constexpr int CW = Chunk<TO>::CW;
-  const int block_n = pick_block_n(N);
-  CUtensorMap mx, mw, my, mr;
+  int block_n = pick_block_n(N);
+  const bool pair = use_pair(M, N, K, &block_n);
+  const int cg = pair ? 2 : 1;
+  CUtensorMap mx, mw, mr;
   int rc = make_tensor_map_2d(&mx, x, (uint64_t)M, (uint64_t)K, TC_BM, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = make_tensor_map_2d(&mw, w, (uint64_t)N, (uint64_t)K, (uint32_t)block_n, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
-  rc = make_tensor_map_2d(&my, y, (uint64_t)M, (uint64_t)N, 32, CW, (int)sizeof(TO), CU_TENSOR_MAP_SWIZZLE_64B);
+  rc = make_tensor_map_2d(&mw, w, (uint64_t)N, (uint64_t)K, (uint32_t)(block_n / cg), TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   rc = make_tensor_map_2d(&mr, RES ? residual : y, (uint64_t)M, (uint64_t)N, 32, CW, (int)sizeof(TO), CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
-  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)block_n * TC_BK * 2;
-  const size_t epi_bytes = (size_t)EpiCfg<RES>::EW * (RES ? 4 : 2) * TC_TILE_BYTES;
-  const size_t fixed = 1024 + epi_bytes + sizeof(TcSmemTail);
-  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
-  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)(block_n / cg) * TC_BK * 2;
+  const size_t bias_bytes = (size_t)((N + block_n - 1) / block_n) * block_n * sizeof(float);
+  const int k_blocks = (K + TC_BK - 1) / TC_BK;
+  // 16 epilogue warps when the pipeline still gets enough stages next to their staging tiles, else 8
+  int gw = 8, stages = 0;
+  size_t fixed = 0;
+  for (;; gw = 4) {
+    const size_t epi_bytes = (size_t)2 * gw * (RES ? 3 : 1) * TC_TILE_BYTES;
+    fixed = 1024 + epi_bytes + sizeof(TcSmemTail) + bias_bytes;
+    stages = (int)((227 * 1024 - fixed) / stage_bytes);
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (gw == 4 || stages >= 4 || stages >= 2 * k_blocks) break;
+  }
+  if ((g_tc_mode >> 25) & 1) gw = 4;
+  if (((g_tc_mode >> 8) & 15) && ((g_tc_mode >> 8) & 15) < stages) stages = (g_tc_mode >> 8) & 15;
   PSW_REQUIRE(stages >= 2, PSW_ERR_UNSUPPORTED, "psw_linear_fwd(bf16): tile too large for shared memory");
   const size_t smem = fixed + stages * stage_bytes;
-  const int64_t tiles = ((M + TC_BM - 1) / TC_BM) * ((N + block_n - 1) / block_n);
-  int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  auto kern = linear_tc_kernel<GELU, RES, TO>;
-  PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, EpiCfg<RES>::THREADS, smem, st>>>(mx, mw, my, mr, bias, M, N, K, block_n, stages);
-  return launch_status("linear_tc_kernel");
+  if (pair) {
+    if (gw == 8) return launch_tc_gw<GELU, RES, TO, 8, 2>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, st);
+    return launch_tc_gw<GELU, RES, TO, 4, 2>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, st);
+  }
+  if (gw == 8) return launch_tc_gw<GELU, RES, TO, 8, 1>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, st);
+  return launch_tc_gw<GELU, RES, TO, 4, 1>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, st);
 }
 
 int linear_f32(const float* x, const float* w, const float* bias, const float* residual, float* y, int64_t M, int N,
@@ -348,6 +534,18 @@ int linear_f32(const float* x, const float* w, const float* bias, const float* r
 }  // namespace psw
 
 using namespace psw;
+
+extern "C" PSW_API int psw_debug_linear_mode(int mode) {
+  const int old = g_tc_mode;
+  g_tc_mode = mode;
+  return old;
+}
+
+extern "C" PSW_API int psw_debug_linear_cycles(long long* host_out16) {
+  PSW_REQUIRE(host_out16, PSW_ERR_BAD_ARG, "psw_debug_linear_cycles: null pointer");
+  PSW_CUDA(cudaMemcpyFromSymbol(host_out16, g_tc_cycles, sizeof(long long) * 16));
+  return PSW_OK;
+}
 
 extern "C" PSW_API int psw_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
                               int64_t M, int N, int K, int flags, int dtype, int out_dtype, void* stream) {

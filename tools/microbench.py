@@ -50,6 +50,8 @@ def linear(iters):
               (8192, 576, 192, 0, 0, "bf16"), (8192, 768, 192, 1, 0, "bf16"), (8192, 192, 768, 0, 1, "f32"),
               (2048, 1152, 384, 0, 0, "bf16"), (2048, 1536, 384, 1, 0, "bf16"), (2048, 384, 1536, 0, 1, "f32"),
               (512, 2304, 768, 0, 0, "bf16"), (512, 3072, 768, 1, 0, "bf16"), (512, 768, 3072, 0, 1, "f32")]
+    if os.environ.get("MB_SHAPES"):
+        shapes = [shapes[int(i)] for i in os.environ["MB_SHAPES"].split(",")]
     for (tok, N, K, gelu, res, odt) in shapes:
         M = tok * B
         od = torch.bfloat16 if odt == "bf16" else torch.float32
@@ -141,3 +143,123 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "phases":
     attn_phases()
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "skeleton":
     attn_skeleton()
+
+
+def linear_modes(iters=20):
+    """GEMM diagnostics: which of loads / MMAs / stores bounds each shape (psw_debug_linear_mode), the stage-count and
+    tile-width sensitivity, and the cuBLAS time of the same product (library reference, no epilogue fusion)."""
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    shapes = [(32768, 288, 96, 0, 0, "bf16"), (32768, 384, 96, 1, 0, "bf16"), (32768, 96, 96, 0, 1, "f32"),
+              (8192, 768, 192, 1, 0, "bf16"), (2048, 1152, 384, 0, 0, "bf16"), (2048, 384, 1536, 0, 1, "f32"),
+              (512, 3072, 768, 1, 0, "bf16")]
+    if os.environ.get("MB_SHAPES"):
+        shapes = [shapes[int(i)] for i in os.environ["MB_SHAPES"].split(",")]
+    variants = [("full", 0), ("no-store", 1), ("no-load", 2), ("no-mma", 4), ("no-load/mma", 6), ("only-epi", 7), ("only-epi-nofence", 15), ("nofence", 8),
+                ("stages2", 2 << 8), ("stages3", 3 << 8), ("bn64", 64 << 16), ("bn96", 96 << 16), ("bn128", 128 << 16),
+                ("bn192", 192 << 16), ("bn256", 256 << 16), ("1cta", 1 << 26), ("1cta-bn256", (1 << 26) | (256 << 16)),
+                ("pair", 1 << 27), ("pair-bn128", (1 << 27) | (128 << 16)),
+                ("pair-bn192", (1 << 27) | (192 << 16)), ("pair-bn256", (1 << 27) | (256 << 16)), ("pair-gw4", (1 << 27) | (1 << 25))]
+    for (tok, N, K, gelu, res, odt) in shapes:
+        M = tok * B
+        od = torch.bfloat16 if odt == "bf16" else torch.float32
+        nb = max(2, int(400e6 // (M * (K * 2 + N * od.itemsize))) + 1)
+        x = [torch.randn(M, K, device=DEV).bfloat16() for _ in range(nb)]
+        y = [torch.randn(M, N, device=DEV).to(od) for _ in range(nb)]
+        w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+        b = torch.randn(N, device=DEV)
+        line = []
+        for name, mode in variants:
+            if ((mode >> 16) & 0x1ff) and N % ((mode >> 16) & 0x1ff):
+                continue
+            lib.psw_debug_linear_mode(mode)
+            try:
+                us = time_op(lambda i: ops.linear(x[i], w, b, residual=y[i] if res else None, gelu=bool(gelu), out=y[i], out_dtype=od),
+                             nb, iters)
+                line.append(f"{name} {us:.0f}")
+            except Exception as e:  # noqa: BLE001
+                line.append(f"{name} ERR")
+            lib.psw_debug_linear_mode(0)
+        yb = [torch.empty(M, N, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
+        us = time_op(lambda i: torch.matmul(x[i], w.t(), out=yb[i]), nb, iters)
+        line.append(f"cublas(no epi, bf16 out) {us:.0f}")
+        print(f"linear M{M} N{N} K{K} gelu{gelu} res{res} {odt} [us]: " + "  ".join(line), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "linmodes":
+    linear_modes()
+
+
+def linear_cycles():
+    """Per-role SM-cycle breakdown of CTA 0 of the tcgen05 GEMM (psw_debug_linear_mode bit 4)."""
+    import ctypes
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    shapes = [(32768, 288, 96, 0, 0, "bf16"), (32768, 384, 96, 1, 0, "bf16"), (32768, 96, 96, 0, 1, "f32"),
+              (8192, 768, 192, 1, 0, "bf16"), (2048, 1152, 384, 0, 0, "bf16"), (2048, 384, 1536, 0, 1, "f32"),
+              (512, 3072, 768, 1, 0, "bf16")]
+    names = ["prod wait-empty", "mma wait-tempty", "mma wait-full", "mma issue", "epi wait-tfull", "epi tmem-ld",
+             "epi math", "epi stage+store"]
+    for (tok, N, K, gelu, res, odt) in shapes:
+        M = tok * B
+        od = torch.bfloat16 if odt == "bf16" else torch.float32
+        x = torch.randn(M, K, device=DEV).bfloat16()
+        y = torch.randn(M, N, device=DEV).to(od)
+        w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+        b = torch.randn(N, device=DEV)
+        for extra in (1 << 26, 1 << 27):
+            lib.psw_debug_linear_mode(16 | extra)
+            for _ in range(2):
+                ops.linear(x, w, b, residual=y if res else None, gelu=bool(gelu), out=y, out_dtype=od)
+            buf = (ctypes.c_longlong * 16)()
+            _lib.check(lib.psw_debug_linear_cycles(ctypes.cast(buf, ctypes.c_void_p)), "cycles")
+            lib.psw_debug_linear_mode(0)
+            v = list(buf)
+            n = max(v[8], 1)
+            print(f"linear M{M} N{N} K{K} gelu{gelu} res{res} {odt} {'pair' if extra >> 27 else '1cta'}: tiles {v[8]}  per tile (epilogue warp 0 sees every 2nd tile): " +
+                  "  ".join(f"{nm} {v[i] / n:.0f}" for i, nm in enumerate(names) if nm), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "lincycles":
+    linear_cycles()
+
+
+def linear_sweep(iters=20):
+    """Tile-shape / CTA-pair sweep over the stage 1-3 GEMM shapes (three interleaved repeats, best of)."""
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    shapes = [(8192, 576, 192, 0, 0, "bf16"), (8192, 192, 192, 0, 1, "f32"), (8192, 768, 192, 1, 0, "bf16"), (8192, 192, 768, 0, 1, "f32"),
+              (2048, 1152, 384, 0, 0, "bf16"), (2048, 384, 384, 0, 1, "f32"), (2048, 1536, 384, 1, 0, "bf16"), (2048, 384, 1536, 0, 1, "f32"),
+              (512, 2304, 768, 0, 0, "bf16"), (512, 768, 768, 0, 1, "f32"), (512, 3072, 768, 1, 0, "bf16"), (512, 768, 3072, 0, 1, "f32"),
+              (8192, 192, 384, 0, 0, "bf16"), (2048, 384, 768, 0, 0, "bf16"), (512, 768, 1536, 0, 0, "bf16")]
+    variants = [("auto", 0)]
+    for bn in (128, 192, 256, 384):
+        variants.append((f"1cta-bn{bn}", (1 << 26) | (bn << 16)))
+        variants.append((f"pair-bn{bn}", (1 << 27) | (bn << 16)))
+    for (tok, N, K, gelu, res, odt) in shapes:
+        M = tok * B
+        od = torch.bfloat16 if odt == "bf16" else torch.float32
+        nb = max(2, int(400e6 // (M * (K * 2 + N * od.itemsize))) + 1)
+        x = [torch.randn(M, K, device=DEV).bfloat16() for _ in range(nb)]
+        y = [torch.randn(M, N, device=DEV).to(od) for _ in range(nb)]
+        w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+        b = torch.randn(N, device=DEV)
+        best = {}
+        for rep in range(3):
+            for name, mode in variants:
+                bn = (mode >> 16) & 0x1ff
+                if bn and (N % bn or bn > 256):
+                    continue
+                lib.psw_debug_linear_mode(mode)
+                try:
+                    us = time_op(lambda i: ops.linear(x[i], w, b, residual=y[i] if res else None, gelu=bool(gelu), out=y[i], out_dtype=od),
+                                 nb, iters)
+                    best[name] = min(best.get(name, 1e9), us)
+                except Exception:  # noqa: BLE001
+                    best[name] = float("nan")
+                lib.psw_debug_linear_mode(0)
+        print(f"linear M{M} N{N} K{K} gelu{gelu} res{res} {odt} [us]: " + "  ".join(f"{k} {v:.1f}" for k, v in best.items()), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "linsweep":
+    linear_sweep()
