@@ -41,9 +41,11 @@ def gather_features(local_outs: Sequence[torch.Tensor], world: int, group=None) 
 
 
 class GraphedForward:
-    """The backbone forward for one fixed input shape captured into a CUDA graph: one `replay()` re-issues the
-    ~100 kernel launches of a forward without any Python / ctypes work (small chunks are launch-bound otherwise).
-    `static_in` is the graph's input buffer, `static_out` its tuple of output maps."""
+    """The backbone forward for one fixed input shape captured into CUDA graphs: a replay re-issues the ~100 kernel
+    launches of a forward without any Python / ctypes work (small chunks are launch-bound otherwise).
+    The forward is cut into one graph per output map (all in one memory pool, replayed in capture order), so a
+    caller can start reading output k while the stages after it still run (`replay(on_output)`).
+    `static_in` is the graphs' input buffer, `static_out` the tuple of output maps."""
 
     def __init__(self, model, shape, device):
         self.static_in = torch.zeros(shape, device=device)
@@ -54,26 +56,52 @@ class GraphedForward:
                 model(self.static_in)
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph), torch.no_grad():
-            self.static_out = model(self.static_in)
+        self.graphs = []
+        n_out = len(tuple(model.out_indices))
+        pool = torch.cuda.graph_pool_handle()
 
-    def replay(self):
-        self.graph.replay()
+        def begin():
+            g = torch.cuda.CUDAGraph()
+            g.capture_begin(pool=pool)
+            self.graphs.append(g)
+
+        def on_output(k, _fmap):                            # cut after every output map but the last
+            if k < n_out - 1:
+                self.graphs[-1].capture_end()
+                begin()
+
+        with torch.cuda.stream(side), torch.no_grad():
+            begin()
+            try:
+                self.static_out = model.forward_streamed(self.static_in, on_output)
+            finally:
+                self.graphs[-1].capture_end()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+
+    def replay(self, on_output=None):
+        """Re-run the forward on the current stream; `on_output(k, map)` is called right after the graph that
+        produces output k has been launched."""
+        for k, g in enumerate(self.graphs):
+            g.replay()
+            if on_output is not None:
+                on_output(k, self.static_out[k])
         return self.static_out
 
 
 class HostPipeline:
     """model(images on the host) -> feature maps on the host, chunked and overlapped.
 
-    Three streams: copy-in (H2D of chunk i+1), compute (forward of chunk i), copy-out (D2H of chunk i-1; the
-    feature maps are 3.75x the input bytes, so the D2H stream is the critical resource).  With `graphs=True`
-    (default) each of the two chunk slots owns a CUDA graph of the forward, so chunks can be small (early first
-    D2H, short tail) without becoming launch-bound.  Input must be a pinned fp32 [B, 3, H, W] tensor; outputs are
+    Three streams: copy-in (H2D of chunk i+1), compute (forward of chunk i), copy-out (the feature maps are 3.75x
+    the input bytes, so the D2H stream is the critical resource: the copy of output map k of a chunk starts as soon
+    as stage k has run, while the later stages still compute).  With `graphs=True` (default) each of the two chunk
+    slots owns the CUDA graphs of the forward, so chunks can be small (early first D2H, short tail) without
+    becoming launch-bound.  Input must be a pinned fp32 [B, 3, H, W] tensor; outputs are
     pinned fp32 NCHW maps reused across calls."""
 
-    def __init__(self, model, chunk: int = 8, graphs: bool = True):
+    def __init__(self, model, chunk: int = 8, graphs: bool = True, sizes: Sequence[int] = None):
         self.model = model
+        self.sizes = list(sizes) if sizes else None     # explicit chunk sizes (must sum to the batch), else _schedule
         self.chunk = int(chunk)
         self.graphs = graphs
         self.dev = next(model.parameters()).device
@@ -99,7 +127,9 @@ class HostPipeline:
         c = self.chunk
         sizes = []
         left = B
-        if B > 2 * c and c >= 2:
+        if self.sizes is not None and sum(self.sizes) == B:
+            sizes = list(self.sizes)
+        elif B > 2 * c and c >= 2:
             sizes.append(c // 2)
             left -= c // 2
             while left > c + c // 2:
@@ -150,19 +180,23 @@ class HostPipeline:
                 ready.record(self.s_in)
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(ready)
-                if id(slot) in out_free:              # the graph's static outputs are still being copied out
+                if id(slot) in out_free:              # the slot's static outputs are still being copied out
                     self.s_cmp.wait_event(out_free[id(slot)])
-                outs = slot.replay() if self.graphs else self.model(xin)
+
+                def copy_out(idx, o, b0=b0, b1=b1):   # output idx is enqueued: its D2H may start while later stages run
+                    ev = torch.cuda.Event()
+                    ev.record(self.s_cmp)
+                    self.s_out.wait_event(ev)
+                    with torch.cuda.stream(self.s_out):
+                        self._ensure_host_out(B, idx, o)[b0:b1].copy_(o, non_blocking=True)
+
+                outs = slot.replay(copy_out) if self.graphs else self.model.forward_streamed(xin, copy_out)
                 done = torch.cuda.Event()
                 done.record(self.s_cmp)
                 in_free[id(slot)] = done
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(done)
-                for idx, o in enumerate(outs):
-                    self._ensure_host_out(B, idx, o)[b0:b1].copy_(o, non_blocking=True)
-                copied = torch.cuda.Event()
-                copied.record(self.s_out)
-                out_free[id(slot)] = copied
+            copied = torch.cuda.Event()
+            copied.record(self.s_out)
+            out_free[id(slot)] = copied
             live.append(outs)
             n_out = len(outs)
         cur.wait_stream(self.s_out)

@@ -117,6 +117,52 @@ def test_linear_bf16_tcgen05(ops, mnk, odt, gelu, res, bias):
     assert rel_l2(got.float(), want) <= (4e-3 if odt == torch.bfloat16 else 2e-5)
 
 
+PAIR_SHAPES = [(333, 96, 64), (512, 256, 128), (1000, 384, 1536), (4100, 768, 768), (20000, 1152, 384), (257, 64, 3072)]
+
+
+@pytest.mark.parametrize("mnk", PAIR_SHAPES)
+@pytest.mark.parametrize("odt,gelu,res", [(torch.bfloat16, False, False), (torch.bfloat16, True, False), (torch.float32, False, True)])
+@pytest.mark.parametrize("mode", [1 << 27, (1 << 27) | (1 << 25), 1 << 26])
+def test_linear_bf16_cta_pair(ops, mnk, odt, gelu, res, mode):
+    """The cta_group::2 (CTA-pair, 256-row tiles) variant of the tcgen05 GEMM forced on ragged / small / deep-K
+    shapes, with 16 and 8 epilogue warps, against the forced single-CTA variant and the fp64 reference."""
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    M, N, K = mnk
+    g = _g(M + 7 * N + K)
+    x = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g).to(odt) if res else None
+    want = F.linear(x.double(), w.double(), b.double())
+    if gelu:
+        want = F.gelu(want)
+    if res:
+        want = want + r.double()
+    old = lib.psw_debug_linear_mode(mode)
+    try:
+        got = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), None if r is None else r.to(DEV), gelu, out_dtype=odt)
+        torch.cuda.synchronize()
+    finally:
+        lib.psw_debug_linear_mode(old)
+    assert torch.isfinite(got).all()
+    assert rel_l2(got.float(), want) <= (4e-3 if odt == torch.bfloat16 else 2e-5)
+
+
+def test_linear_bf16_gelu_extremes(ops):
+    """The packed-fp16 GELU epilogue stays finite and exact in the tails (|x| far beyond the fp16 range)."""
+    M, N, K = 256, 64, 64
+    x = torch.zeros(M, K).bfloat16()
+    w = torch.zeros(N, K).bfloat16()
+    b = torch.linspace(-3e5, 3e5, N)
+    got = ops.linear(x.to(DEV), w.to(DEV), b.to(DEV), None, True, out_dtype=torch.bfloat16).float().cpu()
+    want = F.gelu(b.double()).float().bfloat16().float().expand(M, N)
+    assert torch.isfinite(got).all()
+    big = b.abs() < 6.0e4                                   # inside the fp16 range: exact tails
+    assert torch.equal(got[:, big], want[:, big])
+    assert (got[:, b < -6.0e4] == 0).all() and (got[:, b > 6.0e4] >= 6.0e4).all()
+
+
 def _attn_case(H, W, heads, hd, shift, pano, B=2, seed=0, ws=7):
     g = _g(seed + H * 7 + W)
     C = heads * hd

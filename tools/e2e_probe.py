@@ -29,14 +29,9 @@ print("duplex: ms for 256MiB each way", t(both))
 model = bench.build_model(dev)
 img = torch.rand(32, 3, 512, 1024).pin_memory()
 dimg = img.to(dev)
-for bs in (32, 16, 8, 4, 2):
-    x = dimg[:bs]
-    ms = t(lambda: model(x), 5)
-    print(f"device-resident forward batch {bs}: {ms:.2f} ms -> {bs / ms * 1e3:.0f} img/s")
-for graphs in (False, True):
-    for chunk in (16, 8, 4, 2):
-        pipe = HostPipeline(model, chunk=chunk, graphs=graphs)
-        ms = t(lambda: pipe(img), 5)
-        print(f"pipeline graphs={graphs} chunk {chunk}: {ms:.2f} ms -> {32 / ms * 1e3:.0f} img/s", flush=True)
-        del pipe
-        torch.cuda.empty_cache()
+for sizes in ([4, 8, 8, 8, 4], [4] * 8, [2, 4, 6, 8, 8, 4], [4, 6, 6, 8, 8], [3, 5, 8, 8, 8], [8] * 4, [2, 6, 8, 8, 8], [6, 6, 6, 6, 8]):
+    pipe = HostPipeline(model, graphs=True, sizes=sizes)
+    ms = min(t(lambda: pipe(img), 5) for _ in range(2))
+    print(f"pipeline sizes {sizes}: {ms:.2f} ms -> {32 / ms * 1e3:.0f} img/s", flush=True)
+    del pipe
+    torch.cuda.empty_cache()
