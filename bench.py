@@ -124,6 +124,9 @@ def launch_work(fn, a):
         B, H, W, cin, cout = a[4], a[5], a[6], a[7], a[8]
         return dict(kind="stem_conv1", shape=f"B{B} {H}x{W} {cin}->{cout}", bytes=float(B * H * W * (cin * 4 + cout * 2)),
                     flops=2.0 * B * H * W * cin * 9 * cout)
+    if fn == "psw_stem_conv3x3_c32_relu_fwd":
+        B, H, W, co = a[4], a[5], a[6], a[7]
+        return dict(kind="stem_conv2", shape=f"B{B} {H}x{W} 32->{co}", bytes=float(B * H * W * (64 + 2 * co)), flops=2.0 * B * H * W * 288 * co)
     return dict(kind=fn, shape="", bytes=0.0, flops=0.0)
 
 
@@ -340,7 +343,7 @@ def run_ours(args):
                                f"bf16 activations / {args.residual} residual stream, random-init weights",
                    "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective in the forward",
                    "l2": "inputs (201 MB of images, >=400 MB activations per layer) exceed the 126 MB L2; no explicit flush",
-                   "stem": "conv stem runs on cuDNN (torch), everything after it on libpanoswin_b200",
+                   "stem": "conv1 / conv2 of the stem on libpanoswin_b200 (tcgen05), the 4x4/s4 patch conv on cuDNN (torch), everything after it on libpanoswin_b200",
                    "launch": "eager" if args.eager else "CUDA-graph replay of the forward (timed region); eager for the per-kernel trace"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -149,6 +149,15 @@ PSW_API int psw_layernorm_nchw_fwd(const void* x, float* y, const float* gamma, 
 PSW_API int psw_stem_conv3x3_relu_fwd(const float* img, const float* w_folded, const float* bias_folded, void* out,
                                       int B, int H, int W, int cin, int cout, void* stream);
 
+/*
+ * Stem, second layer: conv3x3(32 -> cout, padding 1) + eval-mode BatchNorm + ReLU (PatchEmbed.proj[3..5], reference
+ * :746-748; cout = 64 for embed_dim 96) on tcgen05, NHWC bf16 in and out: x [B, H, W, 32] -> out [B, H, W, cout].
+ * w_taps [9][cout][32 in] bf16 with tap = ky*3 + kx holds the BatchNorm-folded weights, bias [cout] fp32 the folded
+ * bias.  cout must be 32 or 64.
+ */
+PSW_API int psw_stem_conv3x3_c32_relu_fwd(const void* x, const void* w_taps, const float* bias, void* out,
+                                          int B, int H, int W, int cout, void* stream);
+
 /* dtype conversion helper for activations entering / leaving the bf16 path: n elements. */
 PSW_API int psw_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
 

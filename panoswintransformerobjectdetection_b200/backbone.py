@@ -408,9 +408,19 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                                            conv3.bias.to(torch.bfloat16)),
                                           ((conv1.weight * s1[:, None, None, None]).reshape(conv1.out_channels, -1).float().contiguous(),
                                            ((conv1.bias - bn1.running_mean) * s1 + bn1.bias).float().contiguous()))
+            s2 = bn2.weight / torch.sqrt(bn2.running_var + bn2.eps)           # conv2 for psw_stem_conv3x3_c32_relu_fwd:
+            self._weight_cache["stem2"] = (                                    # [tap = ky*3+kx][out][in] bf16, fp32 bias
+                (conv2.weight * s2[:, None, None, None]).permute(2, 3, 0, 1).reshape(9, conv2.out_channels, -1)
+                .to(torch.bfloat16).contiguous(), ((conv2.bias - bn2.running_mean) * s2 + bn2.bias).float().contiguous())
             self._weight_cache["stem_key"] = key
         (w1, b1), (w2, b2), (w3, b3), (w1f, b1f) = self._weight_cache["stem"]
         own_conv1 = conv1.in_channels == 3 and conv1.out_channels == 32       # libpanoswin_b200 tcgen05 conv (E = 96)
+        own_conv2 = own_conv1 and conv2.in_channels == 32 and conv2.out_channels in (32, 64) and conv2.kernel_size == (3, 3)
+        if own_conv2:
+            w2t, b2f = self._weight_cache["stem2"]
+            y = ops.stem_conv3x3_c32_relu(ops.stem_conv3x3_relu(x.contiguous(), w1f, b1f), w2t, b2f).permute(0, 3, 1, 2)
+            y = F.conv2d(y, w3, b3, stride=pe.patch_size)
+            return y.permute(0, 2, 3, 1).contiguous()      # no copy when the conv output is channels-last
         if own_conv1:
             # fp32 NCHW image -> bf16 NHWC, seen by the next convolution as a channels-last NCHW tensor (no copy)
             y = ops.stem_conv3x3_relu(x.contiguous(), w1f, b1f).permute(0, 3, 1, 2)

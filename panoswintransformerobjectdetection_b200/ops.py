@@ -224,6 +224,21 @@ def stem_conv3x3_relu(img, w_folded, bias_folded):
     return out
 
 
+def stem_conv3x3_c32_relu(x_nhwc, w_taps, bias):
+    """conv3x3(32 -> cout, pad 1) + folded BatchNorm + ReLU on NHWC bf16 [B, H, W, 32] -> [B, H, W, cout] (reference
+    PatchEmbed.proj[3..5], :746-748).  w_taps [9, cout, 32 in] bf16 (tap = ky*3 + kx), bias [cout] fp32; cout 32 or 64."""
+    dev = _chk(x_nhwc, w_taps, bias)
+    B, H, W, C = x_nhwc.shape
+    cout = w_taps.shape[1]
+    if C != 32 or x_nhwc.dtype != torch.bfloat16 or tuple(w_taps.shape) != (9, cout, 32) or w_taps.dtype != torch.bfloat16:
+        raise PanoSwinB200Error("stem_conv3x3_c32_relu wants bf16 NHWC x [B,H,W,32] and bf16 w_taps [9,cout,32]")
+    out = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=x_nhwc.device)
+    with torch.cuda.device(dev):
+        _call("psw_stem_conv3x3_c32_relu_fwd", _ptr(x_nhwc), _ptr(w_taps), _ptr(_f32(bias, "bias")), _ptr(out), B, H, W,
+              cout, _stream(dev))
+    return out
+
+
 def cast(x, dtype):
     dev = _chk(x)
     out = torch.empty(x.shape, dtype=dtype, device=x.device)

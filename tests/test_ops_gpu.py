@@ -262,3 +262,21 @@ def test_stem_conv_rejects_unsupported_shapes(ops):
         ops.stem_conv3x3_relu(torch.zeros(1, 3, 8, 70, device=DEV), w, b)
     with pytest.raises(PanoSwinB200Error):                      # built for 3 -> 32 channels
         ops.stem_conv3x3_relu(torch.zeros(1, 3, 8, 64, device=DEV), torch.zeros(48, 27, device=DEV), torch.zeros(48, device=DEV))
+
+
+@pytest.mark.parametrize("cout", [32, 64])
+@pytest.mark.parametrize("B,H,W", [(1, 8, 128), (2, 13, 100), (1, 4, 260), (3, 33, 129), (2, 64, 256)])
+def test_stem_conv2_tcgen05(ops, B, H, W, cout):
+    """conv3x3 32->32 + folded BN + ReLU on NHWC bf16 (implicit GEMM over shifted patch views) vs torch fp32,
+    including ragged heights / widths (zero padding comes from TMA out-of-bounds fill)."""
+    g = _g(B * 1000 + H * 10 + W)
+    x = torch.randn(B, H, W, 32, generator=g).bfloat16()
+    w = (torch.randn(cout, 32, 3, 3, generator=g) / 17.0).bfloat16()
+    b = torch.randn(cout, generator=g)
+    want = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1)).permute(0, 2, 3, 1)
+    w_taps = w.permute(2, 3, 0, 1).reshape(9, cout, 32).contiguous()
+    got = ops.stem_conv3x3_c32_relu(x.to(DEV), w_taps.to(DEV), b.to(DEV))
+    torch.cuda.synchronize()
+    assert got.shape == (B, H, W, cout) and got.dtype == torch.bfloat16
+    assert rel_l2(got.float(), want) <= 4e-3
+    assert (got.float().cpu() - want).abs().max() <= 0.05

@@ -16,3 +16,16 @@ for _ in range(10):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 print(f"stem conv1: {ms*1e3:.1f} us  {img.numel()*4/1e9/ms*1e3 + y.numel()*2/1e9/ms*1e3:.0f} GB/s")
+x2 = y
+w2 = (torch.randn(9, 64, 32, device=dev) / 17).bfloat16()
+b = torch.randn(64, device=dev) * 0.1
+outs = [torch.empty_like(x2) for _ in range(2)]
+for _ in range(3):
+    z = ops.stem_conv3x3_c32_relu(x2, w2, b)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(10):
+    z = ops.stem_conv3x3_c32_relu(x2, w2, b)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+print(f"stem conv2: {ms*1e3:.1f} us  {(x2.numel() + z.numel())*2/1e9/ms*1e3:.0f} GB/s")
