@@ -7,6 +7,7 @@ template <typename T>
 int window_attn_simt(const T* qkv, T* out, const float* alpha, const float* beta, const float* qkv_bias,
                      const float* uv, const float* mask, int B, int H, int W, int C, int heads, int window, int shift,
                      int pano, float scale, cudaStream_t st);
+void attn_debug_set_hc(int hc);
 int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const void* tables,
                    const float* qkv_bias, const void* hav_table, const float* mask, int B, int H, int W, int C,
                    int heads, int window, int shift, int pano, float scale, long long* dbg, int mode, cudaStream_t st);
@@ -59,7 +60,8 @@ extern "C" PSW_API int psw_window_bias_tables(const float* alpha, const float* b
 
 // Diagnostics: same as the PSW_BF16 path of psw_window_attn_fwd, plus per-phase SM-cycle totals of CTA 0 written to
 // phase_cycles[6] (device memory, may be NULL): {wait-for-loads, S MMA, softmax, P.V MMA, store, steps}.
-// mode 1 runs the memory skeleton only (same gathers and stores, no MMA / softmax; output = q rows).
+// mode 1 runs the memory skeleton only (same gathers and stores, no MMA / softmax; output = q rows); mode bits
+// [8,12) force the number of heads per work item.
 extern "C" PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, const float* alpha, const float* beta,
                                                    const void* bias_tables, const float* qkv_bias,
                                                    const void* hav_table, int B, int H, int W,
@@ -67,9 +69,12 @@ extern "C" PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, c
                                                    long long* phase_cycles, int mode, void* stream) {
   int rc = check_attn_args(qkv, out, alpha, beta, hav_table, B, H, W, C, heads, window, shift, 1);
   if (rc) return rc;
-  PSW_REQUIRE(C / heads == 32 && (mode == 0 || mode == 1), PSW_ERR_BAD_ARG, "psw_window_attn_fwd_profile: bad arguments");
-  return window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, nullptr, B, H, W, C,
-                        heads, window, shift, 1, scale, phase_cycles, mode, (cudaStream_t)stream);
+  PSW_REQUIRE(C / heads == 32 && ((mode & 0xff) == 0 || (mode & 0xff) == 1), PSW_ERR_BAD_ARG, "psw_window_attn_fwd_profile: bad arguments");
+  attn_debug_set_hc((mode >> 8) & 15);                       // bits [8,12): force the heads-per-item choice
+  rc = window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, nullptr, B, H, W, C,
+                      heads, window, shift, 1, scale, phase_cycles, mode & 0xff, (cudaStream_t)stream);
+  attn_debug_set_hc(0);
+  return rc;
 }
 
 extern "C" PSW_API int psw_window_grid(int H, int W, int window, int pano_mode, int* nwh, int* nww) {

@@ -30,6 +30,9 @@
 
 namespace psw {
 
+int attn_debug_hc();          // diagnostics: force the heads-per-item choice (0 = heuristic)
+
+
 constexpr int AT_THREADS = 128;
 constexpr int AT_PART_BYTES = 128 * 64;            // 128 rows x 64 B (32 bf16), SWIZZLE_64B
 constexpr int AT_BUF_BYTES = 3 * AT_PART_BYTES;    // q, k, v
@@ -522,8 +525,12 @@ int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* 
   p.mask = mask;
   p.g = make_geom(H, W, window, shift, pano);
   p.B = B; p.C = C; p.heads = heads; p.scale = scale; p.dbg = dbg; p.mode = mode;
-  p.hc = heads % 3 == 0 ? 3 : (heads % 4 == 0 ? 4 : (heads % 2 == 0 ? 2 : 1));
   p.n_windows = B * p.g.nWh * p.g.nWw;
+  // heads per work item: one.  Sharing a window pair's token maps / distance rows between the heads of a wider
+  // item saves little (measured: equal at stage 0), while single-head items balance the small launches of the late
+  // stages better (items are dealt out in contiguous ranges: a CTA runs ceil(items / CTAs) of them; -10% at stage 3).
+  p.hc = 1;
+  if (attn_debug_hc() > 0 && heads % attn_debug_hc() == 0) p.hc = attn_debug_hc();
   p.n_items = ((p.n_windows + 1) / 2) * (heads / p.hc);
   const size_t smem = attn_tc_smem_bytes(window, C);
   PSW_REQUIRE(smem <= 220 * 1024, PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd(bf16): C=%d too large", C);
@@ -536,6 +543,10 @@ int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* 
   kern<<<grid, AT_THREADS, smem, st>>>(p);
   return launch_status("window_attn_tc_kernel");
 }
+
+static int g_attn_hc = 0;
+int attn_debug_hc() { return g_attn_hc; }
+void attn_debug_set_hc(int hc) { g_attn_hc = hc; }
 
 int window_hav_table(const float* uv, void* table, int H, int W, int window, int shift, cudaStream_t st) {
   WinGeom g = make_geom(H, W, window, shift, 1);

@@ -14,11 +14,10 @@ run linear_f32 300 python -m pytest tests/test_ops_gpu.py -q -k "linear_fp32"
 run attn_f32 300 python -m pytest tests/test_ops_gpu.py -q -k "window_attention_fp32 or no_qkv_bias"
 run linear_tc 300 python -m pytest tests/test_ops_gpu.py -q -k "linear_bf16"
 run attn_simt16 300 python -m pytest tests/test_ops_gpu.py -q -k "window_attention_bf16 and simt"
-run attn_tc0 300 python -m pytest tests/test_ops_gpu.py -q -k "window_attention_bf16 and tc0"
-run attn_tc1 300 python -m pytest tests/test_ops_gpu.py -q -k "window_attention_bf16 and tc1"
+run attn_tc 300 python -m pytest tests/test_ops_gpu.py -q -k "window_attention_bf16 and not simt"
+run stem 300 python -m pytest tests/test_ops_gpu.py -q -k "stem"
 run diag_linear 200 python tools/gpu_diag.py linear
-run diag_attn0 200 python tools/gpu_diag.py attn0
-run diag_attn1 200 python tools/gpu_diag.py attn1
+run diag_attn 200 python tools/gpu_diag.py attn
 run diag_attnsimt 200 python tools/gpu_diag.py attnsimt
 run backbone 600 python -m pytest tests/test_backbone_gpu.py -q
 run smoke 300 python __graft_entry__.py smoke

@@ -1,5 +1,5 @@
 """GPU diagnostics with numbers instead of pass/fail (first contact with new tcgen05 kernels).
-usage: python tools/gpu_diag.py {linear|attn0|attn1|attnsimt}   — dumps tensors to gpurun_out/ for offline analysis."""
+usage: python tools/gpu_diag.py {linear|attn|attnsimt}   — dumps tensors to gpurun_out/ for offline analysis."""
 import os
 import sys
 

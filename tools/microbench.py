@@ -263,3 +263,34 @@ def linear_sweep(iters=20):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "linsweep":
     linear_sweep()
+
+
+def attn_hc(iters=20):
+    """Heads-per-item sweep of the attention kernel (profile entry, mode bits [8,12))."""
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    for (H, W, C, heads) in [(128, 256, 96, 3), (64, 128, 192, 6), (32, 64, 384, 12), (16, 32, 768, 24)]:
+        nb = max(2, int(400e6 // (B * H * W * 4 * C * 2)) + 1)
+        qkv = [torch.randn(B, H, W, 3 * C, device=DEV).bfloat16() for _ in range(nb)]
+        out = [torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
+        alpha = torch.randn(169, heads, device=DEV) * 0.1
+        beta = torch.randn(169, heads, device=DEV) * 0.1
+        qb = torch.randn(3 * C, device=DEV) * 0.1
+        hav = ops.window_hav_table(make_uv_hw2(H, W).to(DEV), 7, 3)
+        bt = ops.window_bias_tables(alpha, beta, 7)
+        res = []
+        for hc in (0, 1, 2, 3, 4):
+            if hc and heads % hc:
+                continue
+            def run(i):
+                rc = lib.psw_window_attn_fwd_profile(qkv[i].data_ptr(), out[i].data_ptr(), alpha.data_ptr(), beta.data_ptr(),
+                                                     bt.data_ptr(), qb.data_ptr(), hav.data_ptr(), B, H, W, C, heads, 7, 3, 32 ** -0.5, None,
+                                                     hc << 8, torch.cuda.current_stream().cuda_stream)
+                _lib.check(rc, "profile")
+            us = min(time_op(run, nb, iters) for _ in range(2))
+            res.append(f"hc{hc if hc else '-auto'} {us:.1f}")
+        print(f"attn {H}x{W} C{C} h{heads}: " + "  ".join(res), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "attnhc":
+    attn_hc()
