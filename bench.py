@@ -103,6 +103,13 @@ def launch_work(fn, a):
         nwin_w = -(-(((W + 1) // 2) if a[16] else W) // ws)
         flops = 4.0 * (ws * ws) ** 2 * (C // heads) * B * nwin_h * nwin_w * heads
         return dict(kind="window_attn", shape=f"B{B} {H}x{W} C{C} h{heads} s{a[15]}", bytes=4.0 * tok * C * es, flops=flops)
+    if fn == "psw_window_attn_full_fwd":
+        B, H, W, C, heads, ws, pano = a[4], a[5], a[6], a[7], a[8], a[9], a[11]
+        tok = B * H * W
+        nwin_h = -(-(2 * H if pano else H) // ws)
+        nwin_w = -(-(((W + 1) // 2) if pano else W) // ws)
+        flops = 4.0 * (ws * ws) ** 2 * (C // heads) * B * nwin_h * nwin_w * heads
+        return dict(kind="window_attn", shape=f"B{B} {H}x{W} C{C} h{heads} s{a[10]}", bytes=8.0 * tok * C, flops=flops)
     if fn == "psw_linear_fwd":
         M, N, K = a[5], a[6], a[7]
         es, eo = sz[a[9]], sz[a[10]]

@@ -125,6 +125,23 @@ PSW_API int psw_window_bias_tables(const float* alpha, const float* beta, void* 
 PSW_API int psw_window_hav_table(const float* uv, void* table, int H, int W, int window, int shift, void* stream);
 
 /*
+ * Production bf16 path.  psw_window_bias_full() evaluates EVERY additive term of the attention logits of one block at
+ * one resolution — hav(uv_i, uv_j) * alpha[idx] + beta[idx] (_sphere_bias, reference :241-272, fp32 math) and, in planar
+ * mode, the shifted-window mask (:621-643; mask may be NULL) — for every window of ONE image and every head:
+ * table fp32 [windows][heads][13][64][4], element (i, j) at chunk j/4, row i, lane j%4; psw_window_bias_full_bytes()
+ * is its size.  It depends on the geometry and the block's alpha / beta only (not on the batch): build it once per
+ * block and resolution; the kernel reads it with 13 coalesced 16-byte loads per row (it stays L2-resident across the
+ * images of a batch).  psw_window_attn_full_fwd() is psw_window_attn_fwd(PSW_BF16) taking that table instead of
+ * alpha / beta / uv / hav_table / bias_tables / mask.
+ */
+PSW_API int64_t psw_window_bias_full_bytes(int H, int W, int heads, int window, int pano_mode);
+PSW_API int psw_window_bias_full(const float* alpha, const float* beta, const float* uv, const float* mask, void* table,
+                                 int H, int W, int heads, int window, int shift, int pano_mode, void* stream);
+PSW_API int psw_window_attn_full_fwd(const void* qkv, void* out, const void* bias_full, const float* qkv_bias,
+                                     int B, int H, int W, int C, int heads, int window, int shift, int pano_mode,
+                                     float scale, void* stream);
+
+/*
  * PatchMerging front half: 2x2 gather in the order (0,0),(1,0),(0,1),(1,1) with zero padding of odd
  * H/W, then LayerNorm(4C) (:563-574).  x [B, H, W, C] (in_dtype) -> y [B, ceil(H/2)*ceil(W/2), 4C]
  * (out_dtype).  The reduction Linear(4C -> 2C) (:575) is psw_linear_fwd.
@@ -170,7 +187,7 @@ PSW_API int psw_cast(const void* src, void* dst, int64_t n, int src_dtype, int d
  * gathers and stores without MMA / softmax (output = q rows), to measure what the access pattern alone sustains. */
 PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, const float* alpha, const float* beta,
                                         const void* bias_tables, const float* qkv_bias, const void* hav_table,
-                                        int B, int H, int W,
+                                        const void* bias_full, int B, int H, int W,
                                         int C, int heads, int window, int shift, float scale,
                                         long long* phase_cycles, int mode, void* stream);
 /* Process-wide diagnostic switch of the bf16 GEMM kernel (profiling only; 0 = normal operation, returns the previous

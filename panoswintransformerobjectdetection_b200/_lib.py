@@ -22,12 +22,15 @@ SIGNATURES = {
     "psw_window_bias_tables": [_fp, _fp, _vp, _i, _i, _vp],
     "psw_window_grid": [_i, _i, _i, _i, _vp, _vp],
     "psw_window_hav_table": [_fp, _vp, _i, _i, _i, _i, _vp],
+    "psw_window_bias_full_bytes": [_i, _i, _i, _i, _i],
+    "psw_window_bias_full": [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "psw_window_attn_full_fwd": [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "psw_patch_merge_ln_fwd": [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _f, _i, _i, _vp],
     "psw_layernorm_nchw_fwd": [_vp, _vp, _fp, _fp, _i, _i64, _i, _f, _i, _vp],
     "psw_stem_conv3x3_relu_fwd": [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],
     "psw_stem_conv3x3_c32_relu_fwd": [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _vp],
     "psw_cast": [_vp, _vp, _i64, _i, _i, _vp],
-    "psw_window_attn_fwd_profile": [_vp, _vp, _fp, _fp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp],
+    "psw_window_attn_fwd_profile": [_vp, _vp, _fp, _fp, _vp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp],
     "psw_debug_linear_mode": [_i],
     "psw_debug_linear_cycles": [_vp],
     "psw_debug_source_map": [_i, _i, _i, _i, _i, _vp, _i, _vp, _vp],
@@ -59,7 +62,7 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)            # AttributeError here = header / library mismatch
         fn.argtypes = argtypes
-        fn.restype = C.c_int
+        fn.restype = C.c_int64 if name == "psw_window_bias_full_bytes" else C.c_int
     lib.psw_last_error_string.argtypes = []
     lib.psw_last_error_string.restype = C.c_char_p
     _lib = lib

@@ -366,6 +366,19 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             self._weight_cache[k] = hit
         return hit[1]
 
+    def _bias_full(self, attn, uv, mask, H, W, ws, shift):
+        """Full additive-bias table of one block at one resolution for the bf16 attention kernel (great-circle +
+        relative-position bias, planar shift mask), cached until alpha / beta change."""
+        al, be = attn.sphere_position_alpha_table_Te, attn.sphere_position_beta_table_Te
+        k = ("bfull", id(attn), H, W, ws, shift, self.pano_mode)
+        ver = (al._version, be._version, al.data_ptr(), be.data_ptr())
+        hit = self._weight_cache.get(k)
+        if hit is None or hit[0] != ver:
+            hit = (ver, ops.window_bias_full(al.detach().contiguous(), be.detach().contiguous(), uv, mask, H, W, ws, shift,
+                                             self.pano_mode))
+            self._weight_cache[k] = hit
+        return hit[1]
+
     @staticmethod
     def _f(p: Optional[torch.Tensor]):
         return None if p is None else p.detach().contiguous()
@@ -516,17 +529,16 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                 mask = None
                 if not self.pano_mode and shift > 0:
                     mask = self._const(("mask", H, W, ws, shift), lambda: planar_attention_mask(H, W, ws, shift), dev)
-                hav = btab = None
-                if cd == torch.bfloat16:
-                    if self.pano_mode:
-                        hav = self._const(("hav", H, W, ws, shift), lambda: ops.window_hav_table(uv, ws, shift), dev)
-                    btab = self._bias_tables(a, ws)
                 xn = ops.layernorm(x, self._f(blk.norm1.weight), self._f(blk.norm1.bias), blk.norm1.eps, cd)
                 qkv = ops.linear(xn, self._w(a.qkv.weight, cd), self._f(a.qkv.bias))
-                att = ops.window_attention(qkv.view(B, H, W, 3 * C), self._f(a.sphere_position_alpha_table_Te),
-                                           self._f(a.sphere_position_beta_table_Te), self._f(a.qkv.bias), uv, mask,
-                                           a.num_heads, ws, shift, self.pano_mode, a.scale, hav_table=hav,
-                                           bias_tables=btab)
+                full_ok = cd == torch.bfloat16 and ws == 7 and C // a.num_heads == 32
+                if full_ok:                                  # tcgen05 kernel, all additive logit terms precomputed
+                    att = ops.window_attention_full(qkv.view(B, H, W, 3 * C), self._bias_full(a, uv, mask, H, W, ws, shift),
+                                                    self._f(a.qkv.bias), a.num_heads, ws, shift, self.pano_mode, a.scale)
+                else:
+                    att = ops.window_attention(qkv.view(B, H, W, 3 * C), self._f(a.sphere_position_alpha_table_Te),
+                                               self._f(a.sphere_position_beta_table_Te), self._f(a.qkv.bias), uv, mask,
+                                               a.num_heads, ws, shift, self.pano_mode, a.scale)
                 x = ops.linear(att.view(B, H * W, C), self._w(a.proj.weight, cd), self._f(a.proj.bias), residual=x, out=x)
                 xn = ops.layernorm(x, self._f(blk.norm2.weight), self._f(blk.norm2.bias), blk.norm2.eps, cd)
                 hid = ops.linear(xn, self._w(blk.mlp.fc1.weight, cd), self._f(blk.mlp.fc1.bias), gelu=True)

@@ -9,8 +9,11 @@ int window_attn_simt(const T* qkv, T* out, const float* alpha, const float* beta
                      int pano, float scale, cudaStream_t st);
 void attn_debug_set_hc(int hc);
 int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const void* tables,
-                   const float* qkv_bias, const void* hav_table, const float* mask, int B, int H, int W, int C,
-                   int heads, int window, int shift, int pano, float scale, long long* dbg, int mode, cudaStream_t st);
+                   const float* qkv_bias, const void* hav_table, const float* mask, const void* bias_full, int B, int H,
+                   int W, int C, int heads, int window, int shift, int pano, float scale, long long* dbg, int mode,
+                   cudaStream_t st);
+int window_bias_full(const float* alpha, const float* beta, const float* uv, const float* mask, void* table, int H, int W,
+                     int heads, int window, int shift, int pano, cudaStream_t st);
 int window_bias_tables(const float* alpha, const float* beta, void* tables, int heads, int window, cudaStream_t st);
 int window_hav_table(const float* uv, void* table, int H, int W, int window, int shift, cudaStream_t st);
 }  // namespace psw
@@ -47,8 +50,45 @@ extern "C" PSW_API int psw_window_attn_fwd(const void* qkv, void* out, const flo
   PSW_REQUIRE(aligned16(qkv) && aligned16(out), PSW_ERR_BAD_ARG, "psw_window_attn_fwd(bf16): pointers must be 16-byte aligned");
   PSW_REQUIRE(aligned16(hav_table), PSW_ERR_BAD_ARG, "psw_window_attn_fwd(bf16): great-circle table must be 16-byte aligned");
   PSW_REQUIRE(aligned16(bias_tables), PSW_ERR_BAD_ARG, "psw_window_attn_fwd(bf16): bias tables must be 16-byte aligned");
-  return window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, mask, B, H, W, C,
-                        heads, window, shift, pano_mode, scale, nullptr, 0, st);
+  return window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, mask, nullptr, B, H,
+                        W, C, heads, window, shift, pano_mode, scale, nullptr, 0, st);
+}
+
+// bf16 production path: every additive term of the logits (great-circle bias, relative-position bias, planar shift
+// mask) comes from the table psw_window_bias_full() built for this block and resolution.
+extern "C" PSW_API int psw_window_attn_full_fwd(const void* qkv, void* out, const void* bias_full, const float* qkv_bias,
+                                                int B, int H, int W, int C, int heads, int window, int shift,
+                                                int pano_mode, float scale, void* stream) {
+  PSW_REQUIRE(qkv && out && bias_full, PSW_ERR_BAD_ARG, "psw_window_attn_full_fwd: null pointer");
+  PSW_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && heads > 0 && window > 0, PSW_ERR_BAD_ARG,
+              "psw_window_attn_full_fwd: bad dims B=%d H=%d W=%d C=%d heads=%d window=%d", B, H, W, C, heads, window);
+  PSW_REQUIRE(C % heads == 0, PSW_ERR_BAD_ARG, "psw_window_attn_full_fwd: channels %d not divisible by heads %d", C, heads);
+  PSW_REQUIRE(shift >= 0 && shift < window, PSW_ERR_BAD_ARG, "psw_window_attn_full_fwd: shift_size must be in [0, window)");
+  PSW_REQUIRE((int64_t)B * H * W < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_window_attn_full_fwd: too many tokens");
+  PSW_REQUIRE(window * window <= 64 && C / heads == 32, PSW_ERR_UNSUPPORTED,
+              "psw_window_attn_full_fwd: tcgen05 kernel needs window^2 <= 64 and head_dim == 32 (window=%d head_dim=%d)",
+              window, C / heads);
+  PSW_REQUIRE(aligned16(qkv) && aligned16(out) && aligned16(bias_full), PSW_ERR_BAD_ARG,
+              "psw_window_attn_full_fwd: pointers must be 16-byte aligned");
+  return window_attn_tc((const bf16*)qkv, (bf16*)out, nullptr, nullptr, nullptr, qkv_bias, nullptr, nullptr, bias_full, B, H,
+                        W, C, heads, window, shift, pano_mode, scale, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" PSW_API int64_t psw_window_bias_full_bytes(int H, int W, int heads, int window, int pano_mode) {
+  if (H <= 0 || W <= 0 || heads <= 0 || window <= 0) return 0;
+  WinGeom g = make_geom(H, W, window, 0, pano_mode);
+  return (int64_t)g.nWh * g.nWw * heads * 13 * 64 * 16;
+}
+
+extern "C" PSW_API int psw_window_bias_full(const float* alpha, const float* beta, const float* uv, const float* mask,
+                                            void* table, int H, int W, int heads, int window, int shift, int pano_mode,
+                                            void* stream) {
+  PSW_REQUIRE(alpha && beta && table, PSW_ERR_BAD_ARG, "psw_window_bias_full: null pointer");
+  PSW_REQUIRE(H > 0 && W > 0 && heads > 0 && window > 0 && shift >= 0 && shift < window, PSW_ERR_BAD_ARG,
+              "psw_window_bias_full: bad dims H=%d W=%d heads=%d window=%d shift=%d", H, W, heads, window, shift);
+  PSW_REQUIRE(!pano_mode || uv, PSW_ERR_BAD_ARG, "psw_window_bias_full: pano mode needs the uv table");
+  PSW_REQUIRE(aligned16(table), PSW_ERR_BAD_ARG, "psw_window_bias_full: table must be 16-byte aligned");
+  return window_bias_full(alpha, beta, uv, mask, table, H, W, heads, window, shift, pano_mode, (cudaStream_t)stream);
 }
 
 extern "C" PSW_API int psw_window_bias_tables(const float* alpha, const float* beta, void* tables, int heads, int window,
@@ -64,15 +104,15 @@ extern "C" PSW_API int psw_window_bias_tables(const float* alpha, const float* b
 // [8,12) force the number of heads per work item.
 extern "C" PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, const float* alpha, const float* beta,
                                                    const void* bias_tables, const float* qkv_bias,
-                                                   const void* hav_table, int B, int H, int W,
+                                                   const void* hav_table, const void* bias_full, int B, int H, int W,
                                                    int C, int heads, int window, int shift, float scale,
                                                    long long* phase_cycles, int mode, void* stream) {
-  int rc = check_attn_args(qkv, out, alpha, beta, hav_table, B, H, W, C, heads, window, shift, 1);
+  int rc = check_attn_args(qkv, out, alpha, beta, bias_full ? bias_full : hav_table, B, H, W, C, heads, window, shift, 1);
   if (rc) return rc;
-  PSW_REQUIRE(C / heads == 32 && ((mode & 0xff) == 0 || (mode & 0xff) == 1), PSW_ERR_BAD_ARG, "psw_window_attn_fwd_profile: bad arguments");
+  PSW_REQUIRE(C / heads == 32 && (mode & 0xff) <= 2, PSW_ERR_BAD_ARG, "psw_window_attn_fwd_profile: bad arguments");
   attn_debug_set_hc((mode >> 8) & 15);                       // bits [8,12): force the heads-per-item choice
-  rc = window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, nullptr, B, H, W, C,
-                      heads, window, shift, 1, scale, phase_cycles, mode & 0xff, (cudaStream_t)stream);
+  rc = window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, nullptr, bias_full, B, H,
+                      W, C, heads, window, shift, 1, scale, phase_cycles, mode & 0xff, (cudaStream_t)stream);
   attn_debug_set_hc(0);
   return rc;
 }

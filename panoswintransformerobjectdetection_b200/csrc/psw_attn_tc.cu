@@ -44,6 +44,7 @@ constexpr int AT_CTAS_PER_SM = 4;                 // 128 registers per thread (n
 constexpr int AT_TAB_PITCH = 39;                   // half2 (alpha, beta) words per table row: 13 used; 39 = 7 mod 32 makes
                                                    // the row-per-lane lookups bank-conflict-free
 constexpr int AT_TAB_WORDS = 508;                  // 13 * 39 = 507 words per head, padded to a multiple of 4 (16 B)
+constexpr int AT_FULL_CHUNKS = 13;                 // float4 chunks per bias row: 49 logits padded to 52
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& r) {
@@ -108,6 +109,7 @@ struct AttnParams {
   const float* alpha;
   const float* beta;
   const __half2* tables;  // [heads][AT_TAB_WORDS] packed (alpha, beta) from psw_window_bias_tables
+  const float4* bias_full; // FULL kernels: [windows per image][heads][AT_FULL_CHUNKS][64 rows] x 4 fp32 from psw_window_bias_full
   const float* qkv_bias;
   const __half* hav;      // [wpi][N][56] or nullptr (planar mode: d == 0)
   const float* mask;
@@ -130,7 +132,10 @@ struct Step {
   int n;                  // running step count of this CTA (parity selects the buffers)
 };
 
-template <int WS, bool HAS_MASK>
+// FULL: the whole additive bias of a (window, head) -- great-circle term, relative-position term and, in planar mode,
+// the shift mask -- comes precomputed from p.bias_full (psw_window_bias_full): 13 coalesced 16-byte loads per row
+// instead of ~300 instructions of table lookups per row and step.
+template <int WS, bool HAS_MASK, bool FULL>
 __global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
 window_attn_tc_kernel(const AttnParams p) {
   constexpr int N = WS * WS;                     // tokens per window (<= 64)
@@ -262,7 +267,7 @@ window_attn_tc_kernel(const AttnParams p) {
       }
     }
     // per-head tables: one contiguous 2032-byte block, 127 x 16 B
-    if (tid < TABS / 4) cp_async16(tab + (st.n & 1) * TABS + 4 * tid, p.tables + (size_t)st.e * TABS + 4 * tid);
+    if (!FULL && tid < TABS / 4) cp_async16(tab + (st.n & 1) * TABS + 4 * tid, p.tables + (size_t)st.e * TABS + 4 * tid);
   };
 
   Step cur = first_step(item_begin);
@@ -281,6 +286,28 @@ window_attn_tc_kernel(const AttnParams p) {
 #pragma unroll
   for (int k = 0; k < AT_HAV_PITCH / 8; ++k) hreg[k] = make_uint4(0, 0, 0, 0);
   int hav_wp = -1;
+
+  // FULL: my row of the precomputed bias of a step, requested one step ahead (right after the previous softmax has
+  // consumed the registers) so the L2 latency hides behind the P.V MMA, the store and the next S MMA
+  float bfull[FULL ? 4 * AT_FULL_CHUNKS : 1];
+  auto load_bias = [&](const Step& st) {
+    if constexpr (FULL) {
+      const int w = 2 * st.wp + unit;
+      if (ti < N && w < p.n_windows && p.mode != 2) {        // mode 2 (diagnostics): bias loads skipped
+        const float4* brow = p.bias_full + ((size_t)(w % wpi) * heads + st.e) * (AT_FULL_CHUNKS * 64) + ti;
+#pragma unroll
+        for (int k = 0; k < AT_FULL_CHUNKS; ++k) {
+          const float4 b4 = __ldg(brow + k * 64);
+          bfull[4 * k] = b4.x; bfull[4 * k + 1] = b4.y; bfull[4 * k + 2] = b4.z; bfull[4 * k + 3] = b4.w;
+        }
+      }
+    }
+  };
+  if constexpr (FULL) {
+#pragma unroll
+    for (int k = 0; k < 4 * AT_FULL_CHUNKS; ++k) bfull[k] = 0.f;
+    if (item_begin < item_end) load_bias(cur);
+  }
 
   uint32_t par = 0;
   long long ph[6] = {0, 0, 0, 0, 0, 0};
@@ -333,7 +360,7 @@ window_attn_tc_kernel(const AttnParams p) {
     // MMA, which every thread has waited for) and fetch my distance row when the window pair changed
     if (has_next) issue_loads(nxt);
     cp_async_commit();
-    if (p.hav != nullptr && hav_wp != cur.wp) {
+    if (!FULL && p.hav != nullptr && hav_wp != cur.wp) {
       hav_wp = cur.wp;
       if (row_valid) {
         const uint4* grow = reinterpret_cast<const uint4*>(p.hav + ((size_t)(my_w % wpi) * N + ti) * AT_HAV_PITCH);
@@ -343,8 +370,10 @@ window_attn_tc_kernel(const AttnParams p) {
     }
     // still inside the MMA window: my row's bias d(i,j) * alpha[idx] + beta[idx] (+ mask) — independent of S.
     // Table entries of one key row are fetched as a batch of 7 before they are consumed (LDS latency overlaps).
-    float bia[N];
-    {
+    float bia[FULL ? 1 : N];
+    if constexpr (FULL) {
+      bia[0] = 0.f;
+    } else {
       const __half2* trow = tab + (cur.n & 1) * TABS + (ri + WS - 1) * TP + (ci + WS - 1);
       const float* mrow = nullptr;
       if constexpr (HAS_MASK) mrow = p.mask + ((int64_t)((my_w < p.n_windows ? my_w : 0) % wpi) * N + ic) * N;
@@ -390,7 +419,7 @@ window_attn_tc_kernel(const AttnParams p) {
       float mx = -INFINITY;
 #pragma unroll
       for (int j = 0; j < N; ++j) {
-        t[j] = fmaf(__uint_as_float(sr[j]), p.scale, bia[j]);
+        t[j] = fmaf(__uint_as_float(sr[j]), p.scale, FULL ? bfull[j] : bia[j]);
         mx = fmaxf(mx, t[j]);
       }
       const float mneg = -mx * LOG2E;
@@ -406,6 +435,7 @@ window_attn_tc_kernel(const AttnParams p) {
       tmem_st_x32(tmem_base + lane_base + AT_P_COL, pk);
       tmem_st_wait();
     }
+    if (FULL && has_next) load_bias(nxt);                  // the bias registers are free again
     tc_fence_before();
     __syncthreads();
 
@@ -471,6 +501,309 @@ window_attn_tc_kernel(const AttnParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Batch-innermost variant (production path for batches of 4 images or more, FULL bias only).
+// The 128-row tile holds the SAME window position and head of TWO images; a work item is (window position, head)
+// and its steps walk over the image pairs.  Everything that depends on the geometry or the head only -- the token
+// map of the window and the thread's 49-entry bias row -- is fetched once per item and kept (shared memory /
+// registers) for all of its steps, so a step is nothing but the q/k/v gather, the two MMAs, the softmax and the
+// store.  An item is cut into units of p.hc image pairs (chosen by the host for balance); units are numbered (window, chunk, head) with the
+// head fastest and CTA c runs units c, c + grid, c + 2 grid, ...: at any moment the resident CTAs work on ALL heads of
+// the same windows and images, so the head slices sharing a 128-byte line of the qkv rows meet in L2 (a contiguous
+// range per CTA separates them by ~40 us and doubles the DRAM reads -- measured).
+// ---------------------------------------------------------------------------------------------------
+struct BiStep {
+  int u;                  // unit index: (window position * chunks + chunk) * heads + head
+  int item;               // window position * heads + head
+  int bp;                 // image pair: images 2*bp, 2*bp + 1
+  int bp_end;             // end of the unit's image-pair range
+  int n;                  // running step count of this CTA (parity selects the q/k/v stage)
+  int ic;                 // running unit count of this CTA (parity selects the token-map slot)
+};
+
+template <int WS>
+__global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
+window_attn_bi_kernel(const AttnParams p) {
+  constexpr int N = WS * WS;
+  static_assert(N == 49, "TMEM row load below is written for 49 logits");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* bufs = smem;                                                  // [2 stages][3][128 x 64 B]
+  int* src = reinterpret_cast<int*>(bufs + 2 * AT_BUF_BYTES);            // [2 item slots][64]: token index in the image or -1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(src + 2 * 64);            // [2]: S ready, O ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int C = p.C, heads = p.heads, C3 = 3 * p.C;
+  const WinGeom g = p.g;
+  const int64_t HW = (int64_t)g.H * g.W;
+  const int BP = (p.B + 1) / 2;                            // steps per item
+
+  for (int i = tid; i < 2 * AT_BUF_BYTES / 16; i += AT_THREADS)
+    reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0, 0, 0, 0);          // padding rows must stay finite
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(AT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  auto bias_chunk = [&](int ch) {
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (p.qkv_bias) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.qkv_bias + ch));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.qkv_bias + ch) + 1);
+      r = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+    return r;
+  };
+
+  const int n_units = p.n_items;                           // (window positions) x chunks x heads
+  const int CH = p.hc;                                     // image pairs per unit
+  const int NCH = (BP + CH - 1) / CH;
+
+  const int unit = tid >> 6;                               // warp-uniform: which image of the pair
+  const int ti = tid & 63;
+  const int ic = ti < N ? ti : 0;
+  const int ri = ic / WS, ci = ic - ri * WS;
+  const int lc = tid & 3;
+  const int lt0 = tid >> 2;
+
+  auto decode = [&](BiStep& st) {                          // unit index -> item and image-pair range
+    const int e = st.u % heads;
+    const int wc = st.u / heads;
+    const int chunk = wc % NCH;
+    st.item = (wc / NCH) * heads + e;
+    st.bp = chunk * CH;
+    st.bp_end = st.bp + CH < BP ? st.bp + CH : BP;
+  };
+  auto first_step = [&](int u) {
+    BiStep st;
+    st.u = u; st.n = 0; st.ic = 0;
+    decode(st);
+    return st;
+  };
+  auto next_step = [&](BiStep st) {
+    ++st.n;
+    if (++st.bp == st.bp_end) {
+      st.u += gridDim.x;
+      ++st.ic;
+      if (st.u < n_units) decode(st);
+    }
+    return st;
+  };
+  // token map of the item's window position -> src[ic & 1] (threads 0..63)
+  auto prep_item = [&](const BiStep& st) {
+    if (tid < 64) {
+      int t = -1;
+      if (tid < N) {
+        const int wi = st.item / heads;
+        const int wr = wi / g.nWw, wc = wi - wr * g.nWw;
+        t = source_token(g, wr * WS + ri, wc * WS + ci);
+      }
+      src[(st.ic & 1) * 64 + tid] = t;
+    }
+  };
+  int ld_t[2], ld_dst[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int t = lt0 + 32 * (k & 1);
+    if (k < 2) ld_t[k] = t < N ? t : -1;
+    const int row = (k >> 1) * 64 + t;
+    ld_dst[k] = row * 64 + ((lc ^ ((row >> 1) & 3)) << 4);
+  }
+  auto issue_loads = [&](const BiStep& st) {
+    uint8_t* base = bufs + (st.n & 1) * AT_BUF_BYTES;
+    const int* smap = src + (st.ic & 1) * 64;
+    const int e = st.item % heads;
+    const bf16* gq = p.qkv + e * 32 + lc * 8;
+    const int bch = e * 32 + lc * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int b = 2 * st.bp + (k >> 1);
+      if (ld_t[k & 1] >= 0 && b < p.B) {
+        const int t = smap[ld_t[k & 1]];
+        uint8_t* dst = base + ld_dst[k];
+        if (t >= 0) {
+          const bf16* grow = gq + ((int64_t)b * HW + t) * C3;
+          cp_async16(dst, grow);
+          cp_async16(dst + AT_PART_BYTES, grow + C);
+          cp_async16(dst + 2 * AT_PART_BYTES, grow + 2 * C);
+        } else {                                           // padding cell: q/k/v = bias
+          *reinterpret_cast<uint4*>(dst) = bias_chunk(bch);
+          *reinterpret_cast<uint4*>(dst + AT_PART_BYTES) = bias_chunk(bch + C);
+          *reinterpret_cast<uint4*>(dst + 2 * AT_PART_BYTES) = bias_chunk(bch + 2 * C);
+        }
+      }
+    }
+  };
+  // my row of the item's precomputed bias: [window][head][chunk][row] float4
+  float bias[4 * AT_FULL_CHUNKS];
+  auto load_bias = [&](const BiStep& st) {
+    if (ti < N && p.mode != 2) {
+      const float4* brow = p.bias_full + (size_t)st.item * (AT_FULL_CHUNKS * 64) + ti;
+#pragma unroll
+      for (int k = 0; k < AT_FULL_CHUNKS; ++k) {
+        const float4 b4 = __ldg(brow + k * 64);
+        bias[4 * k] = b4.x; bias[4 * k + 1] = b4.y; bias[4 * k + 2] = b4.z; bias[4 * k + 3] = b4.w;
+      }
+    }
+  };
+#pragma unroll
+  for (int k = 0; k < 4 * AT_FULL_CHUNKS; ++k) bias[k] = 0.f;
+
+  BiStep cur = first_step(blockIdx.x);
+  if (cur.u < n_units) {
+    prep_item(cur);
+    const BiStep n1 = next_step(cur);
+    if (n1.u < n_units && n1.ic != cur.ic) prep_item(n1);
+    __syncthreads();
+    issue_loads(cur);
+    load_bias(cur);
+  }
+  cp_async_commit();
+
+  uint32_t par = 0;
+  long long ph[6] = {0, 0, 0, 0, 0, 0};
+  const bool prof = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  while (cur.u < n_units) {
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+    if (prof) c0 = clock64();
+    const BiStep nxt = next_step(cur);
+    const bool has_next = nxt.u < n_units;
+    const int my_b = 2 * cur.bp + unit;
+    const bool row_valid = (ti < N) && (my_b < p.B);
+    const int e = cur.item % heads;
+    // ---- 1. this step's q/k/v (requested one step ago) have landed
+    cp_async_wait<0>();
+    fence_async_shared();
+    __syncthreads();
+    if (prof) c1 = clock64();
+    // ---- 2. S = Q . K^T (both images at once, block diagonal)
+    const uint32_t sq = smem_u32(bufs + (cur.n & 1) * AT_BUF_BYTES);
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+      const uint64_t dq = umma_smem_desc(sq, 16, 512, UMMA_SWIZZLE_64B);
+      const uint64_t dk = umma_smem_desc(sq + AT_PART_BYTES, 16, 512, UMMA_SWIZZLE_64B);
+      umma_ss(tmem_base, dq, dk, idesc, 0);
+      umma_ss(tmem_base, dq + 2, dk + 2, idesc, 1);
+      umma_commit(&bars[0]);
+    }
+    if (has_next) issue_loads(nxt);                        // whole next step into the other stage
+    cp_async_commit();
+    mbar_wait(&bars[0], par);
+    tc_fence_after();
+    if (prof) c2 = clock64();
+    // ---- 3. bias + softmax on my row
+    float sum = 1.f;
+    {
+      uint32_t sr[N];
+      const uint32_t s_addr = tmem_base + lane_base + (uint32_t)(unit * 64);
+      {
+        uint32_t t32[32], t16[16], t1;
+        tmem_ld_x32(s_addr, t32);
+        tmem_ld_x16(s_addr + 32, t16);
+        tmem_ld_x1(s_addr + 48, t1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) sr[k] = t32[k];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sr[32 + k] = t16[k];
+        sr[48] = t1;
+      }
+      float t[N];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        t[j] = fmaf(__uint_as_float(sr[j]), p.scale, bias[j]);
+        mx = fmaxf(mx, t[j]);
+      }
+      const float mneg = -mx * LOG2E;
+      sum = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        float p0 = 0.f, p1 = 0.f;
+        if (2 * k < N) { p0 = fast_exp2(fmaf(t[2 * k], LOG2E, mneg)); sum += p0; }
+        if (2 * k + 1 < N) { p1 = fast_exp2(fmaf(t[2 * k + 1], LOG2E, mneg)); sum += p1; }
+        pk[k] = row_valid ? pack_bf16x2(p0, p1) : 0u;
+      }
+      tmem_st_x32(tmem_base + lane_base + AT_P_COL, pk);
+      tmem_st_wait();
+    }
+    if (has_next && nxt.ic != cur.ic) load_bias(nxt);      // new (window, head): the bias registers are free again
+    tc_fence_before();
+    __syncthreads();
+    if (prof) c3 = clock64();
+    // ---- 4. O = P . [V_img0 | V_img1]
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+      const uint32_t sv = sq + 2 * AT_PART_BYTES;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t dv = umma_smem_desc(sv + k * 1024, 4096, 512, UMMA_SWIZZLE_64B);
+        umma_ts(tmem_base + AT_O_COL, tmem_base + AT_P_COL + k * 8, dv, idesc, k > 0);
+      }
+      umma_commit(&bars[1]);
+    }
+    // while the MMA runs: token map of the item after next's first step (its loader runs after the next barriers)
+    if (has_next) {
+      const BiStep nn = next_step(nxt);
+      if (nn.u < n_units && nn.ic != nxt.ic) prep_item(nn);
+    }
+    mbar_wait(&bars[1], par);
+    tc_fence_after();
+    if (prof) c4 = clock64();
+    // ---- 5. normalise and store my output row at the token's un-shifted position
+    {
+      uint32_t orow[32];
+      tmem_ld_x32(tmem_base + lane_base + AT_O_COL + (uint32_t)(unit * 32), orow);
+      tmem_ld_wait();
+      const int ts = src[(cur.ic & 1) * 64 + ic];
+      if (row_valid && ts >= 0) {
+        const float inv = 1.0f / sum;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)my_b * HW + ts) * C + e * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(orow[8 * c + 0]) * inv, __uint_as_float(orow[8 * c + 1]) * inv);
+          v.y = pack_bf16x2(__uint_as_float(orow[8 * c + 2]) * inv, __uint_as_float(orow[8 * c + 3]) * inv);
+          v.z = pack_bf16x2(__uint_as_float(orow[8 * c + 4]) * inv, __uint_as_float(orow[8 * c + 5]) * inv);
+          v.w = pack_bf16x2(__uint_as_float(orow[8 * c + 6]) * inv, __uint_as_float(orow[8 * c + 7]) * inv);
+          dst[c] = v;
+        }
+      }
+    }
+    tc_fence_before();
+    if (prof) {
+      const long long c5 = clock64();
+      ph[0] += c1 - c0; ph[1] += c2 - c1; ph[2] += c3 - c2; ph[3] += c4 - c3; ph[4] += c5 - c4; ph[5] += 1;
+    }
+    par ^= 1;
+    cur = nxt;
+  }
+  if (prof)
+    for (int k = 0; k < 6; ++k) p.dbg[k] = ph[k];
+
+  cp_async_wait<0>();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(AT_TMEM_COLS) : "memory");
+  }
+}
+
 static size_t attn_tc_smem_bytes(int ws, int C) {
   const int TW = 2 * ws - 1;
   size_t b = 1024;                                   // alignment slack
@@ -500,6 +833,57 @@ __global__ void bias_tables_kernel(const float* __restrict__ alpha, const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Full additive bias of every (window of one image, head): bias[i][j] = hav(uv_i, uv_j) * alpha[idx(i,j)][head] +
+// beta[idx(i,j)][head] (+ mask[window][i][j] in planar mode), fp32, laid out for the kernel's row-per-lane reads:
+// [window][head][chunk k = j / 4][row i (64)][j % 4].  Depends on the geometry and on the block's alpha / beta, not
+// on the batch: built once per block and resolution, read (L2-resident) by every image.  Same formulas and fp32
+// evaluation order as the parity kernel (lzx/models/great_circle.py:82-86, reference :241-272).
+// ---------------------------------------------------------------------------------------------------
+__global__ void bias_full_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ uv,
+                                 const float* __restrict__ mask, float* __restrict__ table, WinGeom g, int heads) {
+  const int ws = g.ws, N = ws * ws, tw = 2 * ws - 1;
+  __shared__ float su[64], sv[64], scv[64];
+  const int wi = blockIdx.x, e = blockIdx.y;
+  const int wr = wi / g.nWw, wc = wi - wr * g.nWw;
+  for (int t = threadIdx.x; t < N; t += blockDim.x) {
+    const int r = t / ws, c = t - r * ws;
+    const int s = source_token(g, wr * ws + r, wc * ws + c);
+    float uu = 0.f, vv = 0.f;
+    if (s >= 0 && uv != nullptr) { uu = uv[2 * s]; vv = uv[2 * s + 1]; }
+    su[t] = uu; sv[t] = vv; scv[t] = cosf(vv);
+  }
+  __syncthreads();
+  float* out = table + ((size_t)wi * heads + e) * (AT_FULL_CHUNKS * 64 * 4);
+  for (int q = threadIdx.x; q < AT_FULL_CHUNKS * 64 * 4; q += blockDim.x) {
+    const int k = q >> 8, i = (q >> 2) & 63, j = 4 * k + (q & 3);
+    float b = 0.f;
+    if (i < N && j < N) {
+      float d = 0.f;
+      if (uv != nullptr) {
+        const float sdv = sinf(0.5f * fabsf(sv[j] - sv[i]));
+        const float sdu = sinf(0.5f * (su[j] - su[i]));
+        const float a = sdv * sdv + (scv[j] * scv[i]) * (sdu * sdu);
+        d = asinf(sqrtf(fminf(a, 1.0f))) * 2.0f;
+      }
+      const int ri = i / ws, ci = i - ri * ws, rj = j / ws, cj = j - rj * ws;
+      const int idx = (ri - rj + ws - 1) * tw + (ci - cj + ws - 1);
+      b = fmaf(d, alpha[idx * heads + e], beta[idx * heads + e]);
+      if (mask != nullptr) b += mask[((size_t)wi * N + i) * N + j];
+    }
+    out[q] = b;
+  }
+}
+
+int window_bias_full(const float* alpha, const float* beta, const float* uv, const float* mask, void* table, int H, int W,
+                     int heads, int window, int shift, int pano, cudaStream_t st) {
+  PSW_REQUIRE(window * window <= 4 * AT_FULL_CHUNKS && window * window <= 64, PSW_ERR_UNSUPPORTED,
+              "psw_window_bias_full: window %d too large", window);
+  WinGeom g = make_geom(H, W, window, shift, pano);
+  bias_full_kernel<<<dim3(g.nWh * g.nWw, heads), 256, 0, st>>>(alpha, beta, pano ? uv : nullptr, mask, (float*)table, g, heads);
+  return launch_status("bias_full_kernel");
+}
+
 int window_bias_tables(const float* alpha, const float* beta, void* tables, int heads, int window, cudaStream_t st) {
   const int tw = 2 * window - 1;
   PSW_REQUIRE(tw * AT_TAB_PITCH <= AT_TAB_WORDS, PSW_ERR_UNSUPPORTED, "psw_window_bias_tables: window %d too large", window);
@@ -509,18 +893,20 @@ int window_bias_tables(const float* alpha, const float* beta, void* tables, int 
 }
 
 int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const void* tables,
-                   const float* qkv_bias, const void* hav_table, const float* mask, int B, int H, int W, int C,
-                   int heads, int window, int shift, int pano, float scale, long long* dbg, int mode, cudaStream_t st) {
+                   const float* qkv_bias, const void* hav_table, const float* mask, const void* bias_full, int B, int H,
+                   int W, int C, int heads, int window, int shift, int pano, float scale, long long* dbg, int mode,
+                   cudaStream_t st) {
   PSW_REQUIRE(window == 7, PSW_ERR_UNSUPPORTED,
               "psw_window_attn_fwd(bf16): the tcgen05 kernel is instantiated for window 7 (every shipped PanoSwin config); got %d",
               window);
-  PSW_REQUIRE(tables != nullptr, PSW_ERR_BAD_ARG,
+  PSW_REQUIRE(bias_full != nullptr || tables != nullptr, PSW_ERR_BAD_ARG,
               "psw_window_attn_fwd(bf16): needs the per-head bias tables (psw_window_bias_tables)");
-  PSW_REQUIRE(!pano || hav_table, PSW_ERR_BAD_ARG,
+  PSW_REQUIRE(bias_full != nullptr || !pano || hav_table, PSW_ERR_BAD_ARG,
               "psw_window_attn_fwd(bf16): pano mode needs the great-circle table (psw_window_hav_table)");
   AttnParams p;
   p.qkv = qkv; p.out = out; p.alpha = alpha; p.beta = beta; p.qkv_bias = qkv_bias;
   p.tables = (const __half2*)tables;
+  p.bias_full = (const float4*)bias_full;
   p.hav = pano ? (const __half*)hav_table : nullptr;
   p.mask = mask;
   p.g = make_geom(H, W, window, shift, pano);
@@ -535,7 +921,26 @@ int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* 
   const size_t smem = attn_tc_smem_bytes(window, C);
   PSW_REQUIRE(smem <= 220 * 1024, PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd(bf16): C=%d too large", C);
   PSW_REQUIRE((int64_t)B * H * W < (1ll << 31) / 1, PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd(bf16): too many tokens");
-  auto kern = mask ? window_attn_tc_kernel<7, true> : window_attn_tc_kernel<7, false>;
+  const bool batch_inner = bias_full != nullptr && B >= 4 && attn_debug_hc() != 15 && (mode == 0 || mode == 2);
+  if (batch_inner) {
+    // image pairs per unit: as many as possible (the bias row and the token map are fetched once per unit) while the
+    // units still spread evenly over the resident CTAs (CTA c runs units c, c + grid, ...)
+    const int bp_total = (B + 1) / 2, ctas = num_sms() * AT_CTAS_PER_SM;
+    const int wh = p.g.nWh * p.g.nWw * heads;
+    double best = -1.0;
+    p.hc = 1;
+    for (int ch = 4; ch >= 1; ch >>= 1) {                 // measured: 8 is not better than 4 where both balance
+      const int64_t units = (int64_t)wh * ((bp_total + ch - 1) / ch);
+      const double steps_max = (double)((units + ctas - 1) / ctas) * ch;             // steps of the busiest CTA (upper bound)
+      const double eff = (double)wh * bp_total / ctas / steps_max;
+      const int forced = attn_debug_hc();
+      if (forced ? ch == forced : (best < 0.9 && eff > best + 1e-9)) { best = eff; p.hc = ch; }
+    }
+    p.n_items = wh * ((bp_total + p.hc - 1) / p.hc);                                // units: (window, chunk, head)
+  }
+  auto kern = batch_inner ? window_attn_bi_kernel<7>
+              : (bias_full ? window_attn_tc_kernel<7, false, true>
+                           : (mask ? window_attn_tc_kernel<7, true, false> : window_attn_tc_kernel<7, false, false>));
   PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int grid = num_sms() * AT_CTAS_PER_SM;

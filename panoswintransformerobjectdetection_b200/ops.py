@@ -151,6 +151,34 @@ def window_bias_tables(alpha, beta, window):
     return out
 
 
+def window_bias_full(alpha, beta, uv, mask, H, W, window, shift, pano_mode):
+    """Every additive term of the logits of one block at one resolution (great-circle + relative-position bias, planar
+    shift mask) for all windows of one image and all heads: fp32 [windows, heads, 13, 64, 4] for window_attention_full."""
+    dev = _chk(alpha, beta, uv, mask)
+    heads = alpha.shape[1]
+    nbytes = _lib.load().psw_window_bias_full_bytes(H, W, heads, window, 1 if pano_mode else 0)
+    out = torch.empty((nbytes // (heads * 13 * 64 * 16), heads, 13, 64, 4), dtype=torch.float32, device=alpha.device)
+    with torch.cuda.device(dev):
+        _call("psw_window_bias_full", _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta")), _ptr(_f32(uv, "uv")),
+              _ptr(_f32(mask, "mask")), _ptr(out), H, W, heads, window, shift, 1 if pano_mode else 0, _stream(dev))
+    return out
+
+
+def window_attention_full(qkv, bias_full, qkv_bias, heads, window, shift, pano_mode, scale, out=None):
+    """The bf16 tcgen05 attention kernel with the precomputed bias table of window_bias_full() (production path)."""
+    dev = _chk(qkv, bias_full, qkv_bias, out)
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    if qkv.dtype != torch.bfloat16:
+        raise PanoSwinB200Error("window_attention_full is the bf16 path")
+    if out is None:
+        out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
+    with torch.cuda.device(dev):
+        _call("psw_window_attn_full_fwd", _ptr(qkv), _ptr(out), _ptr(bias_full), _ptr(_f32(qkv_bias, "qkv_bias")), B, H, W, C,
+              heads, window, shift, 1 if pano_mode else 0, float(scale), _stream(dev))
+    return out
+
+
 def window_attention(qkv, alpha, beta, qkv_bias, uv, mask, heads, window, shift, pano_mode, scale, out=None,
                      impl=None, hav_table=None, bias_tables=None):
     """Fused shift + partition + W-MSA core + reverse + un-shift.  qkv [B, H, W, 3C] -> [B, H, W, C].

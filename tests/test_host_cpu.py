@@ -23,7 +23,7 @@ def lib():
 
 def _header_symbols():
     text = open(os.path.join(ROOT, "include", "panoswin_b200.h")).read()
-    return sorted(set(re.findall(r"PSW_API\s+(?:const\s+char\*|int)\s+(psw_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"PSW_API\s+(?:const\s+char\*|int64_t|int)\s+(psw_\w+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol(lib):

@@ -196,7 +196,7 @@ def test_window_attention_fp32(ops, case, hd):
 
 
 @pytest.mark.parametrize("case", ATTN_CASES)
-@pytest.mark.parametrize("impl", [None, "tables", "simt"])
+@pytest.mark.parametrize("impl", [None, "tables", "simt", "full"])
 def test_window_attention_bf16(ops, case, impl):
     H, W, heads, shift, pano = case
     qkv, alpha, beta, qb, uv, C = _attn_case(H, W, heads, 32, shift, pano, seed=5)
@@ -207,11 +207,35 @@ def test_window_attention_bf16(ops, case, impl):
                           shift, pano, scale)
     mask = O.planar_shift_mask(H, W, 7, shift).to(DEV) if (not pano and shift) else None
     bt = ops.window_bias_tables(alpha.to(DEV), beta.to(DEV), 7) if impl == "tables" else None
-    got = ops.window_attention(qkv.to(DEV), alpha.to(DEV), beta.to(DEV), qb.to(DEV), uv.to(DEV) if pano else None, mask,
-                               heads, 7, shift, pano, scale, impl="simt" if impl == "simt" else None, bias_tables=bt)
+    if impl == "full":                                           # production path: all additive terms precomputed (fp32)
+        bf = ops.window_bias_full(alpha.to(DEV), beta.to(DEV), uv.to(DEV) if pano else None, mask, H, W, 7, shift, pano)
+        got = ops.window_attention_full(qkv.to(DEV), bf, qb.to(DEV), heads, 7, shift, pano, scale)
+    else:
+        got = ops.window_attention(qkv.to(DEV), alpha.to(DEV), beta.to(DEV), qb.to(DEV), uv.to(DEV) if pano else None, mask,
+                                   heads, 7, shift, pano, scale, impl="simt" if impl == "simt" else None, bias_tables=bt)
     torch.cuda.synchronize()
     assert got.dtype == torch.bfloat16 and torch.isfinite(got.float()).all()
     assert rel_l2(got.float(), want) <= 1e-2
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+@pytest.mark.parametrize("B", [4, 5, 9])
+def test_window_attention_bf16_batch_inner(ops, case, B):
+    """Batches of >= 4 images take the batch-innermost kernel (same window position of two images per tile, bias row
+    and token map kept across the image pairs of an item); odd batches leave half of the last tile empty."""
+    H, W, heads, shift, pano = case
+    qkv, alpha, beta, qb, uv, C = _attn_case(H, W, heads, 32, shift, pano, B=B, seed=11)
+    qkv = qkv.bfloat16()
+    scale = 32 ** -0.5
+    want = attention_core(qkv.float(), alpha, beta, qb.bfloat16().float(), uv, H, W, heads, 7, shift, pano, scale)
+    mask = O.planar_shift_mask(H, W, 7, shift).to(DEV) if (not pano and shift) else None
+    bf = ops.window_bias_full(alpha.to(DEV), beta.to(DEV), uv.to(DEV) if pano else None, mask, H, W, 7, shift, pano)
+    got = ops.window_attention_full(qkv.to(DEV), bf, qb.to(DEV), heads, 7, shift, pano, scale)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all()
+    assert rel_l2(got.float(), want) <= 1e-2
+    for b in range(B):                                           # per-image check: no cross-talk between the tile halves
+        assert rel_l2(got[b].float(), want[b]) <= 1.5e-2
 
 
 def test_window_attention_no_qkv_bias(ops):

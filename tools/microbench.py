@@ -39,10 +39,13 @@ def attn(iters):
         for shift in (0, 3):
             hav = ops.window_hav_table(uv, 7, shift)
             bt = ops.window_bias_tables(alpha, beta, 7)
+            bf = ops.window_bias_full(alpha, beta, uv, None, H, W, 7, shift, True)
             us = time_op(lambda i: ops.window_attention(qkv[i], alpha, beta, qb, uv, None, heads, 7, shift, True, 32 ** -0.5,
                                                         out=out[i], hav_table=hav, bias_tables=bt), nb, iters)
+            us2 = time_op(lambda i: ops.window_attention_full(qkv[i], bf, qb, heads, 7, shift, True, 32 ** -0.5, out=out[i]), nb, iters)
             byt = B * H * W * C * 8
-            print(f"attn B{B} {H}x{W} C{C} h{heads} s{shift}: {us:8.1f} us  {byt / us / 1e3:7.0f} GB/s", flush=True)
+            print(f"attn B{B} {H}x{W} C{C} h{heads} s{shift}: tables {us:8.1f} us  {byt / us / 1e3:7.0f} GB/s   "
+                  f"full-bias {us2:8.1f} us  {byt / us2 / 1e3:7.0f} GB/s", flush=True)
 
 
 def linear(iters):
@@ -102,18 +105,20 @@ def attn_phases():
         uv = make_uv_hw2(H, W).to(DEV)
         hav = ops.window_hav_table(uv, 7, 3)
         bt = ops.window_bias_tables(alpha, beta, 7)
-        ph = torch.zeros(6, dtype=torch.int64, device=DEV)
-        for _ in range(2):
-            rc = lib.psw_window_attn_fwd_profile(qkv.data_ptr(), out.data_ptr(), alpha.data_ptr(), beta.data_ptr(), bt.data_ptr(), qb.data_ptr(),
-                                                 hav.data_ptr(), B, H, W, C, heads, 7, 3, 32 ** -0.5, ph.data_ptr(), 0,
-                                                 torch.cuda.current_stream().cuda_stream)
-            _lib.check(rc, "profile")
-        torch.cuda.synchronize()
-        v = ph.tolist()
-        n = max(v[5], 1)
-        names = ["wait-loads", "S-mma", "softmax", "PV-mma", "store"]
-        print(f"attn phases {H}x{W} C{C}: steps {v[5]}  " + "  ".join(f"{nm} {v[i] / n:.0f}" for i, nm in enumerate(names)) +
-              f"  total/step {sum(v[:5]) / n:.0f} cyc", flush=True)
+        bf = ops.window_bias_full(alpha, beta, uv, None, H, W, 7, 3, True)
+        for full in (None, bf):
+            ph = torch.zeros(6, dtype=torch.int64, device=DEV)
+            for _ in range(2):
+                rc = lib.psw_window_attn_fwd_profile(qkv.data_ptr(), out.data_ptr(), alpha.data_ptr(), beta.data_ptr(), bt.data_ptr(), qb.data_ptr(),
+                                                     hav.data_ptr(), None if full is None else full.data_ptr(), B, H, W, C, heads, 7, 3,
+                                                     32 ** -0.5, ph.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+                _lib.check(rc, "profile")
+            torch.cuda.synchronize()
+            v = ph.tolist()
+            n = max(v[5], 1)
+            names = ["wait-loads", "S-mma", "softmax", "PV-mma", "store"]
+            print(f"attn phases {H}x{W} C{C} {'tables' if full is None else 'full-bias'}: steps {v[5]}  " +
+                  "  ".join(f"{nm} {v[i] / n:.0f}" for i, nm in enumerate(names)) + f"  total/step {sum(v[:5]) / n:.0f} cyc", flush=True)
 
 
 def attn_skeleton(iters=20):
@@ -129,14 +134,15 @@ def attn_skeleton(iters=20):
         qb = torch.randn(3 * C, device=DEV) * 0.1
         hav = ops.window_hav_table(make_uv_hw2(H, W).to(DEV), 7, 3)
         bt = ops.window_bias_tables(alpha, beta, 7)
-        for mode in (1, 0):
+        bf = ops.window_bias_full(alpha, beta, make_uv_hw2(H, W).to(DEV), None, H, W, 7, 3, True)
+        for mode in (1, 0, 2, 3):
             def run(i):
                 rc = lib.psw_window_attn_fwd_profile(qkv[i].data_ptr(), out[i].data_ptr(), alpha.data_ptr(), beta.data_ptr(),
-                                                     bt.data_ptr(), qb.data_ptr(), hav.data_ptr(), B, H, W, C, heads, 7, 3, 32 ** -0.5, None,
-                                                     mode, torch.cuda.current_stream().cuda_stream)
+                                                     bt.data_ptr(), qb.data_ptr(), hav.data_ptr(), bf.data_ptr() if mode >= 2 else None, B, H, W, C,
+                                                     heads, 7, 3, 32 ** -0.5, None, 0 if mode == 3 else mode, torch.cuda.current_stream().cuda_stream)
                 _lib.check(rc, "profile")
             us = time_op(run, nb, iters)
-            print(f"attn {'skeleton' if mode else 'full    '} {H}x{W} C{C}: {us:8.1f} us  {B * H * W * C * 8 / us / 1e3:7.0f} GB/s", flush=True)
+            print(f"attn {['tables  ', 'skeleton', 'fullbias-noload', 'fullbias'][mode]} {H}x{W} C{C}: {us:8.1f} us  {B * H * W * C * 8 / us / 1e3:7.0f} GB/s", flush=True)
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "phases":
@@ -266,7 +272,8 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "linsweep":
 
 
 def attn_hc(iters=20):
-    """Heads-per-item sweep of the attention kernel (profile entry, mode bits [8,12))."""
+    """Image-pairs-per-unit sweep of the batch-innermost attention kernel (profile entry, mode bits [8,12); 15 = the
+    window-pair kernel with the full bias table)."""
     from panoswintransformerobjectdetection_b200 import _lib
     lib = _lib.load()
     for (H, W, C, heads) in [(128, 256, 96, 3), (64, 128, 192, 6), (32, 64, 384, 12), (16, 32, 768, 24)]:
@@ -278,13 +285,12 @@ def attn_hc(iters=20):
         qb = torch.randn(3 * C, device=DEV) * 0.1
         hav = ops.window_hav_table(make_uv_hw2(H, W).to(DEV), 7, 3)
         bt = ops.window_bias_tables(alpha, beta, 7)
+        bf = ops.window_bias_full(alpha, beta, make_uv_hw2(H, W).to(DEV), None, H, W, 7, 3, True)
         res = []
-        for hc in (0, 1, 2, 3, 4):
-            if hc and heads % hc:
-                continue
+        for hc in (0, 1, 2, 4, 8, 15):
             def run(i):
                 rc = lib.psw_window_attn_fwd_profile(qkv[i].data_ptr(), out[i].data_ptr(), alpha.data_ptr(), beta.data_ptr(),
-                                                     bt.data_ptr(), qb.data_ptr(), hav.data_ptr(), B, H, W, C, heads, 7, 3, 32 ** -0.5, None,
+                                                     bt.data_ptr(), qb.data_ptr(), hav.data_ptr(), bf.data_ptr(), B, H, W, C, heads, 7, 3, 32 ** -0.5, None,
                                                      hc << 8, torch.cuda.current_stream().cuda_stream)
                 _lib.check(rc, "profile")
             us = min(time_op(run, nb, iters) for _ in range(2))
