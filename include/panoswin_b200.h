@@ -132,14 +132,16 @@ PSW_API int psw_window_hav_table(const float* uv, void* table, int H, int W, int
  * is its size.  It depends on the geometry and the block's alpha / beta only (not on the batch): build it once per
  * block and resolution; the kernel reads it with 13 coalesced 16-byte loads per row (it stays L2-resident across the
  * images of a batch).  psw_window_attn_full_fwd() is psw_window_attn_fwd(PSW_BF16) taking that table instead of
- * alpha / beta / uv / hav_table / bias_tables / mask.
+ * alpha / beta / uv / hav_table / bias_tables / mask.  qkv_rows = B*H*W, or B*H*W + 1 when the qkv tensor carries one
+ * extra row holding the bf16 qkv bias (what the qkv GEMM produces for an all-zero extra input row): padding cells then
+ * gather that row and the kernel loads q/k/v with TMA (tile::gather4) instead of per-thread cp.async.
  */
 PSW_API int64_t psw_window_bias_full_bytes(int H, int W, int heads, int window, int pano_mode);
 PSW_API int psw_window_bias_full(const float* alpha, const float* beta, const float* uv, const float* mask, void* table,
                                  int H, int W, int heads, int window, int shift, int pano_mode, void* stream);
 PSW_API int psw_window_attn_full_fwd(const void* qkv, void* out, const void* bias_full, const float* qkv_bias,
-                                     int B, int H, int W, int C, int heads, int window, int shift, int pano_mode,
-                                     float scale, void* stream);
+                                     int64_t qkv_rows, int B, int H, int W, int C, int heads, int window, int shift,
+                                     int pano_mode, float scale, void* stream);
 
 /*
  * PatchMerging front half: 2x2 gather in the order (0,0),(1,0),(0,1),(1,1) with zero padding of odd

@@ -24,7 +24,7 @@ SIGNATURES = {
     "psw_window_hav_table": [_fp, _vp, _i, _i, _i, _i, _vp],
     "psw_window_bias_full_bytes": [_i, _i, _i, _i, _i],
     "psw_window_bias_full": [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    "psw_window_attn_full_fwd": [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "psw_window_attn_full_fwd": [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "psw_patch_merge_ln_fwd": [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _f, _i, _i, _vp],
     "psw_layernorm_nchw_fwd": [_vp, _vp, _fp, _fp, _i, _i64, _i, _f, _i, _vp],
     "psw_stem_conv3x3_relu_fwd": [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],

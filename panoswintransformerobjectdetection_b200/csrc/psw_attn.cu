@@ -9,9 +9,9 @@ int window_attn_simt(const T* qkv, T* out, const float* alpha, const float* beta
                      int pano, float scale, cudaStream_t st);
 void attn_debug_set_hc(int hc);
 int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const void* tables,
-                   const float* qkv_bias, const void* hav_table, const float* mask, const void* bias_full, int B, int H,
-                   int W, int C, int heads, int window, int shift, int pano, float scale, long long* dbg, int mode,
-                   cudaStream_t st);
+                   const float* qkv_bias, const void* hav_table, const float* mask, const void* bias_full,
+                   bool bias_row_present, int B, int H, int W, int C, int heads, int window, int shift, int pano, float scale,
+                   long long* dbg, int mode, cudaStream_t st);
 int window_bias_full(const float* alpha, const float* beta, const float* uv, const float* mask, void* table, int H, int W,
                      int heads, int window, int shift, int pano, cudaStream_t st);
 int window_bias_tables(const float* alpha, const float* beta, void* tables, int heads, int window, cudaStream_t st);
@@ -50,15 +50,15 @@ extern "C" PSW_API int psw_window_attn_fwd(const void* qkv, void* out, const flo
   PSW_REQUIRE(aligned16(qkv) && aligned16(out), PSW_ERR_BAD_ARG, "psw_window_attn_fwd(bf16): pointers must be 16-byte aligned");
   PSW_REQUIRE(aligned16(hav_table), PSW_ERR_BAD_ARG, "psw_window_attn_fwd(bf16): great-circle table must be 16-byte aligned");
   PSW_REQUIRE(aligned16(bias_tables), PSW_ERR_BAD_ARG, "psw_window_attn_fwd(bf16): bias tables must be 16-byte aligned");
-  return window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, mask, nullptr, B, H,
-                        W, C, heads, window, shift, pano_mode, scale, nullptr, 0, st);
+  return window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, mask, nullptr, false, B,
+                        H, W, C, heads, window, shift, pano_mode, scale, nullptr, 0, st);
 }
 
 // bf16 production path: every additive term of the logits (great-circle bias, relative-position bias, planar shift
 // mask) comes from the table psw_window_bias_full() built for this block and resolution.
 extern "C" PSW_API int psw_window_attn_full_fwd(const void* qkv, void* out, const void* bias_full, const float* qkv_bias,
-                                                int B, int H, int W, int C, int heads, int window, int shift,
-                                                int pano_mode, float scale, void* stream) {
+                                                int64_t qkv_rows, int B, int H, int W, int C, int heads, int window,
+                                                int shift, int pano_mode, float scale, void* stream) {
   PSW_REQUIRE(qkv && out && bias_full, PSW_ERR_BAD_ARG, "psw_window_attn_full_fwd: null pointer");
   PSW_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && heads > 0 && window > 0, PSW_ERR_BAD_ARG,
               "psw_window_attn_full_fwd: bad dims B=%d H=%d W=%d C=%d heads=%d window=%d", B, H, W, C, heads, window);
@@ -70,8 +70,11 @@ extern "C" PSW_API int psw_window_attn_full_fwd(const void* qkv, void* out, cons
               window, C / heads);
   PSW_REQUIRE(aligned16(qkv) && aligned16(out) && aligned16(bias_full), PSW_ERR_BAD_ARG,
               "psw_window_attn_full_fwd: pointers must be 16-byte aligned");
-  return window_attn_tc((const bf16*)qkv, (bf16*)out, nullptr, nullptr, nullptr, qkv_bias, nullptr, nullptr, bias_full, B, H,
-                        W, C, heads, window, shift, pano_mode, scale, nullptr, 0, (cudaStream_t)stream);
+  const int64_t T = (int64_t)B * H * W;
+  PSW_REQUIRE(qkv_rows == T || qkv_rows == T + 1, PSW_ERR_BAD_ARG,
+              "psw_window_attn_full_fwd: qkv_rows must be B*H*W (or B*H*W + 1 with the bias row), got %lld", (long long)qkv_rows);
+  return window_attn_tc((const bf16*)qkv, (bf16*)out, nullptr, nullptr, nullptr, qkv_bias, nullptr, nullptr, bias_full,
+                        qkv_rows == T + 1, B, H, W, C, heads, window, shift, pano_mode, scale, nullptr, 0, (cudaStream_t)stream);
 }
 
 extern "C" PSW_API int64_t psw_window_bias_full_bytes(int H, int W, int heads, int window, int pano_mode) {
@@ -101,7 +104,8 @@ extern "C" PSW_API int psw_window_bias_tables(const float* alpha, const float* b
 // Diagnostics: same as the PSW_BF16 path of psw_window_attn_fwd, plus per-phase SM-cycle totals of CTA 0 written to
 // phase_cycles[6] (device memory, may be NULL): {wait-for-loads, S MMA, softmax, P.V MMA, store, steps}.
 // mode 1 runs the memory skeleton only (same gathers and stores, no MMA / softmax; output = q rows); mode bits
-// [8,12) force the number of heads per work item.
+// [8,12) force the number of heads per work item / image pairs per unit (15: window-pair kernel, 14: no TMA gather);
+// bit 12: the qkv tensor has the extra bias row (enables the TMA gather loader).
 extern "C" PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, const float* alpha, const float* beta,
                                                    const void* bias_tables, const float* qkv_bias,
                                                    const void* hav_table, const void* bias_full, int B, int H, int W,
@@ -109,10 +113,11 @@ extern "C" PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, c
                                                    long long* phase_cycles, int mode, void* stream) {
   int rc = check_attn_args(qkv, out, alpha, beta, bias_full ? bias_full : hav_table, B, H, W, C, heads, window, shift, 1);
   if (rc) return rc;
-  PSW_REQUIRE(C / heads == 32 && (mode & 0xff) <= 2, PSW_ERR_BAD_ARG, "psw_window_attn_fwd_profile: bad arguments");
+  PSW_REQUIRE(C / heads == 32 && (mode & 0xff) <= 4, PSW_ERR_BAD_ARG, "psw_window_attn_fwd_profile: bad arguments");
   attn_debug_set_hc((mode >> 8) & 15);                       // bits [8,12): force the heads-per-item choice
-  rc = window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, nullptr, bias_full, B, H,
-                      W, C, heads, window, shift, 1, scale, phase_cycles, mode & 0xff, (cudaStream_t)stream);
+  rc = window_attn_tc((const bf16*)qkv, (bf16*)out, alpha, beta, bias_tables, qkv_bias, hav_table, nullptr, bias_full,
+                      ((mode >> 12) & 1) != 0, B, H, W, C, heads, window, shift, 1, scale, phase_cycles, mode & 0xff,
+                      (cudaStream_t)stream);
   attn_debug_set_hc(0);
   return rc;
 }

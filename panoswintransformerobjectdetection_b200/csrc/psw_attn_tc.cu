@@ -40,6 +40,7 @@ constexpr int AT_HAV_PITCH = 56;                   // halfs per distance-table r
 constexpr int AT_TMEM_COLS = 128;
 constexpr int AT_P_COL = 0;                        // P (bf16x2 packed): TMEM columns [0, 32)
 constexpr int AT_O_COL = 32;                       // O (fp32): TMEM columns [32, 96)
+constexpr int AT_SUM_COL = 96;                     // row sums of P (fp32, batch-innermost kernel): TMEM columns [96, 112)
 constexpr int AT_CTAS_PER_SM = 4;                 // 128 registers per thread (no spills), 4 x 128 TMEM columns
 constexpr int AT_TAB_PITCH = 39;                   // half2 (alpha, beta) words per table row: 13 used; 39 = 7 mod 32 makes
                                                    // the row-per-lane lookups bank-conflict-free
@@ -60,6 +61,11 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&r)[
         "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
@@ -521,9 +527,21 @@ struct BiStep {
   int ic;                 // running unit count of this CTA (parity selects the token-map slot)
 };
 
-template <int WS>
+// GATHER: the q/k/v rows are fetched by TMA (cp.async.bulk.tensor tile::gather4: four 64-byte token rows per
+// instruction, written with the 64-byte swizzle the MMA descriptors expect; tools/probes/tma_gather4_probe.cu) instead
+// of per-thread cp.async: 78 instructions per step, no address arithmetic per 16-byte chunk, no proxy fence, and only
+// the MMA-issuing thread waits for the data.  Needs the qkv tensor to carry one extra row (index B*H*W) holding the
+// bf16 qkv bias, which padding cells gather (psw_window_attn_full_fwd: qkv_rows == B*H*W + 1).
+__device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int col, int r0, int r1,
+                                            int r2, int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
+template <int WS, bool GATHER>
 __global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
-window_attn_bi_kernel(const AttnParams p) {
+window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_qkv) {
   constexpr int N = WS * WS;
   static_assert(N == 49, "TMEM row load below is written for 49 logits");
   extern __shared__ uint8_t smem_raw[];
@@ -532,6 +550,8 @@ window_attn_bi_kernel(const AttnParams p) {
   int* src = reinterpret_cast<int*>(bufs + 2 * AT_BUF_BYTES);            // [2 item slots][64]: token index in the image or -1
   uint64_t* bars = reinterpret_cast<uint64_t*>(src + 2 * 64);            // [2]: S ready, O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint8_t* ones = bufs + 2 * AT_BUF_BYTES + 1024;                        // 1 KB of bf16 1.0: B operand of the row-sum MMA
+  uint64_t* full = reinterpret_cast<uint64_t*>(tmem_slot + 2);           // [2] GATHER: q/k/v of a stage have landed
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -542,11 +562,16 @@ window_attn_bi_kernel(const AttnParams p) {
 
   for (int i = tid; i < 2 * AT_BUF_BYTES / 16; i += AT_THREADS)
     reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0, 0, 0, 0);          // padding rows must stay finite
+  if (tid < 64) reinterpret_cast<uint4*>(ones)[tid] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    if (GATHER) tma_prefetch_desc(&map_qkv);
     mbar_fence_init();
   }
+  if (GATHER) fence_async_shared();                        // zero-filled stages / ones tile vs. the async proxy
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(AT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -620,7 +645,28 @@ window_attn_bi_kernel(const AttnParams p) {
     const int row = (k >> 1) * 64 + t;
     ld_dst[k] = row * 64 + ((lc ^ ((row >> 1) & 3)) << 4);
   }
+  // GATHER loader role: thread j < 78 fetches token slots 4*grp .. 4*grp+3 of image `gu` for part `gpart` (q / k / v)
+  const int gpart = tid / 26, grem = tid - gpart * 26;
+  const int gu = grem / 13, ggrp = grem - gu * 13;
+  const int bias_row = p.B * (int)HW;                      // the extra row of the qkv tensor: bf16 qkv bias
   auto issue_loads = [&](const BiStep& st) {
+    if constexpr (GATHER) {
+      uint64_t* fb = &full[st.n & 1];
+      if (tid == 0) mbar_expect_tx(fb, 78 * 256);
+      if (tid < 78) {
+        const int4 t4 = *reinterpret_cast<const int4*>(src + (st.ic & 1) * 64 + 4 * ggrp);   // slots >= 49 hold -1
+        const int b = 2 * st.bp + gu;
+        const int base_row = b * (int)HW;
+        const bool bv = b < p.B;
+        const int r0 = (bv && t4.x >= 0) ? base_row + t4.x : bias_row;
+        const int r1 = (bv && t4.y >= 0) ? base_row + t4.y : bias_row;
+        const int r2 = (bv && t4.z >= 0) ? base_row + t4.z : bias_row;
+        const int r3 = (bv && t4.w >= 0) ? base_row + t4.w : bias_row;
+        uint8_t* dst = bufs + (st.n & 1) * AT_BUF_BYTES + gpart * AT_PART_BYTES + (gu * 64 + 4 * ggrp) * 64;
+        tma_gather4(dst, &map_qkv, fb, gpart * C + (st.item % heads) * 32, r0, r1, r2, r3);
+      }
+      return;
+    }
     uint8_t* base = bufs + (st.n & 1) * AT_BUF_BYTES;
     const int* smap = src + (st.ic & 1) * 64;
     const int e = st.item % heads;
@@ -683,13 +729,16 @@ window_attn_bi_kernel(const AttnParams p) {
     const bool row_valid = (ti < N) && (my_b < p.B);
     const int e = cur.item % heads;
     // ---- 1. this step's q/k/v (requested one step ago) have landed
-    cp_async_wait<0>();
-    fence_async_shared();
+    if constexpr (!GATHER) {
+      cp_async_wait<0>();
+      fence_async_shared();
+    }
     __syncthreads();
     if (prof) c1 = clock64();
     // ---- 2. S = Q . K^T (both images at once, block diagonal)
     const uint32_t sq = smem_u32(bufs + (cur.n & 1) * AT_BUF_BYTES);
     if (tid == 0) {
+      if constexpr (GATHER) mbar_wait(&full[cur.n & 1], (uint32_t)(cur.n >> 1) & 1);
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
       const uint64_t dq = umma_smem_desc(sq, 16, 512, UMMA_SWIZZLE_64B);
@@ -698,13 +747,12 @@ window_attn_bi_kernel(const AttnParams p) {
       umma_ss(tmem_base, dq + 2, dk + 2, idesc, 1);
       umma_commit(&bars[0]);
     }
-    if (has_next) issue_loads(nxt);                        // whole next step into the other stage
+    if (has_next && p.mode != 3) issue_loads(nxt);         // whole next step into the other stage (mode 3: diagnostics, no loads)
     cp_async_commit();
     mbar_wait(&bars[0], par);
     tc_fence_after();
     if (prof) c2 = clock64();
     // ---- 3. bias + softmax on my row
-    float sum = 1.f;
     {
       uint32_t sr[N];
       const uint32_t s_addr = tmem_base + lane_base + (uint32_t)(unit * 64);
@@ -721,20 +769,18 @@ window_attn_bi_kernel(const AttnParams p) {
         sr[48] = t1;
       }
       float t[N];
-      float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < N; ++j) {
-        t[j] = fmaf(__uint_as_float(sr[j]), p.scale, bias[j]);
-        mx = fmaxf(mx, t[j]);
-      }
+      for (int j = 0; j < N; ++j) t[j] = fmaf(__uint_as_float(sr[j]), p.scale, bias[j]);
+      float mx = t[N - 1];
+#pragma unroll
+      for (int j = 0; j + 1 < N; j += 2) mx = fmax3(mx, t[j], t[j + 1]);
       const float mneg = -mx * LOG2E;
-      sum = 0.f;
-      uint32_t pk[32];
+      uint32_t pk[32];                                     // the row sum comes from the tensor core (P . ones)
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
         float p0 = 0.f, p1 = 0.f;
-        if (2 * k < N) { p0 = fast_exp2(fmaf(t[2 * k], LOG2E, mneg)); sum += p0; }
-        if (2 * k + 1 < N) { p1 = fast_exp2(fmaf(t[2 * k + 1], LOG2E, mneg)); sum += p1; }
+        if (2 * k < N) p0 = fast_exp2(fmaf(t[2 * k], LOG2E, mneg));
+        if (2 * k + 1 < N) p1 = fast_exp2(fmaf(t[2 * k + 1], LOG2E, mneg));
         pk[k] = row_valid ? pack_bf16x2(p0, p1) : 0u;
       }
       tmem_st_x32(tmem_base + lane_base + AT_P_COL, pk);
@@ -748,11 +794,14 @@ window_attn_bi_kernel(const AttnParams p) {
     if (tid == 0) {
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
+      const uint32_t idesc1 = umma_idesc_bf16(128, 16, 0, 1);    // row sums: P . ones[keys][16]
       const uint32_t sv = sq + 2 * AT_PART_BYTES;
+      const uint64_t d1 = umma_smem_desc(smem_u32(ones), 4096, 512, UMMA_SWIZZLE_64B);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint64_t dv = umma_smem_desc(sv + k * 1024, 4096, 512, UMMA_SWIZZLE_64B);
         umma_ts(tmem_base + AT_O_COL, tmem_base + AT_P_COL + k * 8, dv, idesc, k > 0);
+        umma_ts(tmem_base + AT_SUM_COL, tmem_base + AT_P_COL + k * 8, d1, idesc1, k > 0);
       }
       umma_commit(&bars[1]);
     }
@@ -766,12 +815,13 @@ window_attn_bi_kernel(const AttnParams p) {
     if (prof) c4 = clock64();
     // ---- 5. normalise and store my output row at the token's un-shifted position
     {
-      uint32_t orow[32];
+      uint32_t orow[32], osum;
       tmem_ld_x32(tmem_base + lane_base + AT_O_COL + (uint32_t)(unit * 32), orow);
+      tmem_ld_x1(tmem_base + lane_base + AT_SUM_COL, osum);
       tmem_ld_wait();
       const int ts = src[(cur.ic & 1) * 64 + ic];
       if (row_valid && ts >= 0) {
-        const float inv = 1.0f / sum;
+        const float inv = 1.0f / __uint_as_float(osum);
         uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)my_b * HW + ts) * C + e * 32);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -893,9 +943,9 @@ int window_bias_tables(const float* alpha, const float* beta, void* tables, int 
 }
 
 int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const void* tables,
-                   const float* qkv_bias, const void* hav_table, const float* mask, const void* bias_full, int B, int H,
-                   int W, int C, int heads, int window, int shift, int pano, float scale, long long* dbg, int mode,
-                   cudaStream_t st) {
+                   const float* qkv_bias, const void* hav_table, const float* mask, const void* bias_full,
+                   bool bias_row_present, int B, int H, int W, int C, int heads, int window, int shift, int pano, float scale,
+                   long long* dbg, int mode, cudaStream_t st) {
   PSW_REQUIRE(window == 7, PSW_ERR_UNSUPPORTED,
               "psw_window_attn_fwd(bf16): the tcgen05 kernel is instantiated for window 7 (every shipped PanoSwin config); got %d",
               window);
@@ -921,7 +971,7 @@ int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* 
   const size_t smem = attn_tc_smem_bytes(window, C);
   PSW_REQUIRE(smem <= 220 * 1024, PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd(bf16): C=%d too large", C);
   PSW_REQUIRE((int64_t)B * H * W < (1ll << 31) / 1, PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd(bf16): too many tokens");
-  const bool batch_inner = bias_full != nullptr && B >= 4 && attn_debug_hc() != 15 && (mode == 0 || mode == 2);
+  const bool batch_inner = bias_full != nullptr && B >= 4 && attn_debug_hc() != 15 && mode != 1;
   if (batch_inner) {
     // image pairs per unit: as many as possible (the bias row and the token map are fetched once per unit) while the
     // units still spread evenly over the resident CTAs (CTA c runs units c, c + grid, ...)
@@ -938,9 +988,28 @@ int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* 
     }
     p.n_items = wh * ((bp_total + p.hc - 1) / p.hc);                                // units: (window, chunk, head)
   }
-  auto kern = batch_inner ? window_attn_bi_kernel<7>
-              : (bias_full ? window_attn_tc_kernel<7, false, true>
-                           : (mask ? window_attn_tc_kernel<7, true, false> : window_attn_tc_kernel<7, false, false>));
+  if (batch_inner) {
+    const bool gather = bias_row_present && attn_debug_hc() != 14;
+    CUtensorMap map_qkv;
+    if (gather) {
+      const uint64_t dims[2] = {(uint64_t)(3 * C), (uint64_t)((int64_t)B * H * W + 1)};
+      const uint64_t strides[1] = {(uint64_t)(3 * C) * 2};
+      const uint32_t box[2] = {32, 1};
+      int rc = make_tensor_map_nd(&map_qkv, qkv, 2, dims, strides, box, 2, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    } else {
+      memset(&map_qkv, 0, sizeof(map_qkv));
+    }
+    auto kern = gather ? window_attn_bi_kernel<7, true> : window_attn_bi_kernel<7, false>;
+    PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int grid = num_sms() * AT_CTAS_PER_SM;
+    if (grid > p.n_items) grid = p.n_items;
+    kern<<<grid, AT_THREADS, smem, st>>>(p, map_qkv);
+    return launch_status("window_attn_bi_kernel");
+  }
+  auto kern = bias_full ? window_attn_tc_kernel<7, false, true>
+                        : (mask ? window_attn_tc_kernel<7, true, false> : window_attn_tc_kernel<7, false, false>);
   PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int grid = num_sms() * AT_CTAS_PER_SM;

@@ -164,18 +164,27 @@ def window_bias_full(alpha, beta, uv, mask, H, W, window, shift, pano_mode):
     return out
 
 
-def window_attention_full(qkv, bias_full, qkv_bias, heads, window, shift, pano_mode, scale, out=None):
-    """The bf16 tcgen05 attention kernel with the precomputed bias table of window_bias_full() (production path)."""
+def window_attention_full(qkv, bias_full, qkv_bias, heads, window, shift, pano_mode, scale, out=None, dims=None):
+    """The bf16 tcgen05 attention kernel with the precomputed bias table of window_bias_full() (production path).
+    qkv is [B, H, W, 3C], or -- with dims=(B, H, W) -- a [B*H*W + 1, 3C] tensor whose last row holds the bf16 qkv bias
+    (the qkv GEMM of an input with one extra all-zero row), which lets the kernel gather q/k/v with TMA."""
     dev = _chk(qkv, bias_full, qkv_bias, out)
-    B, H, W, C3 = qkv.shape
+    if dims is None:
+        B, H, W, C3 = qkv.shape
+        rows = B * H * W
+    else:
+        B, H, W = dims
+        rows, C3 = qkv.shape
+        if rows not in (B * H * W, B * H * W + 1):
+            raise PanoSwinB200Error("window_attention_full: qkv rows must be B*H*W or B*H*W + 1")
     C = C3 // 3
     if qkv.dtype != torch.bfloat16:
         raise PanoSwinB200Error("window_attention_full is the bf16 path")
     if out is None:
         out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
     with torch.cuda.device(dev):
-        _call("psw_window_attn_full_fwd", _ptr(qkv), _ptr(out), _ptr(bias_full), _ptr(_f32(qkv_bias, "qkv_bias")), B, H, W, C,
-              heads, window, shift, 1 if pano_mode else 0, float(scale), _stream(dev))
+        _call("psw_window_attn_full_fwd", _ptr(qkv), _ptr(out), _ptr(bias_full), _ptr(_f32(qkv_bias, "qkv_bias")), rows, B, H, W,
+              C, heads, window, shift, 1 if pano_mode else 0, float(scale), _stream(dev))
     return out
 
 

@@ -236,6 +236,13 @@ def test_window_attention_bf16_batch_inner(ops, case, B):
     assert rel_l2(got.float(), want) <= 1e-2
     for b in range(B):                                           # per-image check: no cross-talk between the tile halves
         assert rel_l2(got[b].float(), want[b]) <= 1.5e-2
+    # same kernel with the TMA (tile::gather4) loader: the qkv tensor carries the bf16 qkv bias as one extra row
+    rows = torch.cat([qkv.reshape(B * H * W, 3 * C), qb.bfloat16()[None]], 0).contiguous()
+    got2 = ops.window_attention_full(rows.to(DEV), bf, qb.to(DEV), heads, 7, shift, pano, scale, dims=(B, H, W))
+    torch.cuda.synchronize()
+    assert torch.isfinite(got2.float()).all()
+    assert rel_l2(got2.float(), want) <= 1e-2
+    assert rel_l2(got2.float(), got.float()) <= 2e-3             # bit-level differences only from accumulation order
 
 
 def test_window_attention_no_qkv_bias(ops):

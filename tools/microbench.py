@@ -43,9 +43,12 @@ def attn(iters):
             us = time_op(lambda i: ops.window_attention(qkv[i], alpha, beta, qb, uv, None, heads, 7, shift, True, 32 ** -0.5,
                                                         out=out[i], hav_table=hav, bias_tables=bt), nb, iters)
             us2 = time_op(lambda i: ops.window_attention_full(qkv[i], bf, qb, heads, 7, shift, True, 32 ** -0.5, out=out[i]), nb, iters)
+            rows = [torch.cat([q.reshape(-1, 3 * C), qb.bfloat16()[None]], 0).contiguous() for q in qkv]
+            us3 = time_op(lambda i: ops.window_attention_full(rows[i], bf, qb, heads, 7, shift, True, 32 ** -0.5, out=out[i],
+                                                              dims=(B, H, W)), nb, iters)
             byt = B * H * W * C * 8
             print(f"attn B{B} {H}x{W} C{C} h{heads} s{shift}: tables {us:8.1f} us  {byt / us / 1e3:7.0f} GB/s   "
-                  f"full-bias {us2:8.1f} us  {byt / us2 / 1e3:7.0f} GB/s", flush=True)
+                  f"full-bias {us2:8.1f} us  {byt / us2 / 1e3:7.0f} GB/s   +tma-gather {us3:8.1f} us  {byt / us3 / 1e3:7.0f} GB/s", flush=True)
 
 
 def linear(iters):
@@ -135,14 +138,14 @@ def attn_skeleton(iters=20):
         hav = ops.window_hav_table(make_uv_hw2(H, W).to(DEV), 7, 3)
         bt = ops.window_bias_tables(alpha, beta, 7)
         bf = ops.window_bias_full(alpha, beta, make_uv_hw2(H, W).to(DEV), None, H, W, 7, 3, True)
-        for mode in (1, 0, 2, 3):
+        for mode in (1, 0, 2, 3, 4):
             def run(i):
                 rc = lib.psw_window_attn_fwd_profile(qkv[i].data_ptr(), out[i].data_ptr(), alpha.data_ptr(), beta.data_ptr(),
                                                      bt.data_ptr(), qb.data_ptr(), hav.data_ptr(), bf.data_ptr() if mode >= 2 else None, B, H, W, C,
-                                                     heads, 7, 3, 32 ** -0.5, None, 0 if mode == 3 else mode, torch.cuda.current_stream().cuda_stream)
+                                                     heads, 7, 3, 32 ** -0.5, None, {0: 0, 1: 1, 2: 2, 3: 0, 4: 3}[mode], torch.cuda.current_stream().cuda_stream)
                 _lib.check(rc, "profile")
             us = time_op(run, nb, iters)
-            print(f"attn {['tables  ', 'skeleton', 'fullbias-noload', 'fullbias'][mode]} {H}x{W} C{C}: {us:8.1f} us  {B * H * W * C * 8 / us / 1e3:7.0f} GB/s", flush=True)
+            print(f"attn {['tables  ', 'skeleton', 'fullbias-nobiasload', 'fullbias', 'fullbias-noqkvload'][mode]} {H}x{W} C{C}: {us:8.1f} us  {B * H * W * C * 8 / us / 1e3:7.0f} GB/s", flush=True)
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "phases":
