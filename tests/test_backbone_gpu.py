@@ -97,8 +97,10 @@ def test_batch_rows_are_independent_and_sharding_is_exact():
         full = m(img)
         halves = [m(img[:2]), m(img[2:])]
         for i, o in enumerate(full):
-            # cuDNN may pick another stem algorithm per batch size, hence a tolerance instead of equality
-            assert rel_l2(o, torch.cat([halves[0][i], halves[1][i]], 0)) <= (1e-5 if dtype == "fp32" else 5e-3), (dtype, i)
+            # a tolerance instead of equality: cuDNN may pick another patch-conv algorithm per batch size, and batches of
+            # >= 4 images take the batch-innermost attention kernel (row sums of the bf16-rounded probabilities on the
+            # tensor core) while smaller ones take the window-pair kernel (fp32 sums) -- bf16-rounding-level differences
+            assert rel_l2(o, torch.cat([halves[0][i], halves[1][i]], 0)) <= (1e-5 if dtype == "fp32" else 1e-2), (dtype, i)
 
 
 def test_api_surface_on_gpu():
