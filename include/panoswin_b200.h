@@ -177,6 +177,15 @@ PSW_API int psw_stem_conv3x3_relu_fwd(const float* img, const float* w_folded, c
 PSW_API int psw_stem_conv3x3_c32_relu_fwd(const void* x, const void* w_taps, const float* bias, void* out,
                                           int B, int H, int W, int cout, void* stream);
 
+/*
+ * Stem, last layer: the non-overlapping patch convolution conv(cin -> cout, kernel = stride = patch) (PatchEmbed.proj[6],
+ * reference :749) as a tcgen05 GEMM over a 3-D TMA view of the NHWC bf16 input (no im2col; bias in the epilogue).
+ * x [B, H, W, cin] bf16 -> out [B * H/ph * W/pw, cout] bf16 tokens.  w [cout][ph][pw][cin] bf16 (the reference's
+ * [cout, cin, ph, pw] weight permuted to (0, 2, 3, 1)), bias [cout] fp32 or NULL.  H, W must be multiples of the patch.
+ */
+PSW_API int psw_patch_conv_fwd(const void* x, const void* w, const float* bias, void* out, int B, int H, int W,
+                               int cin, int cout, int patch_h, int patch_w, void* stream);
+
 /* dtype conversion helper for activations entering / leaving the bf16 path: n elements. */
 PSW_API int psw_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
 

@@ -431,8 +431,16 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         own_conv2 = own_conv1 and conv2.in_channels == 32 and conv2.out_channels in (32, 64) and conv2.kernel_size == (3, 3)
         if own_conv2:
             w2t, b2f = self._weight_cache["stem2"]
-            y = ops.stem_conv3x3_c32_relu(ops.stem_conv3x3_relu(x.contiguous(), w1f, b1f), w2t, b2f).permute(0, 3, 1, 2)
-            y = F.conv2d(y, w3, b3, stride=pe.patch_size)
+            y = ops.stem_conv3x3_c32_relu(ops.stem_conv3x3_relu(x.contiguous(), w1f, b1f), w2t, b2f)       # NHWC bf16
+            if (pw * conv3.in_channels) % 64 == 0 and conv3.out_channels % 16 == 0:
+                k3 = ("stem3", conv3.weight._version, conv3.weight.data_ptr(), None if conv3.bias is None else conv3.bias._version)
+                hit = self._weight_cache.get("stem3")
+                if hit is None or hit[0] != k3:              # [cout, cin, ph, pw] -> [cout, ph, pw, cin] bf16
+                    hit = (k3, conv3.weight.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous(),
+                           None if conv3.bias is None else conv3.bias.detach().float().contiguous())
+                    self._weight_cache["stem3"] = hit
+                return ops.patch_conv(y, hit[1], hit[2], pe.patch_size)                                  # [B, Hs, Ws, E]
+            y = F.conv2d(y.permute(0, 3, 1, 2), w3, b3, stride=pe.patch_size)
             return y.permute(0, 2, 3, 1).contiguous()      # no copy when the conv output is channels-last
         if own_conv1:
             # fp32 NCHW image -> bf16 NHWC, seen by the next convolution as a channels-last NCHW tensor (no copy)

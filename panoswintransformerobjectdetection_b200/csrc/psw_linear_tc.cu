@@ -33,6 +33,16 @@ constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_MAX_EPI_WARPS = 16;
 constexpr int TC_TILE_BYTES = 32 * 64;      // epilogue staging tile: 32 rows x 64 B, SWIZZLE_64B
 
+// Patch-convolution view of the A operand (psw_patch_conv_fwd): token (ty, tx) of a non-overlapping ph x pw patch grid
+// is GEMM row ty * wt + tx, its K axis is (dy, dx, c): for a fixed dy the pw * cin values are contiguous in the NHWC
+// image, so x-tiles are boxes of a 3-D tensor {pw * cin, wt, B * H}.  tiles_x = 0 means a plain 2-D A operand.
+struct ConvView {
+  int tiles_x;            // M-tiles per token row
+  int wt;                 // tokens per image row
+  int kb_per_dy;          // K-blocks (64 elements) per patch row: pw * cin / 64
+  int ph;                 // patch height
+};
+
 struct alignas(16) TcSmemTail {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
@@ -73,6 +83,17 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
+}
+// 3-D variants for the patch-convolution view of the A operand (coordinates: k inside the patch row, token x, image row)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, bool accumulate) {
   asm volatile(
@@ -131,7 +152,8 @@ template <bool GELU, bool RES, typename TO, int GW, int CG>
 __global__ void __launch_bounds__(EpiCfg<GW>::THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_r,
-                 const float* __restrict__ bias, TO* __restrict__ y, int64_t M, int N, int K, int block_n, int stages, int mode) {
+                 const float* __restrict__ bias, TO* __restrict__ y, int64_t M, int N, int K, int block_n, int stages, int mode,
+                 const ConvView cv) {
   constexpr int CW = Chunk<TO>::CW;
   constexpr int TC_EPI_WARPS = EpiCfg<GW>::EW;
   constexpr int PER_QUAD = GW / 4;                            // warps of one group sharing a TMEM lane quadrant
@@ -150,7 +172,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int n_tiles = (N + block_n - 1) / block_n;
   constexpr int TILE_M = TC_BM * CG;                          // rows per tile (of the CTA or of the CTA pair)
-  const int64_t m_tiles = (M + TILE_M - 1) / TILE_M;
+  const int64_t m_tiles = cv.tiles_x ? (M / cv.wt) * cv.tiles_x : (M + TILE_M - 1) / TILE_M;
   const int64_t total_tiles = m_tiles * n_tiles;
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int unit = blockIdx.x / CG;                           // index of this CTA (pair) among the tile workers
@@ -204,13 +226,25 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           if (CG == 2) {                                      // bytes of both CTAs are counted on the leader's barrier
             if (cta_rank == 0) mbar_expect_tx(&tail->full[stage], 2 * stage_bytes);
-            tma_load_2d_pair(sa, &map_x, &tail->full[stage], kb * TC_BK, m_t * TILE_M + cta_rank * TC_BM);
+            if (cv.tiles_x) {
+              const int trow = m_t / cv.tiles_x, x0 = (m_t - trow * cv.tiles_x) * TILE_M + cta_rank * TC_BM;
+              const int dy = kb / cv.kb_per_dy;
+              tma_load_3d_pair(sa, &map_x, &tail->full[stage], (kb - dy * cv.kb_per_dy) * TC_BK, x0, trow * cv.ph + dy);
+            } else {
+              tma_load_2d_pair(sa, &map_x, &tail->full[stage], kb * TC_BK, m_t * TILE_M + cta_rank * TC_BM);
+            }
             tma_load_2d_pair(sa + a_bytes, &map_w, &tail->full[stage], kb * TC_BK, n_t * block_n + cta_rank * (block_n / 2));
           } else if (mode & 2) {                              // diagnostics: no loads
             mbar_arrive(&tail->full[stage]);
           } else {
             mbar_expect_tx(&tail->full[stage], stage_bytes);
-            tma_load_2d(sa, &map_x, &tail->full[stage], kb * TC_BK, m_t * TILE_M);
+            if (cv.tiles_x) {
+              const int trow = m_t / cv.tiles_x, x0 = (m_t - trow * cv.tiles_x) * TILE_M;
+              const int dy = kb / cv.kb_per_dy;
+              tma_load_3d(sa, &map_x, &tail->full[stage], (kb - dy * cv.kb_per_dy) * TC_BK, x0, trow * cv.ph + dy);
+            } else {
+              tma_load_2d(sa, &map_x, &tail->full[stage], kb * TC_BK, m_t * TILE_M);
+            }
             tma_load_2d(sa + a_bytes, &map_w, &tail->full[stage], kb * TC_BK, n_t * block_n);
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -284,7 +318,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     for (int64_t tile = unit + (int64_t)grp * n_units; tile < total_tiles; tile += 2 * n_units, ++tile_iter) {
       const int m_t = (int)((uint32_t)tile / (uint32_t)n_tiles);     // total_tiles < 2^31 (checked on the host)
       const int n_t = (int)tile - m_t * n_tiles;
-      const int row0 = m_t * TILE_M + cta_rank * TC_BM + quad * 32;
+      int row0 = m_t * TILE_M + cta_rank * TC_BM + quad * 32;
+      int64_t row_lim = M;
+      if (cv.tiles_x) {                                     // token row `trow`: GEMM rows [trow * wt, trow * wt + wt)
+        const int trow = m_t / cv.tiles_x;
+        row0 = trow * cv.wt + (m_t - trow * cv.tiles_x) * TILE_M + cta_rank * TC_BM + quad * 32;
+        row_lim = (int64_t)(trow + 1) * cv.wt;
+      }
       const int col0 = n_t * block_n;
       // chunks of this warp in this tile: c = first, first + PER_QUAD, ... (first rotates with the tile count so a
       // chunk count that is not a multiple of PER_QUAD still balances the warps of a quadrant)
@@ -412,7 +452,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const int64_t step = (int64_t)8 * N * (int64_t)sizeof(TO);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (row0 + t_row + 8 * j < M) *reinterpret_cast<uint4*>(gp + j * step) = t[j];
+              if (row0 + t_row + 8 * j < row_lim) *reinterpret_cast<uint4*>(gp + j * step) = t[j];
           }
         }
         __syncwarp();                                         // the staging row may be overwritten by the next chunk
@@ -449,8 +489,10 @@ static int pick_block_n(int N) {
 
 template <bool GELU, bool RES, typename TO, int GW, int CG>
 static int launch_tc_gw(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& mr, const float* bias, void* y,
-                        int64_t M, int N, int K, int block_n, int stages, size_t smem, cudaStream_t st) {
-  const int64_t tiles = ((M + TC_BM * CG - 1) / (TC_BM * CG)) * ((N + block_n - 1) / block_n);
+                        int64_t M, int N, int K, int block_n, int stages, size_t smem, ConvView cv, cudaStream_t st) {
+  if (cv.tiles_x) cv.tiles_x = (cv.wt + TC_BM * CG - 1) / (TC_BM * CG);
+  const int64_t m_tiles = cv.tiles_x ? (M / cv.wt) * cv.tiles_x : (M + TC_BM * CG - 1) / (TC_BM * CG);
+  const int64_t tiles = m_tiles * ((N + block_n - 1) / block_n);
   const int units = num_sms() / CG;
   const int grid = CG * (int)(tiles < units ? tiles : units);
   auto kern = linear_tc_kernel<GELU, RES, TO, GW, CG>;
@@ -467,7 +509,7 @@ static int launch_tc_gw(const CUtensorMap& mx, const CUtensorMap& mw, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
-  PSW_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mw, mr, bias, (TO*)y, M, N, K, block_n, stages, g_tc_mode & 31));
+  PSW_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mw, mr, bias, (TO*)y, M, N, K, block_n, stages, g_tc_mode & 31, cv));
   return launch_status("linear_tc_kernel");
 }
 
@@ -489,15 +531,31 @@ static bool use_pair(int64_t M, int N, int K, int* block_n) {
   return true;
 }
 
+// conv != nullptr: x is an NHWC image [rows = B*H][W][cin] viewed through ConvView (wt tokens per row, ph x pw patches)
+struct ConvArgs { int BH, W, cin, ph, pw; };
+
 template <bool GELU, bool RES, typename TO>
 static int launch_tc(const void* x, const void* w, const float* bias, const void* residual, void* y, int64_t M, int N,
-                     int K, cudaStream_t st) {
+                     int K, cudaStream_t st, const ConvArgs* conv = nullptr) {
   constexpr int CW = Chunk<TO>::CW;
   int block_n = pick_block_n(N);
   const bool pair = use_pair(M, N, K, &block_n);
   const int cg = pair ? 2 : 1;
   CUtensorMap mx, mw, mr;
-  int rc = make_tensor_map_2d(&mx, x, (uint64_t)M, (uint64_t)K, TC_BM, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
+  ConvView cv = {0, 0, 0, 0};
+  int rc;
+  if (conv) {
+    const uint64_t dims[3] = {(uint64_t)conv->pw * conv->cin, (uint64_t)(conv->W / conv->pw), (uint64_t)conv->BH};
+    const uint64_t strides[2] = {(uint64_t)conv->pw * conv->cin * 2, (uint64_t)conv->W * conv->cin * 2};
+    const uint32_t box[3] = {TC_BK, TC_BM, 1};
+    rc = make_tensor_map_nd(&mx, x, 3, dims, strides, box, 2, CU_TENSOR_MAP_SWIZZLE_128B);
+    cv.tiles_x = 1;                                         // finalised per CTA-group size in launch_tc_gw
+    cv.wt = conv->W / conv->pw;
+    cv.kb_per_dy = conv->pw * conv->cin / TC_BK;
+    cv.ph = conv->ph;
+  } else {
+    rc = make_tensor_map_2d(&mx, x, (uint64_t)M, (uint64_t)K, TC_BM, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
   if (rc) return rc;
   rc = make_tensor_map_2d(&mw, w, (uint64_t)N, (uint64_t)K, (uint32_t)(block_n / cg), TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
@@ -521,11 +579,11 @@ static int launch_tc(const void* x, const void* w, const float* bias, const void
   PSW_REQUIRE(stages >= 2, PSW_ERR_UNSUPPORTED, "psw_linear_fwd(bf16): tile too large for shared memory");
   const size_t smem = fixed + stages * stage_bytes;
   if (pair) {
-    if (gw == 8) return launch_tc_gw<GELU, RES, TO, 8, 2>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, st);
-    return launch_tc_gw<GELU, RES, TO, 4, 2>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, st);
+    if (gw == 8) return launch_tc_gw<GELU, RES, TO, 8, 2>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, cv, st);
+    return launch_tc_gw<GELU, RES, TO, 4, 2>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, cv, st);
   }
-  if (gw == 8) return launch_tc_gw<GELU, RES, TO, 8, 1>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, st);
-  return launch_tc_gw<GELU, RES, TO, 4, 1>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, st);
+  if (gw == 8) return launch_tc_gw<GELU, RES, TO, 8, 1>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, cv, st);
+  return launch_tc_gw<GELU, RES, TO, 4, 1>(mx, mw, mr, bias, y, M, N, K, block_n, stages, smem, cv, st);
 }
 
 int linear_f32(const float* x, const float* w, const float* bias, const float* residual, float* y, int64_t M, int N,
@@ -539,6 +597,25 @@ extern "C" PSW_API int psw_debug_linear_mode(int mode) {
   const int old = g_tc_mode;
   g_tc_mode = mode;
   return old;
+}
+
+// Non-overlapping patch convolution (PatchEmbed.proj[6], reference :749: conv(kernel = stride = patch)) as a GEMM over
+// a 3-D TMA view of the NHWC image: no im2col, bias fused in the epilogue.
+extern "C" PSW_API int psw_patch_conv_fwd(const void* x, const void* w, const float* bias, void* out, int B, int H, int W,
+                                          int cin, int cout, int patch_h, int patch_w, void* stream) {
+  PSW_REQUIRE(x && w && out, PSW_ERR_BAD_ARG, "psw_patch_conv_fwd: null pointer");
+  PSW_REQUIRE(B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0 && patch_h > 0 && patch_w > 0, PSW_ERR_BAD_ARG,
+              "psw_patch_conv_fwd: bad dims");
+  PSW_REQUIRE(H % patch_h == 0 && W % patch_w == 0, PSW_ERR_BAD_ARG,
+              "psw_patch_conv_fwd: H=%d W=%d must be multiples of the patch %dx%d (pad the image first)", H, W, patch_h, patch_w);
+  PSW_REQUIRE((patch_w * cin) % TC_BK == 0 && cout % 16 == 0, PSW_ERR_UNSUPPORTED,
+              "psw_patch_conv_fwd: needs patch_w * cin %% 64 == 0 and cout %% 16 == 0 (cin=%d patch_w=%d cout=%d)", cin, patch_w, cout);
+  PSW_REQUIRE(aligned16(x) && aligned16(w) && aligned16(out) && aligned16(bias), PSW_ERR_BAD_ARG,
+              "psw_patch_conv_fwd: pointers must be 16-byte aligned");
+  const int64_t M = (int64_t)B * (H / patch_h) * (W / patch_w);
+  PSW_REQUIRE(M < (1ll << 31) && (int64_t)B * H < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_patch_conv_fwd: too many tokens");
+  const ConvArgs conv = {B * H, W, cin, patch_h, patch_w};
+  return launch_tc<false, false, bf16>(x, w, bias, nullptr, out, M, cout, patch_h * patch_w * cin, (cudaStream_t)stream, &conv);
 }
 
 extern "C" PSW_API int psw_debug_linear_cycles(long long* host_out16) {

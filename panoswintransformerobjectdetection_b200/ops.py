@@ -276,6 +276,22 @@ def stem_conv3x3_c32_relu(x_nhwc, w_taps, bias):
     return out
 
 
+def patch_conv(x_nhwc, w_ohwi, bias, patch):
+    """conv(kernel = stride = patch) of an NHWC bf16 image as a GEMM (reference PatchEmbed.proj[6], :749):
+    x [B, H, W, cin] -> tokens [B, H/ph, W/pw, cout] bf16.  w_ohwi [cout, ph, pw, cin] bf16, bias [cout] fp32."""
+    dev = _chk(x_nhwc, w_ohwi, bias)
+    B, H, W, cin = x_nhwc.shape
+    ph, pw = patch
+    cout = w_ohwi.shape[0]
+    if x_nhwc.dtype != torch.bfloat16 or w_ohwi.dtype != torch.bfloat16 or tuple(w_ohwi.shape) != (cout, ph, pw, cin):
+        raise PanoSwinB200Error("patch_conv wants bf16 NHWC x and bf16 w [cout, ph, pw, cin]")
+    out = torch.empty((B, H // ph, W // pw, cout), dtype=torch.bfloat16, device=x_nhwc.device)
+    with torch.cuda.device(dev):
+        _call("psw_patch_conv_fwd", _ptr(x_nhwc), _ptr(w_ohwi), _ptr(_f32(bias, "bias")), _ptr(out), B, H, W, cin, cout, ph, pw,
+              _stream(dev))
+    return out
+
+
 def cast(x, dtype):
     dev = _chk(x)
     out = torch.empty(x.shape, dtype=dtype, device=x.device)

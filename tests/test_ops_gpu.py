@@ -311,3 +311,19 @@ def test_stem_conv2_tcgen05(ops, B, H, W, cout):
     assert got.shape == (B, H, W, cout) and got.dtype == torch.bfloat16
     assert rel_l2(got.float(), want) <= 4e-3
     assert (got.float().cpu() - want).abs().max() <= 0.05
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,patch", [(2, 16, 512, 64, 96, (4, 4)), (1, 8, 1024, 64, 96, (4, 4)), (3, 12, 100, 64, 96, (4, 4)),
+                                                   (2, 8, 64, 32, 48, (2, 2)), (1, 4, 2048, 64, 128, (4, 4))])
+def test_patch_conv_as_gemm(ops, B, H, W, cin, cout, patch):
+    """conv(kernel = stride = patch) through the tcgen05 GEMM over a 3-D TMA view of the NHWC image (token rows that are
+    not a multiple of the 128-row tile included) vs torch fp32."""
+    g = _g(B + H + W + cout)
+    x = torch.randn(B, H, W, cin, generator=g).bfloat16()
+    w = (torch.randn(cout, cin, patch[0], patch[1], generator=g) / (cin * patch[0] * patch[1]) ** 0.5).bfloat16()
+    b = torch.randn(cout, generator=g)
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride=patch).permute(0, 2, 3, 1)
+    got = ops.patch_conv(x.to(DEV), w.permute(0, 2, 3, 1).contiguous().to(DEV), b.to(DEV), patch)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and got.dtype == torch.bfloat16
+    assert rel_l2(got.float(), want) <= 4e-3
