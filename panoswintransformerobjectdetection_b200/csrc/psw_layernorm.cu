@@ -11,31 +11,43 @@ namespace psw {
 constexpr int LN_WARPS = 8;
 
 // Row gather policies -----------------------------------------------------------------------------
+// A policy splits the address of 4-vector `vec` of row `r` into a per-vector part (loop invariant for a lane: computed
+// once per thread) and a per-row part (computed once per row), so the inner loop is a single add / compare.
 struct PlainRows {
   int64_t rows;
   int C;
+  struct Vec { int off; };
+  struct Row { int64_t base; };
   __device__ __forceinline__ int64_t num_rows() const { return rows; }
-  // element offset of 4-vector `vec` of row `r`, or -1 for an implicit zero vector
-  __device__ __forceinline__ int64_t offset(int64_t r, int vec) const { return r * C + (int64_t)vec * 4; }
+  __device__ __forceinline__ Vec vec_info(int vec) const { return {vec * 4}; }
+  __device__ __forceinline__ Row row_info(int64_t r) const { return {r * C}; }
+  // element offset of the vector, or -1 for an implicit zero vector
+  __device__ __forceinline__ int64_t offset(const Row& r, const Vec& v) const { return r.base + v.off; }
 };
 
 // PatchMerging (reference :563-573): output row (b, i2, j2) = concat of x[b, 2*i2+dh, 2*j2+dw, :] for
 // quadrant q = 0..3 with dh = q & 1, dw = q >> 1; cells beyond an odd H / W are zero.
 struct MergeRows {
   int B, H, W, C, H2, W2;
+  struct Vec { int dh, dw, off; };                         // quadrant of the vector and its offset inside the token
+  struct Row { int64_t base; int h0, w0; };                // token (2*i2, 2*j2) of the merged row
   __device__ __forceinline__ int64_t num_rows() const { return (int64_t)B * H2 * W2; }
-  __device__ __forceinline__ int64_t offset(int64_t r, int vec) const {
-    int vpc = C >> 2;
-    int q = vec / vpc;
-    int within = vec - q * vpc;
-    int j2 = (int)(r % W2);
-    int64_t t = r / W2;
-    int i2 = (int)(t % H2);
-    int b = (int)(t / H2);
-    int h = 2 * i2 + (q & 1);
-    int w = 2 * j2 + (q >> 1);
-    if (h >= H || w >= W) return -1;
-    return (((int64_t)b * H + h) * W + w) * C + (int64_t)within * 4;
+  __device__ __forceinline__ Vec vec_info(int vec) const {
+    const int vpc = C >> 2;
+    const int q = vec / vpc;
+    return {q & 1, q >> 1, (vec - q * vpc) * 4};
+  }
+  __device__ __forceinline__ Row row_info(int64_t r) const {       // merged rows < 2^31 (checked by the host)
+    const uint32_t ru = (uint32_t)r;
+    const uint32_t t = ru / (uint32_t)W2;
+    const int j2 = (int)(ru - t * (uint32_t)W2);
+    const uint32_t b = t / (uint32_t)H2;
+    const int i2 = (int)(t - b * (uint32_t)H2);
+    return {(((int64_t)b * H + 2 * i2) * W + 2 * j2) * C, 2 * i2, 2 * j2};
+  }
+  __device__ __forceinline__ int64_t offset(const Row& r, const Vec& v) const {
+    if (r.h0 + v.dh >= H || r.w0 + v.dw >= W) return -1;
+    return r.base + ((int64_t)v.dh * W + v.dw) * C + v.off;
   }
 };
 
@@ -58,17 +70,21 @@ layernorm_rows_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float*
   const float inv_c = 1.0f / (float)Cout;
   const int64_t rows_per_iter = (int64_t)GROUPS * U;
   const int64_t stride = (int64_t)gridDim.x * LN_WARPS * rows_per_iter;
+  typename Rows::Vec vinfo[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) vinfo[k] = rows.vec_info(sub + LPR * k);
   for (int64_t r0 = ((int64_t)blockIdx.x * LN_WARPS + warp) * rows_per_iter; r0 < nrows; r0 += stride) {
     float v[U][VPL][4];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t r = r0 + u * GROUPS + grp;
+      const typename Rows::Row rinfo = rows.row_info(r < nrows ? r : 0);
 #pragma unroll
       for (int k = 0; k < VPL; ++k) {
         const int vec = sub + LPR * k;
         v[u][k][0] = v[u][k][1] = v[u][k][2] = v[u][k][3] = 0.f;
         if (vec < nvec && r < nrows) {
-          const int64_t off = rows.offset(r, vec);
+          const int64_t off = rows.offset(rinfo, vinfo[k]);
           if (off >= 0) load4(x + off, v[u][k]);
         }
       }
@@ -205,44 +221,55 @@ layernorm_nchw_kernel(const TI* __restrict__ x, float* __restrict__ y, const flo
   const int b = (int)(blockIdx.x / tiles_per_img);
   const int64_t t0 = (blockIdx.x % tiles_per_img) * TT;
   const float inv_c = 1.0f / (float)C;
-  for (int rr = warp * GROUPS + grp; rr < TT; rr += 8 * GROUPS) {
-    const int64_t t = t0 + rr;
-    float v[VPL][4];
+  constexpr int U = VPL <= 3 ? 4 : 2;              // rows in flight per lane group (memory-level parallelism)
+  for (int rb = warp * GROUPS + grp; rb < TT; rb += 8 * GROUPS * U) {
+    float v[U][VPL][4];
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int vec = sub + LPR * k;
-      v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
-      if (vec < nvec && t < HW) load4(x + ((int64_t)b * HW + t) * C + vec * 4, v[k]);
-    }
-    float s = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int rr = rb + u * 8 * GROUPS;
+      const int64_t t = t0 + rr;
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) s += (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * inv_c;
-    float q = 0.f;
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      if (sub + LPR * k < nvec) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float d = v[k][e] - mean;
-          q += d * d;
-        }
+      for (int k = 0; k < VPL; ++k) {
+        const int vec = sub + LPR * k;
+        v[u][k][0] = v[u][k][1] = v[u][k][2] = v[u][k][3] = 0.f;
+        if (vec < nvec && rr < TT && t < HW) load4(x + ((int64_t)b * HW + t) * C + vec * 4, v[u][k]);
       }
     }
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q * inv_c + eps);
+    for (int u = 0; u < U; ++u) {
+      const int rr = rb + u * 8 * GROUPS;
+      float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int vec = sub + LPR * k;
-      if (vec < nvec) {
-        float g[4], bt[4];
-        load4(gamma + vec * 4, g);
-        load4(beta + vec * 4, bt);
+      for (int k = 0; k < VPL; ++k) s += (v[u][k][0] + v[u][k][1]) + (v[u][k][2] + v[u][k][3]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) tile[rr * P + vec * 4 + e] = (v[k][e] - mean) * rstd * g[e] + bt[e];
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * inv_c;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        if (sub + LPR * k < nvec) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float d = v[u][k][e] - mean;
+            q += d * d;
+          }
+        }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * inv_c + eps);
+      if (rr < TT) {
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          const int vec = sub + LPR * k;
+          if (vec < nvec) {
+            float g[4], bt[4];
+            load4(gamma + vec * 4, g);
+            load4(beta + vec * 4, bt);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) tile[rr * P + vec * 4 + e] = (v[u][k][e] - mean) * rstd * g[e] + bt[e];
+          }
+        }
       }
     }
   }
@@ -317,6 +344,7 @@ extern "C" PSW_API int psw_patch_merge_ln_fwd(const void* x, void* y, const floa
               "psw_patch_merge_ln_fwd: pointers must be 16-byte aligned");
   MergeRows mr{B, H, W, C, (H + 1) / 2, (W + 1) / 2};
   int64_t nrows = (int64_t)B * mr.H2 * mr.W2;
+  PSW_REQUIRE(nrows < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_patch_merge_ln_fwd: too many merged rows");
   return dispatch_ln(x, y, gamma, beta, nullptr, 1, mr, nrows, 4 * C, eps, in_dtype, out_dtype, (cudaStream_t)stream);
 }
 

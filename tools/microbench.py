@@ -303,3 +303,21 @@ def attn_hc(iters=20):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "attnhc":
     attn_hc()
+
+
+def ln_heads(iters=20):
+    """Output LayerNorm -> NCHW and patch-merge LayerNorm at the four stage shapes."""
+    for (tok, C, H, W) in [(32768, 96, 128, 256), (8192, 192, 64, 128), (2048, 384, 32, 64), (512, 768, 16, 32)]:
+        nb = max(2, int(400e6 // (B * tok * C * 8)) + 1)
+        x = [torch.randn(B, tok, C, device=DEV) for _ in range(nb)]
+        g, bb = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+        us = time_op(lambda i: ops.layernorm_nchw(x[i], g, bb, H, W), nb, iters)
+        print(f"layernorm_nchw B{B} {H}x{W} C{C}: {us:8.1f} us  {B * tok * C * 8 / us / 1e3:7.0f} GB/s", flush=True)
+        if C < 768:
+            g4, b4 = torch.ones(4 * C, device=DEV), torch.zeros(4 * C, device=DEV)
+            us = time_op(lambda i: ops.patch_merge_layernorm(x[i], g4, b4, H, W, out_dtype=torch.bfloat16), nb, iters)
+            print(f"patch_merge_ln B{B} {H}x{W} C{C}: {us:8.1f} us  {B * tok * C * 6 / us / 1e3:7.0f} GB/s", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "lnheads":
+    ln_heads()
