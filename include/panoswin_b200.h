@@ -75,6 +75,16 @@ PSW_API int psw_linear_fwd(const void* x, const void* w, const float* bias, cons
                    int64_t M, int N, int K, int flags, int dtype, int out_dtype, void* stream);
 
 /*
+ * psw_linear_fwd (bf16 operands, fp32 output + fp32 residual) with the LayerNorm of the result fused into the epilogue:
+ * y = x . w^T + bias + residual (fp32 [M, N]; y may alias residual) and ln_out = LayerNorm(y) * ln_gamma + ln_beta
+ * (bf16 [M, N]).  In a PanoSwin block: attn.proj + shortcut -> norm2, and mlp.fc2 + shortcut -> the next block's norm1
+ * (reference :520-535).  One tile must hold complete rows: N % 32 == 0 and N <= 256.
+ */
+PSW_API int psw_linear_ln_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                              const float* ln_gamma, const float* ln_beta, float ln_eps, void* ln_out,
+                              int64_t M, int N, int K, void* stream);
+
+/*
  * Fused (shifted-)window multi-head self-attention on an equirectangular token map.
  * Replaces, in ONE pass over HBM, WindowTransition.forward (:376-409, pano shift with longitude
  * wrap-around), pad_x (:486-491), window_partition (:64-75), the core of

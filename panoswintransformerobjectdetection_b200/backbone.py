@@ -531,13 +531,17 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         for i, layer in enumerate(self.layers):
             C = self.num_features[i]
             uv = self._const(("uv", H, W), lambda: make_uv_hw2(H, W), dev) if self.pano_mode else None
-            for blk in layer.blocks:
+            # LayerNorm fused into the producing GEMM's epilogue where one tile holds complete rows (C <= 256)
+            fuse_ln = cd == torch.bfloat16 and rd == torch.float32 and C % 32 == 0 and C <= 256
+            xn = None                                         # norm1(x) of the current block when already computed
+            for j, blk in enumerate(layer.blocks):
                 a = blk.attn
                 shift = blk.shift_size
                 mask = None
                 if not self.pano_mode and shift > 0:
                     mask = self._const(("mask", H, W, ws, shift), lambda: planar_attention_mask(H, W, ws, shift), dev)
-                xn = ops.layernorm(x, self._f(blk.norm1.weight), self._f(blk.norm1.bias), blk.norm1.eps, cd)
+                if xn is None:
+                    xn = ops.layernorm(x, self._f(blk.norm1.weight), self._f(blk.norm1.bias), blk.norm1.eps, cd)
                 qkv = ops.linear(xn, self._w(a.qkv.weight, cd), self._f(a.qkv.bias))
                 full_ok = cd == torch.bfloat16 and ws == 7 and C // a.num_heads == 32
                 if full_ok:                                  # tcgen05 kernel, all additive logit terms precomputed
@@ -547,10 +551,20 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                     att = ops.window_attention(qkv.view(B, H, W, 3 * C), self._f(a.sphere_position_alpha_table_Te),
                                                self._f(a.sphere_position_beta_table_Te), self._f(a.qkv.bias), uv, mask,
                                                a.num_heads, ws, shift, self.pano_mode, a.scale)
-                x = ops.linear(att.view(B, H * W, C), self._w(a.proj.weight, cd), self._f(a.proj.bias), residual=x, out=x)
-                xn = ops.layernorm(x, self._f(blk.norm2.weight), self._f(blk.norm2.bias), blk.norm2.eps, cd)
-                hid = ops.linear(xn, self._w(blk.mlp.fc1.weight, cd), self._f(blk.mlp.fc1.bias), gelu=True)
-                x = ops.linear(hid, self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), residual=x, out=x)
+                if fuse_ln:                                   # proj + shortcut -> norm2 in one kernel
+                    x, xn2 = ops.linear_layernorm(att.view(B, H * W, C), self._w(a.proj.weight, cd), self._f(a.proj.bias), x,
+                                                  self._f(blk.norm2.weight), self._f(blk.norm2.bias), blk.norm2.eps, out=x)
+                else:
+                    x = ops.linear(att.view(B, H * W, C), self._w(a.proj.weight, cd), self._f(a.proj.bias), residual=x, out=x)
+                    xn2 = ops.layernorm(x, self._f(blk.norm2.weight), self._f(blk.norm2.bias), blk.norm2.eps, cd)
+                hid = ops.linear(xn2, self._w(blk.mlp.fc1.weight, cd), self._f(blk.mlp.fc1.bias), gelu=True)
+                nxt = layer.blocks[j + 1] if j + 1 < len(layer.blocks) else None
+                if fuse_ln and nxt is not None:               # fc2 + shortcut -> the next block's norm1
+                    x, xn = ops.linear_layernorm(hid, self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), x,
+                                                 self._f(nxt.norm1.weight), self._f(nxt.norm1.bias), nxt.norm1.eps, out=x)
+                else:
+                    x = ops.linear(hid, self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), residual=x, out=x)
+                    xn = None
             if i in self.out_indices:
                 n = getattr(self, f"norm{i}")
                 outs.append(ops.layernorm_nchw(x, self._f(n.weight), self._f(n.bias), H, W, n.eps))

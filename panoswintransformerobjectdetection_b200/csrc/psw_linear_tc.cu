@@ -148,12 +148,32 @@ template <> struct Chunk<bf16> { static constexpr int CW = 32; };
 // buffer g, i.e. every second tile of the CTA, so the math of one group overlaps the stores of the other.
 template <int GW> struct EpiCfg { static constexpr int EW = 2 * GW; static constexpr int THREADS = 64 + 32 * EW; };
 
-template <bool GELU, bool RES, typename TO, int GW, int CG>
+// LayerNorm of the freshly written rows fused into the epilogue (LNF; proj -> norm2 and fc2 -> next block's norm1 when
+// one tile holds complete rows, N <= 256): the thread that owns TMEM lane r makes three passes over its row, which
+// stays in tensor memory -- (1) x = acc + bias + residual, written out in fp32, summed, and written BACK to TMEM,
+// (2) centred sum of squares, (3) (x - mean) * rstd * gamma + beta -> bf16, written to ln_out.  Two-pass statistics in
+// fp32 like the standalone kernel; saves the LayerNorm kernel's re-read of the fp32 residual stream.
+struct LnFuse {
+  const float* gamma;
+  const float* beta;
+  bf16* out;              // [M, N] bf16
+  float eps;
+};
+
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+template <bool GELU, bool RES, typename TO, int GW, int CG, bool LNF = false>
 __global__ void __launch_bounds__(EpiCfg<GW>::THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_r,
                  const float* __restrict__ bias, TO* __restrict__ y, int64_t M, int N, int K, int block_n, int stages, int mode,
-                 const ConvView cv) {
+                 const ConvView cv, const LnFuse ln) {
   constexpr int CW = Chunk<TO>::CW;
   constexpr int TC_EPI_WARPS = EpiCfg<GW>::EW;
   constexpr int PER_QUAD = GW / 4;                            // warps of one group sharing a TMEM lane quadrant
@@ -181,6 +201,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   const uint32_t acc_stride = 256;
 
   for (int i = threadIdx.x; i < n_tiles * block_n; i += blockDim.x) bias_s[i] = (bias && i < N) ? bias[i] : 0.0f;
+  float* gam_s = bias_s + n_tiles * block_n;                  // LNF: gamma, beta of the fused LayerNorm
+  float* bet_s = gam_s + N;
+  if constexpr (LNF) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { gam_s[i] = ln.gamma[i]; bet_s[i] = ln.beta[i]; }
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_w);
@@ -294,6 +319,144 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
   } else {
     // ------------------------------- epilogue ------------------------------------
+    if constexpr (LNF) {
+      // one warp per TMEM lane quadrant and group (GW = 4): lane r owns row r of the tile for all three passes
+      static_assert(!LNF || (RES && sizeof(TO) == 4 && GW == 4 && CG == 1 && !GELU), "LNF: fp32 residual epilogue, GW = 4");
+      const int ew = warp - 2;
+      const int quad = warp & 3;
+      const int grp = ew / GW;
+      uint8_t* my_smem = epi_smem + ew * EPI_PER_WARP;
+      uint8_t* out_buf = my_smem;
+      uint8_t* res_buf0 = my_smem + TC_TILE_BYTES;
+      uint64_t* res_bar = tail->res_bar[ew];
+      const int n_chunks = N / 16;                            // N % 32 == 0 and N == block_n (checked by the host)
+      const int sw = (lane >> 1) & 3;
+      uint8_t* my_row_out = out_buf + lane * 64;
+      const uint8_t* my_row_res0 = res_buf0 + lane * 64;
+      const int t_row = lane >> 2, t_piece = lane & 3;
+      const int acc = grp;
+      uint32_t acc_phase = 0;
+      uint32_t res_issued = 0, res_used = 0;
+      const float inv_n = 1.0f / (float)N;
+      for (int64_t tile = unit + (int64_t)grp * n_units; tile < total_tiles; tile += 2 * n_units) {
+        const int row0 = (int)tile * TILE_M + quad * 32;      // n_tiles == 1
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            if (j < n_chunks) {
+              const uint32_t b = res_issued & 1;
+              mbar_expect_tx(&res_bar[b], TC_TILE_BYTES);
+              tma_load_2d(res_buf0 + b * TC_TILE_BYTES, &map_r, &res_bar[b], j * 16, row0);
+              ++res_issued;
+            }
+        }
+        mbar_wait(&tail->tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * acc_stride;
+        // ---- pass 1: x = acc + bias + residual -> y (fp32) and back into TMEM; row sum
+        float sum = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t r[16];
+          tmem_ld_x16(t_addr + (uint32_t)(c * 16), r);
+          tmem_ld_wait();
+          float v[16];
+          const float4* bs = reinterpret_cast<const float4*>(bias_s + c * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = bs[i];
+            v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
+          }
+          {
+            const uint32_t b = res_used & 1;
+            mbar_wait(&res_bar[b], (res_used >> 1) & 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 t = *reinterpret_cast<const uint4*>(my_row_res0 + b * TC_TILE_BYTES + ((q ^ sw) << 4));
+              v[4 * q] += __uint_as_float(t.x); v[4 * q + 1] += __uint_as_float(t.y);
+              v[4 * q + 2] += __uint_as_float(t.z); v[4 * q + 3] += __uint_as_float(t.w);
+            }
+            ++res_used;
+            __syncwarp();
+            if (lane == 0 && c + 2 < n_chunks) {
+              const uint32_t nb = res_issued & 1;
+              mbar_expect_tx(&res_bar[nb], TC_TILE_BYTES);
+              tma_load_2d(res_buf0 + nb * TC_TILE_BYTES, &map_r, &res_bar[nb], (c + 2) * 16, row0);
+              ++res_issued;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { sum += v[i]; r[i] = __float_as_uint(v[i]); }
+          tmem_st_x16(t_addr + (uint32_t)(c * 16), r);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(my_row_out + ((q ^ sw) << 4)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+          __syncwarp();
+          {
+            uint4 t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int rr = t_row + 8 * j;
+              t[j] = *reinterpret_cast<const uint4*>(out_buf + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4));
+            }
+            uint8_t* gp = reinterpret_cast<uint8_t*>(y + (int64_t)(row0 + t_row) * N + c * 16) + t_piece * 16;
+            const int64_t step = (int64_t)8 * N * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (row0 + t_row + 8 * j < M) *reinterpret_cast<uint4*>(gp + j * step) = t[j];
+          }
+          __syncwarp();
+        }
+        tmem_st_wait();
+        const float mean = sum * inv_n;
+        // ---- pass 2: centred sum of squares
+        float qs = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t r[16];
+          tmem_ld_x16(t_addr + (uint32_t)(c * 16), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { const float d = __uint_as_float(r[i]) - mean; qs = fmaf(d, d, qs); }
+        }
+        const float rstd = rsqrtf(qs * inv_n + ln.eps);
+        // ---- pass 3: normalise -> bf16, 32 columns (64 B per row) at a time
+        for (int c = 0; c < n_chunks / 2; ++c) {
+          uint32_t r[32];
+          tmem_ld_x32(t_addr + (uint32_t)(c * 32), r);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = c * 32 + 2 * i;
+            const float o0 = fmaf((__uint_as_float(r[2 * i]) - mean) * rstd, gam_s[col], bet_s[col]);
+            const float o1 = fmaf((__uint_as_float(r[2 * i + 1]) - mean) * rstd, gam_s[col + 1], bet_s[col + 1]);
+            pk[i] = pack_bf16x2(o0, o1);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(my_row_out + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          __syncwarp();
+          {
+            uint4 t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int rr = t_row + 8 * j;
+              t[j] = *reinterpret_cast<const uint4*>(out_buf + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4));
+            }
+            uint8_t* gp = reinterpret_cast<uint8_t*>(ln.out + (int64_t)(row0 + t_row) * N + c * 32) + t_piece * 16;
+            const int64_t step = (int64_t)8 * N * 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (row0 + t_row + 8 * j < M) *reinterpret_cast<uint4*>(gp + j * step) = t[j];
+          }
+          __syncwarp();
+        }
+        tc_fence_before();                                    // the accumulator is free again
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->tempty[acc]);
+        acc_phase ^= 1;
+      }
+    } else {
     const int ew = warp - 2;
     const int quad = warp & 3;                                // TMEM lane quadrant this warp may access
     const int grp = ew / GW;                                  // group = accumulator buffer = tile parity of this CTA
@@ -461,6 +624,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       acc_phase ^= 1;
     }
     if (prof && lane == 0) { g_tc_cycles[4] = c_w; g_tc_cycles[5] = c_ld; g_tc_cycles[6] = c_ma; g_tc_cycles[7] = c_st; }
+    }
   }
 
   tc_fence_before();
@@ -509,7 +673,8 @@ static int launch_tc_gw(const CUtensorMap& mx, const CUtensorMap& mw, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
-  PSW_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mw, mr, bias, (TO*)y, M, N, K, block_n, stages, g_tc_mode & 31, cv));
+  const LnFuse no_ln = {nullptr, nullptr, nullptr, 0.f};
+  PSW_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mw, mr, bias, (TO*)y, M, N, K, block_n, stages, g_tc_mode & 31, cv, no_ln));
   return launch_status("linear_tc_kernel");
 }
 
@@ -597,6 +762,46 @@ extern "C" PSW_API int psw_debug_linear_mode(int mode) {
   const int old = g_tc_mode;
   g_tc_mode = mode;
   return old;
+}
+
+// y = x . w^T + bias + residual (fp32, may alias residual) and ln_out = LayerNorm(y) * gamma + beta (bf16) in one pass.
+static int launch_tc_lnf(const void* x, const void* w, const float* bias, const void* residual, void* y, const LnFuse& ln,
+                         int64_t M, int N, int K, cudaStream_t st) {
+  const int block_n = N;
+  CUtensorMap mx, mw, mr;
+  int rc = make_tensor_map_2d(&mx, x, (uint64_t)M, (uint64_t)K, TC_BM, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&mw, w, (uint64_t)N, (uint64_t)K, (uint32_t)block_n, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&mr, residual, (uint64_t)M, (uint64_t)N, 32, 16, 4, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  constexpr int GW = 4;
+  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)block_n * TC_BK * 2;
+  const size_t fixed = 1024 + (size_t)2 * GW * 3 * TC_TILE_BYTES + sizeof(TcSmemTail) + (size_t)3 * N * sizeof(float);
+  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  PSW_REQUIRE(stages >= 2, PSW_ERR_UNSUPPORTED, "psw_linear_ln_fwd: tile too large for shared memory");
+  const size_t smem = fixed + stages * stage_bytes;
+  const int64_t tiles = (M + TC_BM - 1) / TC_BM;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  auto kern = linear_tc_kernel<false, true, float, GW, 1, true>;
+  PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const ConvView cv = {0, 0, 0, 0};
+  kern<<<grid, EpiCfg<GW>::THREADS, smem, st>>>(mx, mw, mr, bias, (float*)y, M, N, K, block_n, stages, 0, cv, ln);
+  return launch_status("linear_tc_kernel<LNF>");
+}
+
+extern "C" PSW_API int psw_linear_ln_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                         const float* ln_gamma, const float* ln_beta, float ln_eps, void* ln_out,
+                                         int64_t M, int N, int K, void* stream) {
+  PSW_REQUIRE(x && w && residual && y && ln_gamma && ln_beta && ln_out, PSW_ERR_BAD_ARG, "psw_linear_ln_fwd: null pointer");
+  PSW_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31), PSW_ERR_BAD_ARG, "psw_linear_ln_fwd: M=%lld N=%d K=%d", (long long)M, N, K);
+  PSW_REQUIRE(N % 32 == 0 && N <= 256 && K % 8 == 0, PSW_ERR_UNSUPPORTED,
+              "psw_linear_ln_fwd: needs N %% 32 == 0, N <= 256 (one tile per row) and K %% 8 == 0 (N=%d K=%d)", N, K);
+  PSW_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(bias) && aligned16(residual) && aligned16(ln_out),
+              PSW_ERR_BAD_ARG, "psw_linear_ln_fwd: pointers must be 16-byte aligned");
+  const LnFuse ln = {ln_gamma, ln_beta, (bf16*)ln_out, ln_eps};
+  return launch_tc_lnf(x, w, bias, residual, y, ln, M, N, K, (cudaStream_t)stream);
 }
 
 // Non-overlapping patch convolution (PatchEmbed.proj[6], reference :749: conv(kernel = stride = patch)) as a GEMM over

@@ -119,6 +119,23 @@ def linear(x, w, bias=None, residual=None, gelu=False, out_dtype=None, out=None)
     return out
 
 
+def linear_layernorm(x, w, bias, residual, ln_gamma, ln_beta, ln_eps, out=None):
+    """y = x @ w^T + bias + residual (fp32; `out` may be the residual tensor itself) and LayerNorm(y) (bf16) in one
+    kernel (bf16 x / w; N % 32 == 0, N <= 256).  Returns (y, ln_out)."""
+    dev = _chk(x, w, bias, residual, ln_gamma, ln_beta, out)
+    M, K = x.numel() // x.shape[-1], x.shape[-1]
+    N = w.shape[0]
+    if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or residual.dtype != torch.float32:
+        raise PanoSwinB200Error("linear_layernorm wants bf16 x / w and an fp32 residual")
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+    ln_out = torch.empty(x.shape[:-1] + (N,), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(dev):
+        _call("psw_linear_ln_fwd", _ptr(x), _ptr(w), _ptr(_f32(bias, "bias")), _ptr(residual), _ptr(out),
+              _ptr(_f32(ln_gamma, "ln_gamma")), _ptr(_f32(ln_beta, "ln_beta")), float(ln_eps), _ptr(ln_out), M, N, K, _stream(dev))
+    return out, ln_out
+
+
 def window_grid(H, W, window, pano_mode):
     """(windows per column, windows per row) of the map the attention runs on (host-only helper)."""
     import ctypes

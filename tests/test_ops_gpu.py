@@ -327,3 +327,26 @@ def test_patch_conv_as_gemm(ops, B, H, W, cin, cout, patch):
     torch.cuda.synchronize()
     assert got.shape == want.shape and got.dtype == torch.bfloat16
     assert rel_l2(got.float(), want) <= 4e-3
+
+
+@pytest.mark.parametrize("mnk", [(300, 96, 96), (4096, 96, 384), (1000, 192, 192), (777, 192, 768), (130, 256, 64), (20000, 96, 96)])
+@pytest.mark.parametrize("alias", [False, True])
+def test_linear_layernorm_fused(ops, mnk, alias):
+    """proj / fc2 with the following LayerNorm fused into the GEMM epilogue: y = x w^T + b + residual (fp32) and
+    LN(y) (bf16), against fp64; `alias` writes y over the residual tensor as the backbone does."""
+    M, N, K = mnk
+    g = _g(M + N + K)
+    x = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g) * 3 + 1.5                   # a mean offset exercises the two-pass variance
+    gam, bet = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g)
+    want_y = F.linear(x.double(), w.double(), b.double()) + r.double()
+    want_ln = F.layer_norm(want_y, (N,), gam.double(), bet.double(), 1e-5)
+    rd = r.to(DEV)
+    y, ln = ops.linear_layernorm(x.to(DEV), w.to(DEV), b.to(DEV), rd, gam.to(DEV), bet.to(DEV), 1e-5, out=rd if alias else None)
+    torch.cuda.synchronize()
+    assert y.dtype == torch.float32 and ln.dtype == torch.bfloat16 and ln.shape == (M, N)
+    assert (y.data_ptr() == rd.data_ptr()) == alias
+    assert rel_l2(y, want_y) <= 2e-5
+    assert rel_l2(ln.float(), want_ln) <= 4e-3

@@ -321,3 +321,25 @@ def ln_heads(iters=20):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "lnheads":
     ln_heads()
+
+
+def linear_lnf(iters=20):
+    """proj / fc2 with the fused LayerNorm epilogue vs the plain GEMM + standalone LayerNorm."""
+    for (tok, N, K) in [(32768, 96, 96), (32768, 96, 384), (8192, 192, 192), (8192, 192, 768)]:
+        M = tok * B
+        nb = max(2, int(400e6 // (M * (K * 2 + N * 10))) + 1)
+        x = [torch.randn(M, K, device=DEV).bfloat16() for _ in range(nb)]
+        y = [torch.randn(M, N, device=DEV) for _ in range(nb)]
+        xn = [torch.empty(M, N, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
+        w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+        b = torch.randn(N, device=DEV)
+        g, bb = torch.ones(N, device=DEV), torch.zeros(N, device=DEV)
+        us0 = time_op(lambda i: ops.linear(x[i], w, b, residual=y[i], out=y[i], out_dtype=torch.float32), nb, iters)
+        us1 = time_op(lambda i: ops.layernorm(y[i], g, bb, 1e-5, torch.bfloat16, out=xn[i]), nb, iters)
+        us2 = time_op(lambda i: ops.linear_layernorm(x[i], w, b, y[i], g, bb, 1e-5, out=y[i]), nb, iters)
+        byt = M * (K * 2 + N * 10)
+        print(f"M{M} N{N} K{K}: linear {us0:.1f} us + layernorm {us1:.1f} us = {us0 + us1:.1f}   fused {us2:.1f} us  {byt / us2 / 1e3:.0f} GB/s", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "lnf":
+    linear_lnf()
