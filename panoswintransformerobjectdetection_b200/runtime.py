@@ -122,24 +122,24 @@ class HostPipeline:
         return h
 
     def _schedule(self, B):
-        """Chunk boundaries: a half-size first chunk (the copy-out stream starts early) and a half-size last chunk
-        (short tail after the last forward), full chunks in between."""
+        """Chunk boundaries.  The copy-out stream is the critical resource: it should start early and then never
+        starve, so the chunks ramp up (c/2, 3c/4, 3c/4, c, c, ...): a small first chunk puts the first feature map
+        on the wire early, and no chunk takes much longer to compute than its predecessor takes to copy out."""
         c = self.chunk
-        sizes = []
-        left = B
         if self.sizes is not None and sum(self.sizes) == B:
             sizes = list(self.sizes)
-        elif B > 2 * c and c >= 2:
-            sizes.append(c // 2)
-            left -= c // 2
-            while left > c + c // 2:
-                sizes.append(c)
-                left -= c
-            if left > c // 2:
-                sizes.append(left - c // 2)
-                left = c // 2
-            sizes.append(left)
+        elif B > 2 * c and c >= 4:
+            sizes, left = [], B
+            for n in (c // 2, (3 * c) // 4, (3 * c) // 4):
+                sizes.append(n)
+                left -= n
+            while left > 0:
+                sizes.append(min(c, left))
+                left -= sizes[-1]
+            if len(sizes) > 1 and sizes[-1] < c // 4:        # fold a tiny tail into the previous chunk
+                sizes[-2] += sizes.pop()
         else:
+            sizes, left = [], B
             while left > 0:
                 sizes.append(min(c, left))
                 left -= sizes[-1]
