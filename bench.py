@@ -142,6 +142,11 @@ def launch_work(fn, a):
         tok = B * (H // ph) * (W // pw)
         return dict(kind="patch_conv", shape=f"B{B} {H}x{W} {cin}->{cout} /{ph}", bytes=float(B * H * W * cin * 2 + tok * cout * 2),
                     flops=2.0 * tok * cout * ph * pw * cin)
+    if fn == "psw_patch_conv_ln_fwd":
+        B, H, W, cin, cout, ph, pw = a[9], a[10], a[11], a[12], a[13], a[14], a[15]
+        tok = B * (H // ph) * (W // pw)
+        return dict(kind="patch_conv", shape=f"B{B} {H}x{W} {cin}->{cout} /{ph} +LN+pos", bytes=float(B * H * W * cin * 2 + tok * cout * 4),
+                    flops=2.0 * tok * cout * ph * pw * cin)
     return dict(kind=fn, shape="", bytes=0.0, flops=0.0)
 
 

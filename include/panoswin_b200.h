@@ -196,6 +196,16 @@ PSW_API int psw_stem_conv3x3_c32_relu_fwd(const void* x, const void* w_taps, con
 PSW_API int psw_patch_conv_fwd(const void* x, const void* w, const float* bias, void* out, int B, int H, int W,
                                int cin, int cout, int patch_h, int patch_w, void* stream);
 
+/*
+ * The whole tail of the stem in one kernel: psw_patch_conv_fwd + patch_norm LayerNorm + absolute position add
+ * (PatchEmbed.forward :768-771, SimplePanoSwinTransformer.forward :925-936):
+ * out fp32 [B * H/ph * W/pw, cout] = LN(conv(x) + bias) * ln_gamma + ln_beta + pos[token % pos_rows].
+ * pos [pos_rows, cout] fp32 or NULL.  cout % 32 == 0, cout <= 256.
+ */
+PSW_API int psw_patch_conv_ln_fwd(const void* x, const void* w, const float* bias, const float* ln_gamma,
+                                  const float* ln_beta, float ln_eps, const float* pos, int64_t pos_rows, void* out,
+                                  int B, int H, int W, int cin, int cout, int patch_h, int patch_w, void* stream);
+
 /* dtype conversion helper for activations entering / leaving the bf16 path: n elements. */
 PSW_API int psw_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
 

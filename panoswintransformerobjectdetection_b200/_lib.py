@@ -31,6 +31,7 @@ SIGNATURES = {
     "psw_stem_conv3x3_relu_fwd": [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],
     "psw_stem_conv3x3_c32_relu_fwd": [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _vp],
     "psw_patch_conv_fwd": [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "psw_patch_conv_ln_fwd": [_vp, _vp, _fp, _fp, _fp, _f, _fp, _i64, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "psw_cast": [_vp, _vp, _i64, _i, _i, _vp],
     "psw_window_attn_fwd_profile": [_vp, _vp, _fp, _fp, _vp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp],
     "psw_debug_linear_mode": [_i],

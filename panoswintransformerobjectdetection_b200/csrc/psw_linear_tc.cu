@@ -156,9 +156,13 @@ template <int GW> struct EpiCfg { static constexpr int EW = 2 * GW; static const
 struct LnFuse {
   const float* gamma;
   const float* beta;
-  bf16* out;              // [M, N] bf16
+  bf16* out;              // LNF 1: [M, N] bf16
   float eps;
+  const float* pos;       // LNF 2: position rows added after the LayerNorm ([pos_rows, N] fp32, row = GEMM row % pos_rows)
+  int pos_rows;
 };
+// LNF 1: y = acc + bias + residual (fp32, written) and ln.out = LN(y) (bf16).
+// LNF 2: y = LN(acc + bias) * gamma + beta + pos (fp32) only -- the stem: patch conv -> patch_norm -> + abs. position.
 
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -168,7 +172,7 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[
       : "memory");
 }
 
-template <bool GELU, bool RES, typename TO, int GW, int CG, bool LNF = false>
+template <bool GELU, bool RES, typename TO, int GW, int CG, int LNF = 0>
 __global__ void __launch_bounds__(EpiCfg<GW>::THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                  const __grid_constant__ CUtensorMap map_r,
@@ -203,7 +207,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   for (int i = threadIdx.x; i < n_tiles * block_n; i += blockDim.x) bias_s[i] = (bias && i < N) ? bias[i] : 0.0f;
   float* gam_s = bias_s + n_tiles * block_n;                  // LNF: gamma, beta of the fused LayerNorm
   float* bet_s = gam_s + N;
-  if constexpr (LNF) {
+  if constexpr (LNF != 0) {
     for (int i = threadIdx.x; i < N; i += blockDim.x) { gam_s[i] = ln.gamma[i]; bet_s[i] = ln.beta[i]; }
   }
   if (warp == 0 && lane == 0) {
@@ -319,9 +323,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     }
   } else {
     // ------------------------------- epilogue ------------------------------------
-    if constexpr (LNF) {
+    if constexpr (LNF != 0) {
       // one warp per TMEM lane quadrant and group (GW = 4): lane r owns row r of the tile for all three passes
-      static_assert(!LNF || (RES && sizeof(TO) == 4 && GW == 4 && CG == 1 && !GELU), "LNF: fp32 residual epilogue, GW = 4");
+      static_assert(LNF == 0 || (sizeof(TO) == 4 && GW == 4 && CG == 1 && !GELU && RES == (LNF == 1)), "LNF: fp32 epilogue, GW = 4");
       const int ew = warp - 2;
       const int quad = warp & 3;
       const int grp = ew / GW;
@@ -339,8 +343,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       uint32_t res_issued = 0, res_used = 0;
       const float inv_n = 1.0f / (float)N;
       for (int64_t tile = unit + (int64_t)grp * n_units; tile < total_tiles; tile += 2 * n_units) {
-        const int row0 = (int)tile * TILE_M + quad * 32;      // n_tiles == 1
-        if (lane == 0) {
+        int row0 = (int)tile * TILE_M + quad * 32;            // n_tiles == 1
+        int64_t row_lim = M;
+        if (cv.tiles_x) {
+          const int trow = (int)tile / cv.tiles_x;
+          row0 = trow * cv.wt + ((int)tile - trow * cv.tiles_x) * TILE_M + quad * 32;
+          row_lim = (int64_t)(trow + 1) * cv.wt;
+        }
+        if (LNF == 1 && lane == 0) {
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             if (j < n_chunks) {
@@ -367,7 +377,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
             v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
           }
-          {
+          if constexpr (LNF == 1) {
             const uint32_t b = res_used & 1;
             mbar_wait(&res_bar[b], (res_used >> 1) & 1);
 #pragma unroll
@@ -388,24 +398,26 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) { sum += v[i]; r[i] = __float_as_uint(v[i]); }
           tmem_st_x16(t_addr + (uint32_t)(c * 16), r);
+          if constexpr (LNF == 1) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(my_row_out + ((q ^ sw) << 4)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-          __syncwarp();
-          {
-            uint4 t[4];
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(my_row_out + ((q ^ sw) << 4)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            __syncwarp();
+            {
+              uint4 t[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int rr = t_row + 8 * j;
-              t[j] = *reinterpret_cast<const uint4*>(out_buf + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4));
+              for (int j = 0; j < 4; ++j) {
+                const int rr = t_row + 8 * j;
+                t[j] = *reinterpret_cast<const uint4*>(out_buf + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4));
+              }
+              uint8_t* gp = reinterpret_cast<uint8_t*>(y + (int64_t)(row0 + t_row) * N + c * 16) + t_piece * 16;
+              const int64_t step = (int64_t)8 * N * 4;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (row0 + t_row + 8 * j < row_lim) *reinterpret_cast<uint4*>(gp + j * step) = t[j];
             }
-            uint8_t* gp = reinterpret_cast<uint8_t*>(y + (int64_t)(row0 + t_row) * N + c * 16) + t_piece * 16;
-            const int64_t step = (int64_t)8 * N * 4;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (row0 + t_row + 8 * j < M) *reinterpret_cast<uint4*>(gp + j * step) = t[j];
+            __syncwarp();
           }
-          __syncwarp();
         }
         tmem_st_wait();
         const float mean = sum * inv_n;
@@ -419,6 +431,58 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           for (int i = 0; i < 16; ++i) { const float d = __uint_as_float(r[i]) - mean; qs = fmaf(d, d, qs); }
         }
         const float rstd = rsqrtf(qs * inv_n + ln.eps);
+        if constexpr (LNF == 2) {
+          // ---- pass 3 (stem): normalise, add the position row, write fp32 -- 16 columns (64 B per row) at a time.  The
+          //      position rows are fetched coalesced (four lanes per row) and handed to the row owners through smem.
+          for (int c = 0; c < n_chunks; ++c) {
+            {
+              const uint8_t* pp = reinterpret_cast<const uint8_t*>(ln.pos) + (size_t)c * 64 + t_piece * 16;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int rr = t_row + 8 * j;
+                uint4 t = make_uint4(0, 0, 0, 0);
+                if (ln.pos != nullptr && row0 + rr < row_lim)
+                  t = __ldg(reinterpret_cast<const uint4*>(pp + (size_t)((row0 + rr) % ln.pos_rows) * N * 4));
+                *reinterpret_cast<uint4*>(out_buf + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4)) = t;
+              }
+            }
+            uint32_t r[16];
+            tmem_ld_x16(t_addr + (uint32_t)(c * 16), r);
+            tmem_ld_wait();
+            __syncwarp();
+            uint32_t o[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 p4 = *reinterpret_cast<const uint4*>(my_row_out + ((q ^ sw) << 4));
+              const uint32_t pw[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int col = c * 16 + 4 * q + i;
+                o[4 * q + i] = __float_as_uint(fmaf((__uint_as_float(r[4 * q + i]) - mean) * rstd, gam_s[col], bet_s[col]) +
+                                               __uint_as_float(pw[i]));
+              }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(my_row_out + ((q ^ sw) << 4)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            __syncwarp();
+            {
+              uint4 t[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int rr = t_row + 8 * j;
+                t[j] = *reinterpret_cast<const uint4*>(out_buf + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4));
+              }
+              uint8_t* gp = reinterpret_cast<uint8_t*>(y + (int64_t)(row0 + t_row) * N + c * 16) + t_piece * 16;
+              const int64_t step = (int64_t)8 * N * 4;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (row0 + t_row + 8 * j < row_lim) *reinterpret_cast<uint4*>(gp + j * step) = t[j];
+            }
+            __syncwarp();
+          }
+        } else {
         // ---- pass 3: normalise -> bf16, 32 columns (64 B per row) at a time
         for (int c = 0; c < n_chunks / 2; ++c) {
           uint32_t r[32];
@@ -447,9 +511,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const int64_t step = (int64_t)8 * N * 2;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (row0 + t_row + 8 * j < M) *reinterpret_cast<uint4*>(gp + j * step) = t[j];
+              if (row0 + t_row + 8 * j < row_lim) *reinterpret_cast<uint4*>(gp + j * step) = t[j];
           }
           __syncwarp();
+        }
         }
         tc_fence_before();                                    // the accumulator is free again
         __syncwarp();
@@ -673,7 +738,7 @@ static int launch_tc_gw(const CUtensorMap& mx, const CUtensorMap& mw, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
-  const LnFuse no_ln = {nullptr, nullptr, nullptr, 0.f};
+  const LnFuse no_ln = {nullptr, nullptr, nullptr, 0.f, nullptr, 1};
   PSW_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mw, mr, bias, (TO*)y, M, N, K, block_n, stages, g_tc_mode & 31, cv, no_ln));
   return launch_status("linear_tc_kernel");
 }
@@ -764,16 +829,30 @@ extern "C" PSW_API int psw_debug_linear_mode(int mode) {
   return old;
 }
 
-// y = x . w^T + bias + residual (fp32, may alias residual) and ln_out = LayerNorm(y) * gamma + beta (bf16) in one pass.
+// LNF 1: y = x . w^T + bias + residual (fp32, may alias residual) and ln_out = LayerNorm(y) * gamma + beta (bf16).
+// LNF 2 (residual == nullptr): y = LayerNorm(x . w^T + bias) * gamma + beta + pos (fp32); x may be a patch-conv view.
 static int launch_tc_lnf(const void* x, const void* w, const float* bias, const void* residual, void* y, const LnFuse& ln,
-                         int64_t M, int N, int K, cudaStream_t st) {
+                         int64_t M, int N, int K, cudaStream_t st, const ConvArgs* conv = nullptr) {
   const int block_n = N;
   CUtensorMap mx, mw, mr;
-  int rc = make_tensor_map_2d(&mx, x, (uint64_t)M, (uint64_t)K, TC_BM, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
+  ConvView cv = {0, 0, 0, 0};
+  int rc;
+  if (conv) {
+    const uint64_t dims[3] = {(uint64_t)conv->pw * conv->cin, (uint64_t)(conv->W / conv->pw), (uint64_t)conv->BH};
+    const uint64_t strides[2] = {(uint64_t)conv->pw * conv->cin * 2, (uint64_t)conv->W * conv->cin * 2};
+    const uint32_t box[3] = {TC_BK, TC_BM, 1};
+    rc = make_tensor_map_nd(&mx, x, 3, dims, strides, box, 2, CU_TENSOR_MAP_SWIZZLE_128B);
+    cv.wt = conv->W / conv->pw;
+    cv.tiles_x = (cv.wt + TC_BM - 1) / TC_BM;
+    cv.kb_per_dy = conv->pw * conv->cin / TC_BK;
+    cv.ph = conv->ph;
+  } else {
+    rc = make_tensor_map_2d(&mx, x, (uint64_t)M, (uint64_t)K, TC_BM, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
+  }
   if (rc) return rc;
   rc = make_tensor_map_2d(&mw, w, (uint64_t)N, (uint64_t)K, (uint32_t)block_n, TC_BK, 2, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = make_tensor_map_2d(&mr, residual, (uint64_t)M, (uint64_t)N, 32, 16, 4, CU_TENSOR_MAP_SWIZZLE_64B);
+  rc = make_tensor_map_2d(&mr, residual ? residual : y, (uint64_t)M, (uint64_t)N, 32, 16, 4, CU_TENSOR_MAP_SWIZZLE_64B);
   if (rc) return rc;
   constexpr int GW = 4;
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)block_n * TC_BK * 2;
@@ -782,12 +861,17 @@ static int launch_tc_lnf(const void* x, const void* w, const float* bias, const 
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   PSW_REQUIRE(stages >= 2, PSW_ERR_UNSUPPORTED, "psw_linear_ln_fwd: tile too large for shared memory");
   const size_t smem = fixed + stages * stage_bytes;
-  const int64_t tiles = (M + TC_BM - 1) / TC_BM;
+  const int64_t tiles = cv.tiles_x ? (M / cv.wt) * cv.tiles_x : (M + TC_BM - 1) / TC_BM;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  auto kern = linear_tc_kernel<false, true, float, GW, 1, true>;
-  PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const ConvView cv = {0, 0, 0, 0};
-  kern<<<grid, EpiCfg<GW>::THREADS, smem, st>>>(mx, mw, mr, bias, (float*)y, M, N, K, block_n, stages, 0, cv, ln);
+  if (residual) {
+    auto kern = linear_tc_kernel<false, true, float, GW, 1, 1>;
+    PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, EpiCfg<GW>::THREADS, smem, st>>>(mx, mw, mr, bias, (float*)y, M, N, K, block_n, stages, 0, cv, ln);
+  } else {
+    auto kern = linear_tc_kernel<false, false, float, GW, 1, 2>;
+    PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, EpiCfg<GW>::THREADS, smem, st>>>(mx, mw, mr, bias, (float*)y, M, N, K, block_n, stages, 0, cv, ln);
+  }
   return launch_status("linear_tc_kernel<LNF>");
 }
 
@@ -800,7 +884,7 @@ extern "C" PSW_API int psw_linear_ln_fwd(const void* x, const void* w, const flo
               "psw_linear_ln_fwd: needs N %% 32 == 0, N <= 256 (one tile per row) and K %% 8 == 0 (N=%d K=%d)", N, K);
   PSW_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(bias) && aligned16(residual) && aligned16(ln_out),
               PSW_ERR_BAD_ARG, "psw_linear_ln_fwd: pointers must be 16-byte aligned");
-  const LnFuse ln = {ln_gamma, ln_beta, (bf16*)ln_out, ln_eps};
+  const LnFuse ln = {ln_gamma, ln_beta, (bf16*)ln_out, ln_eps, nullptr, 1};
   return launch_tc_lnf(x, w, bias, residual, y, ln, M, N, K, (cudaStream_t)stream);
 }
 
@@ -821,6 +905,29 @@ extern "C" PSW_API int psw_patch_conv_fwd(const void* x, const void* w, const fl
   PSW_REQUIRE(M < (1ll << 31) && (int64_t)B * H < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_patch_conv_fwd: too many tokens");
   const ConvArgs conv = {B * H, W, cin, patch_h, patch_w};
   return launch_tc<false, false, bf16>(x, w, bias, nullptr, out, M, cout, patch_h * patch_w * cin, (cudaStream_t)stream, &conv);
+}
+
+// Patch convolution + patch_norm LayerNorm + absolute position add in one kernel (the whole tail of the stem):
+// out fp32 [tokens, cout] = LN(conv(x) + bias) * gamma + beta + pos[token % pos_rows].
+extern "C" PSW_API int psw_patch_conv_ln_fwd(const void* x, const void* w, const float* bias, const float* ln_gamma,
+                                             const float* ln_beta, float ln_eps, const float* pos, int64_t pos_rows, void* out,
+                                             int B, int H, int W, int cin, int cout, int patch_h, int patch_w, void* stream) {
+  PSW_REQUIRE(x && w && out && ln_gamma && ln_beta, PSW_ERR_BAD_ARG, "psw_patch_conv_ln_fwd: null pointer");
+  PSW_REQUIRE(B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0 && patch_h > 0 && patch_w > 0, PSW_ERR_BAD_ARG,
+              "psw_patch_conv_ln_fwd: bad dims");
+  PSW_REQUIRE(H % patch_h == 0 && W % patch_w == 0, PSW_ERR_BAD_ARG,
+              "psw_patch_conv_ln_fwd: H=%d W=%d must be multiples of the patch %dx%d (pad the image first)", H, W, patch_h, patch_w);
+  PSW_REQUIRE((patch_w * cin) % TC_BK == 0 && cout % 32 == 0 && cout <= 256, PSW_ERR_UNSUPPORTED,
+              "psw_patch_conv_ln_fwd: needs patch_w * cin %% 64 == 0, cout %% 32 == 0, cout <= 256 (cin=%d patch_w=%d cout=%d)", cin,
+              patch_w, cout);
+  PSW_REQUIRE(pos == nullptr || (pos_rows > 0 && pos_rows < (1ll << 31)), PSW_ERR_BAD_ARG, "psw_patch_conv_ln_fwd: pos given but bad pos_rows");
+  PSW_REQUIRE(aligned16(x) && aligned16(w) && aligned16(out) && aligned16(bias) && aligned16(pos), PSW_ERR_BAD_ARG,
+              "psw_patch_conv_ln_fwd: pointers must be 16-byte aligned");
+  const int64_t M = (int64_t)B * (H / patch_h) * (W / patch_w);
+  PSW_REQUIRE(M < (1ll << 31) && (int64_t)B * H < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_patch_conv_ln_fwd: too many tokens");
+  const ConvArgs conv = {B * H, W, cin, patch_h, patch_w};
+  const LnFuse ln = {ln_gamma, ln_beta, nullptr, ln_eps, pos, pos ? (int)pos_rows : 1};
+  return launch_tc_lnf(x, w, bias, nullptr, out, ln, M, cout, patch_h * patch_w * cin, (cudaStream_t)stream, &conv);
 }
 
 extern "C" PSW_API int psw_debug_linear_cycles(long long* host_out16) {

@@ -309,6 +309,23 @@ def patch_conv(x_nhwc, w_ohwi, bias, patch):
     return out
 
 
+def patch_conv_layernorm(x_nhwc, w_ohwi, bias, patch, ln_gamma, ln_beta, ln_eps, pos=None):
+    """patch_conv + LayerNorm + position add in one kernel: fp32 tokens [B, H/ph * W/pw, cout] (the stem's tail)."""
+    dev = _chk(x_nhwc, w_ohwi, bias, ln_gamma, ln_beta, pos)
+    B, H, W, cin = x_nhwc.shape
+    ph, pw = patch
+    cout = w_ohwi.shape[0]
+    if x_nhwc.dtype != torch.bfloat16 or w_ohwi.dtype != torch.bfloat16 or tuple(w_ohwi.shape) != (cout, ph, pw, cin):
+        raise PanoSwinB200Error("patch_conv_layernorm wants bf16 NHWC x and bf16 w [cout, ph, pw, cin]")
+    out = torch.empty((B, (H // ph) * (W // pw), cout), dtype=torch.float32, device=x_nhwc.device)
+    pos_rows = 0 if pos is None else pos.numel() // cout
+    with torch.cuda.device(dev):
+        _call("psw_patch_conv_ln_fwd", _ptr(x_nhwc), _ptr(w_ohwi), _ptr(_f32(bias, "bias")), _ptr(_f32(ln_gamma, "ln_gamma")),
+              _ptr(_f32(ln_beta, "ln_beta")), float(ln_eps), _ptr(_f32(pos, "pos")), pos_rows, _ptr(out), B, H, W, cin, cout, ph, pw,
+              _stream(dev))
+    return out
+
+
 def cast(x, dtype):
     dev = _chk(x)
     out = torch.empty(x.shape, dtype=dtype, device=x.device)

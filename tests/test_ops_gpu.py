@@ -350,3 +350,26 @@ def test_linear_layernorm_fused(ops, mnk, alias):
     assert (y.data_ptr() == rd.data_ptr()) == alias
     assert rel_l2(y, want_y) <= 2e-5
     assert rel_l2(ln.float(), want_ln) <= 4e-3
+
+
+@pytest.mark.parametrize("B,H,W,cout", [(2, 16, 512, 96), (1, 8, 1024, 96), (3, 12, 100, 96), (1, 4, 2048, 128)])
+@pytest.mark.parametrize("with_pos", [True, False])
+def test_patch_conv_layernorm_fused(ops, B, H, W, cout, with_pos):
+    """The stem's tail in one kernel: patch conv + LayerNorm + absolute position add -> fp32 residual stream."""
+    cin, patch = 64, (4, 4)
+    g = _g(B + H + W + cout + 1)
+    x = torch.randn(B, H, W, cin, generator=g).bfloat16()
+    w = (torch.randn(cout, cin, 4, 4, generator=g) / 32.0).bfloat16()
+    b = torch.randn(cout, generator=g)
+    gam, bet = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g)
+    HW = (H // 4) * (W // 4)
+    pos = torch.randn(HW, cout, generator=g) if with_pos else None
+    y = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), b.double(), stride=patch).permute(0, 2, 3, 1).reshape(B, HW, cout)
+    want = F.layer_norm(y, (cout,), gam.double(), bet.double(), 1e-5)
+    if with_pos:
+        want = want + pos.double()[None]
+    got = ops.patch_conv_layernorm(x.to(DEV), w.permute(0, 2, 3, 1).contiguous().to(DEV), b.to(DEV), patch, gam.to(DEV),
+                                   bet.to(DEV), 1e-5, None if pos is None else pos.to(DEV))
+    torch.cuda.synchronize()
+    assert got.shape == (B, HW, cout) and got.dtype == torch.float32
+    assert rel_l2(got, want) <= 2e-5
