@@ -23,10 +23,14 @@ items = list(launch.values())
 # keep the second forward only: the last occurrence block (kernels after the last stem / first-LN launch)
 starts = [i for i, d in enumerate(items) if "stem_conv1" in d["name"]]
 items = items[starts[-1]:] if starts else items
+after_conv2 = False
 for d in items:
     cls = next((c for k, c in CLASS if k in d["name"]), None)
     if cls is None:
         continue
+    if cls == "linear" and after_conv2:          # the launch right after stem conv2 is the patch conv (same GEMM kernel)
+        cls = "patch_conv"
+    after_conv2 = cls == "stem_conv2"
     b = to_bytes(d.get("dram__bytes_read.sum", 0), d.get("unit_dram__bytes_read.sum", "byte")) + \
         to_bytes(d.get("dram__bytes_write.sum", 0), d.get("unit_dram__bytes_write.sum", "byte"))
     p = per.setdefault(cls, {"launches": 0, "dram_bytes": 0.0})
