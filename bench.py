@@ -119,6 +119,9 @@ def launch_work(fn, a):
     if fn == "psw_linear_ln_fwd":
         M, N, K = a[9], a[10], a[11]
         return dict(kind="linear", shape=f"M{M} N{N} K{K} +res +LN", bytes=float(M * K * 2 + N * K * 2 + M * N * 10), flops=2.0 * M * N * K)
+    if fn == "psw_linear_ln_nchw_fwd":
+        M, N, K = a[10], a[11], a[12]
+        return dict(kind="linear", shape=f"M{M} N{N} K{K} +res +LN->NCHW", bytes=float(M * K * 2 + N * K * 2 + M * N * 12), flops=2.0 * M * N * K)
     if fn == "psw_layernorm_fwd":
         rows, C = a[5], a[6]
         return dict(kind="layernorm", shape=f"rows{rows} C{C}", bytes=float(rows * C * (sz[a[9]] + sz[a[10]])), flops=8.0 * rows * C)

@@ -83,6 +83,11 @@ PSW_API int psw_linear_fwd(const void* x, const void* w, const float* bias, cons
 PSW_API int psw_linear_ln_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
                               const float* ln_gamma, const float* ln_beta, float ln_eps, void* ln_out,
                               int64_t M, int N, int K, void* stream);
+/* Same, for the last fc2 of a stage: LayerNorm(y) is the stage's output map, written as fp32 NCHW [M / HW, N, HW]
+ * (SimplePanoSwinTransformer.forward :974-978) straight from the epilogue (HW = tokens per image, M % HW == 0). */
+PSW_API int psw_linear_ln_nchw_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                   const float* ln_gamma, const float* ln_beta, float ln_eps, float* out_nchw,
+                                   int64_t HW, int64_t M, int N, int K, void* stream);
 
 /*
  * Fused (shifted-)window multi-head self-attention on an equirectangular token map.

@@ -19,6 +19,7 @@ SIGNATURES = {
     "psw_layernorm_fwd": [_vp, _vp, _fp, _fp, _fp, _i64, _i, _i64, _f, _i, _i, _vp],
     "psw_linear_fwd": [_vp, _vp, _fp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "psw_linear_ln_fwd": [_vp, _vp, _fp, _vp, _vp, _fp, _fp, _f, _vp, _i64, _i, _i, _vp],
+    "psw_linear_ln_nchw_fwd": [_vp, _vp, _fp, _vp, _vp, _fp, _fp, _f, _fp, _i64, _i64, _i, _i, _vp],
     "psw_window_attn_fwd": [_vp, _vp, _fp, _fp, _vp, _fp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
     "psw_window_bias_tables": [_fp, _fp, _vp, _i, _i, _vp],
     "psw_window_grid": [_i, _i, _i, _i, _vp, _vp],

@@ -551,6 +551,7 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             # LayerNorm fused into the producing GEMM's epilogue where one tile holds complete rows (C <= 256)
             fuse_ln = cd == torch.bfloat16 and rd == torch.float32 and C % 32 == 0 and C <= 256
             xn = None                                         # norm1(x) of the current block when already computed
+            stage_map = None                                  # the stage's NCHW output when the last fc2 produced it
             for j, blk in enumerate(layer.blocks):
                 a = blk.attn
                 shift = blk.shift_size
@@ -579,12 +580,18 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                 if fuse_ln and nxt is not None:               # fc2 + shortcut -> the next block's norm1
                     x, xn = ops.linear_layernorm(hid, self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), x,
                                                  self._f(nxt.norm1.weight), self._f(nxt.norm1.bias), nxt.norm1.eps, out=x)
+                elif fuse_ln and i in self.out_indices:       # last fc2 of the stage + shortcut -> the stage's output map
+                    n = getattr(self, f"norm{i}")
+                    x, stage_map = ops.linear_layernorm_nchw(hid, self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), x,
+                                                             self._f(n.weight), self._f(n.bias), n.eps, H, W, out=x)
+                    xn = None
                 else:
                     x = ops.linear(hid, self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), residual=x, out=x)
                     xn = None
             if i in self.out_indices:
                 n = getattr(self, f"norm{i}")
-                outs.append(ops.layernorm_nchw(x, self._f(n.weight), self._f(n.bias), H, W, n.eps))
+                outs.append(stage_map if stage_map is not None else
+                            ops.layernorm_nchw(x, self._f(n.weight), self._f(n.bias), H, W, n.eps))
                 if on_output is not None:
                     on_output(len(outs) - 1, outs[-1])
             if layer.downsample is not None:

@@ -160,9 +160,13 @@ struct LnFuse {
   float eps;
   const float* pos;       // LNF 2: position rows added after the LayerNorm ([pos_rows, N] fp32, row = GEMM row % pos_rows)
   int pos_rows;
+  float* out_nchw;        // LNF 3: LN(y) written transposed, fp32 [M / hw, N, hw] (the stage's output map)
+  int hw;                 // LNF 3: tokens per image
 };
 // LNF 1: y = acc + bias + residual (fp32, written) and ln.out = LN(y) (bf16).
 // LNF 2: y = LN(acc + bias) * gamma + beta + pos (fp32) only -- the stem: patch conv -> patch_norm -> + abs. position.
+// LNF 3: like LNF 1, but LN(y) goes out as the stage's fp32 NCHW feature map: lane r owns token r of the tile, so a
+//        warp-wide store of one channel covers 32 consecutive tokens = 128 contiguous bytes -- no transposition needed.
 
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -325,7 +329,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     // ------------------------------- epilogue ------------------------------------
     if constexpr (LNF != 0) {
       // one warp per TMEM lane quadrant and group (GW = 4): lane r owns row r of the tile for all three passes
-      static_assert(LNF == 0 || (sizeof(TO) == 4 && GW == 4 && CG == 1 && !GELU && RES == (LNF == 1)), "LNF: fp32 epilogue, GW = 4");
+      static_assert(LNF == 0 || (sizeof(TO) == 4 && GW == 4 && CG == 1 && !GELU && RES == (LNF != 2)), "LNF: fp32 epilogue, GW = 4");
       const int ew = warp - 2;
       const int quad = warp & 3;
       const int grp = ew / GW;
@@ -350,7 +354,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           row0 = trow * cv.wt + ((int)tile - trow * cv.tiles_x) * TILE_M + quad * 32;
           row_lim = (int64_t)(trow + 1) * cv.wt;
         }
-        if (LNF == 1 && lane == 0) {
+        if (LNF != 2 && lane == 0) {
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             if (j < n_chunks) {
@@ -377,7 +381,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             v[4 * i] = __uint_as_float(r[4 * i]) + b4.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + b4.y;
             v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + b4.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + b4.w;
           }
-          if constexpr (LNF == 1) {
+          if constexpr (LNF != 2) {
             const uint32_t b = res_used & 1;
             mbar_wait(&res_bar[b], (res_used >> 1) & 1);
 #pragma unroll
@@ -398,7 +402,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) { sum += v[i]; r[i] = __float_as_uint(v[i]); }
           tmem_st_x16(t_addr + (uint32_t)(c * 16), r);
-          if constexpr (LNF == 1) {
+          if constexpr (LNF != 2) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               *reinterpret_cast<uint4*>(my_row_out + ((q ^ sw) << 4)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
@@ -431,7 +435,24 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           for (int i = 0; i < 16; ++i) { const float d = __uint_as_float(r[i]) - mean; qs = fmaf(d, d, qs); }
         }
         const float rstd = rsqrtf(qs * inv_n + ln.eps);
-        if constexpr (LNF == 2) {
+        if constexpr (LNF == 3) {
+          // ---- pass 3 (stage output): normalise and write fp32 NCHW; one coalesced 128-byte store per channel and warp
+          const int64_t g = (int64_t)row0 + lane;              // my token
+          const bool ok = g < row_lim;
+          const int64_t bi = g / ln.hw;
+          float* op = ln.out_nchw + (bi * N) * ln.hw + (g - bi * ln.hw);
+          for (int c = 0; c < n_chunks; ++c) {
+            uint32_t r[16];
+            tmem_ld_x16(t_addr + (uint32_t)(c * 16), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int col = c * 16 + i;
+              const float o = fmaf((__uint_as_float(r[i]) - mean) * rstd, gam_s[col], bet_s[col]);
+              if (ok) op[(int64_t)col * ln.hw] = o;
+            }
+          }
+        } else if constexpr (LNF == 2) {
           // ---- pass 3 (stem): normalise, add the position row, write fp32 -- 16 columns (64 B per row) at a time.  The
           //      position rows are fetched coalesced (four lanes per row) and handed to the row owners through smem.
           for (int c = 0; c < n_chunks; ++c) {
@@ -738,7 +759,7 @@ static int launch_tc_gw(const CUtensorMap& mx, const CUtensorMap& mw, const CUte
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CG == 2 ? 1 : 0;
-  const LnFuse no_ln = {nullptr, nullptr, nullptr, 0.f, nullptr, 1};
+  const LnFuse no_ln = {nullptr, nullptr, nullptr, 0.f, nullptr, 1, nullptr, 1};
   PSW_CUDA(cudaLaunchKernelEx(&cfg, kern, mx, mw, mr, bias, (TO*)y, M, N, K, block_n, stages, g_tc_mode & 31, cv, no_ln));
   return launch_status("linear_tc_kernel");
 }
@@ -863,7 +884,11 @@ static int launch_tc_lnf(const void* x, const void* w, const float* bias, const 
   const size_t smem = fixed + stages * stage_bytes;
   const int64_t tiles = cv.tiles_x ? (M / cv.wt) * cv.tiles_x : (M + TC_BM - 1) / TC_BM;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
-  if (residual) {
+  if (residual && ln.out_nchw) {
+    auto kern = linear_tc_kernel<false, true, float, GW, 1, 3>;
+    PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, EpiCfg<GW>::THREADS, smem, st>>>(mx, mw, mr, bias, (float*)y, M, N, K, block_n, stages, 0, cv, ln);
+  } else if (residual) {
     auto kern = linear_tc_kernel<false, true, float, GW, 1, 1>;
     PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, EpiCfg<GW>::THREADS, smem, st>>>(mx, mw, mr, bias, (float*)y, M, N, K, block_n, stages, 0, cv, ln);
@@ -884,7 +909,23 @@ extern "C" PSW_API int psw_linear_ln_fwd(const void* x, const void* w, const flo
               "psw_linear_ln_fwd: needs N %% 32 == 0, N <= 256 (one tile per row) and K %% 8 == 0 (N=%d K=%d)", N, K);
   PSW_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(bias) && aligned16(residual) && aligned16(ln_out),
               PSW_ERR_BAD_ARG, "psw_linear_ln_fwd: pointers must be 16-byte aligned");
-  const LnFuse ln = {ln_gamma, ln_beta, (bf16*)ln_out, ln_eps, nullptr, 1};
+  const LnFuse ln = {ln_gamma, ln_beta, (bf16*)ln_out, ln_eps, nullptr, 1, nullptr, 1};
+  return launch_tc_lnf(x, w, bias, residual, y, ln, M, N, K, (cudaStream_t)stream);
+}
+
+// The last fc2 of a stage: y = x . w^T + bias + residual (fp32) and the stage's output map LN(y) as fp32 NCHW
+// [M / HW, N, HW] (SimplePanoSwinTransformer.forward :974-978) from the same epilogue.
+extern "C" PSW_API int psw_linear_ln_nchw_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
+                                              const float* ln_gamma, const float* ln_beta, float ln_eps, float* out_nchw,
+                                              int64_t HW, int64_t M, int N, int K, void* stream) {
+  PSW_REQUIRE(x && w && residual && y && ln_gamma && ln_beta && out_nchw, PSW_ERR_BAD_ARG, "psw_linear_ln_nchw_fwd: null pointer");
+  PSW_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && HW > 0 && HW < (1ll << 31) && M % HW == 0, PSW_ERR_BAD_ARG,
+              "psw_linear_ln_nchw_fwd: M=%lld N=%d K=%d HW=%lld (M must be a multiple of HW)", (long long)M, N, K, (long long)HW);
+  PSW_REQUIRE(N % 32 == 0 && N <= 256 && K % 8 == 0, PSW_ERR_UNSUPPORTED,
+              "psw_linear_ln_nchw_fwd: needs N %% 32 == 0, N <= 256 (one tile per row) and K %% 8 == 0 (N=%d K=%d)", N, K);
+  PSW_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(bias) && aligned16(residual), PSW_ERR_BAD_ARG,
+              "psw_linear_ln_nchw_fwd: pointers must be 16-byte aligned");
+  const LnFuse ln = {ln_gamma, ln_beta, nullptr, ln_eps, nullptr, 1, out_nchw, (int)HW};
   return launch_tc_lnf(x, w, bias, residual, y, ln, M, N, K, (cudaStream_t)stream);
 }
 
@@ -926,7 +967,7 @@ extern "C" PSW_API int psw_patch_conv_ln_fwd(const void* x, const void* w, const
   const int64_t M = (int64_t)B * (H / patch_h) * (W / patch_w);
   PSW_REQUIRE(M < (1ll << 31) && (int64_t)B * H < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_patch_conv_ln_fwd: too many tokens");
   const ConvArgs conv = {B * H, W, cin, patch_h, patch_w};
-  const LnFuse ln = {ln_gamma, ln_beta, nullptr, ln_eps, pos, pos ? (int)pos_rows : 1};
+  const LnFuse ln = {ln_gamma, ln_beta, nullptr, ln_eps, pos, pos ? (int)pos_rows : 1, nullptr, 1};
   return launch_tc_lnf(x, w, bias, nullptr, out, ln, M, cout, patch_h * patch_w * cin, (cudaStream_t)stream, &conv);
 }
 

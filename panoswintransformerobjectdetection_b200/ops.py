@@ -136,6 +136,25 @@ def linear_layernorm(x, w, bias, residual, ln_gamma, ln_beta, ln_eps, out=None):
     return out, ln_out
 
 
+def linear_layernorm_nchw(x, w, bias, residual, ln_gamma, ln_beta, ln_eps, H, W, out=None):
+    """y = x @ w^T + bias + residual (fp32 [B, H*W, N]) and LayerNorm(y) as the fp32 NCHW map [B, N, H, W] in one kernel
+    (the last fc2 of a stage + the stage's output norm; N % 32 == 0, N <= 256).  Returns (y, map)."""
+    dev = _chk(x, w, bias, residual, ln_gamma, ln_beta, out)
+    K = x.shape[-1]
+    M = x.numel() // K
+    N = w.shape[0]
+    if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or residual.dtype != torch.float32 or M % (H * W) != 0:
+        raise PanoSwinB200Error("linear_layernorm_nchw wants bf16 x / w, an fp32 residual and M = B * H * W rows")
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (N,), dtype=torch.float32, device=x.device)
+    fmap = torch.empty((M // (H * W), N, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(dev):
+        _call("psw_linear_ln_nchw_fwd", _ptr(x), _ptr(w), _ptr(_f32(bias, "bias")), _ptr(residual), _ptr(out),
+              _ptr(_f32(ln_gamma, "ln_gamma")), _ptr(_f32(ln_beta, "ln_beta")), float(ln_eps), _ptr(fmap), H * W, M, N, K,
+              _stream(dev))
+    return out, fmap
+
+
 def window_grid(H, W, window, pano_mode):
     """(windows per column, windows per row) of the map the attention runs on (host-only helper)."""
     import ctypes

@@ -373,3 +373,25 @@ def test_patch_conv_layernorm_fused(ops, B, H, W, cout, with_pos):
     torch.cuda.synchronize()
     assert got.shape == (B, HW, cout) and got.dtype == torch.float32
     assert rel_l2(got, want) <= 2e-5
+
+
+@pytest.mark.parametrize("B,H,W,N,K", [(2, 8, 16, 96, 384), (3, 5, 9, 192, 768), (1, 16, 32, 96, 96), (4, 7, 11, 256, 64)])
+def test_linear_layernorm_nchw_fused(ops, B, H, W, N, K):
+    """Last fc2 of a stage with the stage's output LayerNorm -> fp32 NCHW fused into the epilogue (token counts that are
+    not multiples of the 128-row tile, so tiles straddle images)."""
+    g = _g(B + H + W + N + K)
+    M = B * H * W
+    x = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, generator=g)
+    r = torch.randn(M, N, generator=g) * 2 - 0.7
+    gam, bet = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g)
+    want_y = F.linear(x.double(), w.double(), b.double()) + r.double()
+    want_map = F.layer_norm(want_y, (N,), gam.double(), bet.double(), 1e-5).view(B, H, W, N).permute(0, 3, 1, 2)
+    rd = r.to(DEV).view(B, H * W, N)
+    y, fmap = ops.linear_layernorm_nchw(x.to(DEV).view(B, H * W, K), w.to(DEV), b.to(DEV), rd, gam.to(DEV), bet.to(DEV), 1e-5,
+                                        H, W, out=rd)
+    torch.cuda.synchronize()
+    assert fmap.shape == (B, N, H, W) and fmap.dtype == torch.float32 and fmap.is_contiguous()
+    assert rel_l2(y.view(M, N), want_y) <= 2e-5
+    assert rel_l2(fmap, want_map) <= 2e-5
