@@ -122,6 +122,9 @@ def launch_work(fn, a):
     if fn == "psw_linear_ln_nchw_fwd":
         M, N, K = a[10], a[11], a[12]
         return dict(kind="linear", shape=f"M{M} N{N} K{K} +res +LN->NCHW", bytes=float(M * K * 2 + N * K * 2 + M * N * 12), flops=2.0 * M * N * K)
+    if fn == "psw_mlp_fused_fwd":
+        M, C, Hd = a[6], a[7], a[8]
+        return dict(kind="mlp_fused", shape=f"M{M} C{C} hidden{Hd}", bytes=float(M * C * 10 + 4 * C * Hd), flops=4.0 * M * C * Hd)
     if fn == "psw_layernorm_fwd":
         rows, C = a[5], a[6]
         return dict(kind="layernorm", shape=f"rows{rows} C{C}", bytes=float(rows * C * (sz[a[9]] + sz[a[10]])), flops=8.0 * rows * C)

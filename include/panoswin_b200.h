@@ -140,6 +140,17 @@ PSW_API int psw_window_bias_tables(const float* alpha, const float* beta, void* 
 PSW_API int psw_window_hav_table(const float* uv, void* table, int H, int W, int window, int shift, void* stream);
 
 /*
+ * The whole MLP of a block in one kernel (Mlp.forward + shortcut, reference :44-61, :534):
+ * x <- x + fc2(GELU(fc1(xn))), xn [M, C] bf16 (= norm2(x)), x [M, C] fp32 updated in place; w1 [hidden, C], w2 [C, hidden]
+ * bf16, b1 [hidden], b2 [C] fp32 (or NULL).  The hidden activation never leaves the SM: both weight matrices stay in
+ * shared memory, fc1 chunks accumulate in tensor memory, GELU writes bf16 back to tensor memory, fc2 consumes it from
+ * there.  Instantiated for C = 96, hidden = 384 (stage 0 of the embed_dim-96 models); other widths return
+ * PSW_ERR_UNSUPPORTED and the caller uses two psw_linear_fwd calls.
+ */
+PSW_API int psw_mlp_fused_fwd(const void* xn, const void* w1, const float* b1, const void* w2, const float* b2,
+                              void* x, int64_t M, int C, int hidden, void* stream);
+
+/*
  * Production bf16 path.  psw_window_bias_full() evaluates EVERY additive term of the attention logits of one block at
  * one resolution — hav(uv_i, uv_j) * alpha[idx] + beta[idx] (_sphere_bias, reference :241-272, fp32 math) and, in planar
  * mode, the shifted-window mask (:621-643; mask may be NULL) — for every window of ONE image and every head:
@@ -231,6 +242,8 @@ PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, const float*
  * bit3 skip the proxy fence, bit4 cycle counters;
  * bits [8,12) cap the pipeline stage count, bits [16,25) force the tile width. */
 PSW_API int psw_debug_linear_mode(int mode);
+/* Same for the fused MLP kernel: bit1 skips the final epilogue (results are garbage). */
+PSW_API int psw_debug_mlp_mode(int mode);
 /* With mode bit 4 set, CTA 0 of the last bf16 GEMM launch accumulated SM-cycle totals; copies them to the HOST
  * array host_out16[16] (synchronises): {producer wait-empty, mma wait-tempty, mma wait-full, mma issue, epilogue
  * wait-tfull, tmem-ld, math+stage, store-issue, tiles}. */

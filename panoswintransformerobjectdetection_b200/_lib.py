@@ -20,6 +20,7 @@ SIGNATURES = {
     "psw_linear_fwd": [_vp, _vp, _fp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "psw_linear_ln_fwd": [_vp, _vp, _fp, _vp, _vp, _fp, _fp, _f, _vp, _i64, _i, _i, _vp],
     "psw_linear_ln_nchw_fwd": [_vp, _vp, _fp, _vp, _vp, _fp, _fp, _f, _fp, _i64, _i64, _i, _i, _vp],
+    "psw_mlp_fused_fwd": [_vp, _vp, _fp, _vp, _fp, _vp, _i64, _i, _i, _vp],
     "psw_window_attn_fwd": [_vp, _vp, _fp, _fp, _vp, _fp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
     "psw_window_bias_tables": [_fp, _fp, _vp, _i, _i, _vp],
     "psw_window_grid": [_i, _i, _i, _i, _vp, _vp],
@@ -36,6 +37,7 @@ SIGNATURES = {
     "psw_cast": [_vp, _vp, _i64, _i, _i, _vp],
     "psw_window_attn_fwd_profile": [_vp, _vp, _fp, _fp, _vp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp],
     "psw_debug_linear_mode": [_i],
+    "psw_debug_mlp_mode": [_i],
     "psw_debug_linear_cycles": [_vp],
     "psw_debug_source_map": [_i, _i, _i, _i, _i, _vp, _i, _vp, _vp],
     "psw_window_attn_fwd_simt_bf16": [_vp, _vp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],

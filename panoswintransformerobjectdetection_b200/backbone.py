@@ -575,8 +575,14 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                 else:
                     x = ops.linear(att.view(B, H * W, C), self._w(a.proj.weight, cd), self._f(a.proj.bias), residual=x, out=x)
                     xn2 = ops.layernorm(x, self._f(blk.norm2.weight), self._f(blk.norm2.bias), blk.norm2.eps, cd)
-                hid = ops.linear(xn2, self._w(blk.mlp.fc1.weight, cd), self._f(blk.mlp.fc1.bias), gelu=True)
                 nxt = layer.blocks[j + 1] if j + 1 < len(layer.blocks) else None
+                if fuse_ln and C == 96 and blk.mlp.fc1.out_features == 384:
+                    # fc1 + GELU + fc2 + shortcut in one kernel: the 4C hidden activation never leaves the SM
+                    x = ops.mlp_fused(xn2, self._w(blk.mlp.fc1.weight, cd), self._f(blk.mlp.fc1.bias),
+                                      self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), x)
+                    xn = None
+                    continue
+                hid = ops.linear(xn2, self._w(blk.mlp.fc1.weight, cd), self._f(blk.mlp.fc1.bias), gelu=True)
                 if fuse_ln and nxt is not None:               # fc2 + shortcut -> the next block's norm1
                     x, xn = ops.linear_layernorm(hid, self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), x,
                                                  self._f(nxt.norm1.weight), self._f(nxt.norm1.bias), nxt.norm1.eps, out=x)

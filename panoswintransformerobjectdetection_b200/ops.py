@@ -155,6 +155,22 @@ def linear_layernorm_nchw(x, w, bias, residual, ln_gamma, ln_beta, ln_eps, H, W,
     return out, fmap
 
 
+def mlp_fused(xn, w1, b1, w2, b2, x):
+    """x <- x + fc2(GELU(fc1(xn))) in one kernel; xn bf16 [..., C], x fp32 [..., C] updated in place (C = 96, hidden = 384)."""
+    dev = _chk(xn, w1, b1, w2, b2, x)
+    C = xn.shape[-1]
+    M = xn.numel() // C
+    hidden = w1.shape[0]
+    if xn.dtype != torch.bfloat16 or w1.dtype != torch.bfloat16 or w2.dtype != torch.bfloat16 or x.dtype != torch.float32:
+        raise PanoSwinB200Error("mlp_fused wants bf16 xn / w1 / w2 and an fp32 x")
+    if tuple(w1.shape) != (hidden, C) or tuple(w2.shape) != (C, hidden) or x.numel() != M * C:
+        raise PanoSwinB200Error("mlp_fused: shape mismatch")
+    with torch.cuda.device(dev):
+        _call("psw_mlp_fused_fwd", _ptr(xn), _ptr(w1), _ptr(_f32(b1, "b1")), _ptr(w2), _ptr(_f32(b2, "b2")), _ptr(x), M, C, hidden,
+              _stream(dev))
+    return x
+
+
 def window_grid(H, W, window, pano_mode):
     """(windows per column, windows per row) of the map the attention runs on (host-only helper)."""
     import ctypes

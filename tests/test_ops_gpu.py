@@ -395,3 +395,22 @@ def test_linear_layernorm_nchw_fused(ops, B, H, W, N, K):
     assert fmap.shape == (B, N, H, W) and fmap.dtype == torch.float32 and fmap.is_contiguous()
     assert rel_l2(y.view(M, N), want_y) <= 2e-5
     assert rel_l2(fmap, want_map) <= 2e-5
+
+
+@pytest.mark.parametrize("M", [128, 300, 4096, 20000, 148 * 128 * 3 + 77])
+def test_mlp_fused(ops, M):
+    """fc1 + GELU + fc2 + shortcut in one kernel (C = 96, hidden = 384) against fp64 with the bf16-rounded hidden."""
+    g = _g(M)
+    C, Hd = 96, 384
+    xn = torch.randn(M, C, generator=g).bfloat16()
+    w1 = (torch.randn(Hd, C, generator=g) / C ** 0.5).bfloat16()
+    w2 = (torch.randn(C, Hd, generator=g) / Hd ** 0.5).bfloat16()
+    b1, b2 = torch.randn(Hd, generator=g) * 0.5, torch.randn(C, generator=g) * 0.5
+    x = torch.randn(M, C, generator=g) * 2
+    hid = F.gelu(F.linear(xn.double(), w1.double(), b1.double()))
+    want = x.double() + F.linear(hid, w2.double(), b2.double())
+    got = ops.mlp_fused(xn.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), x.to(DEV).clone())
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all()
+    assert rel_l2(got, want) <= 3e-3                          # the hidden activation is rounded to bf16 once
+    assert rel_l2(got - x.to(DEV), want - x.double()) <= 6e-3

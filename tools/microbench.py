@@ -343,3 +343,31 @@ def linear_lnf(iters=20):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "lnf":
     linear_lnf()
+
+
+def mlp(iters=20):
+    """Fused MLP kernel (C = 96, hidden = 384) vs fc1(+GELU) and fc2(+residual) as two GEMMs."""
+    M, C, Hd = 32768 * B, 96, 384
+    nb = 2
+    xn = [torch.randn(M, C, device=DEV).bfloat16() for _ in range(nb)]
+    x = [torch.randn(M, C, device=DEV) for _ in range(nb)]
+    hid = torch.empty(M, Hd, device=DEV, dtype=torch.bfloat16)
+    w1 = (torch.randn(Hd, C, device=DEV) / C ** 0.5).bfloat16()
+    w2 = (torch.randn(C, Hd, device=DEV) / Hd ** 0.5).bfloat16()
+    b1, b2 = torch.randn(Hd, device=DEV), torch.randn(C, device=DEV)
+    us1 = time_op(lambda i: ops.linear(xn[i], w1, b1, gelu=True, out=hid), nb, iters)
+    us2 = time_op(lambda i: ops.linear(hid, w2, b2, residual=x[i], out=x[i], out_dtype=torch.float32), nb, iters)
+    us3 = time_op(lambda i: ops.mlp_fused(xn[i], w1, b1, w2, b2, x[i]), nb, iters)
+    byt = M * C * (2 + 4 + 4)
+    print(f"MLP M{M}: fc1 {us1:.1f} us + fc2 {us2:.1f} us = {us1 + us2:.1f}   fused {us3:.1f} us  {byt / us3 / 1e3:.0f} GB/s", flush=True)
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    for mode, name in ((2, "no-final-epilogue"),):
+        lib.psw_debug_mlp_mode(mode)
+        us = time_op(lambda i: ops.mlp_fused(xn[i], w1, b1, w2, b2, x[i]), nb, iters)
+        lib.psw_debug_mlp_mode(0)
+        print(f"   fused {name}: {us:.1f} us", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "mlp":
+    mlp()
