@@ -7,7 +7,7 @@ import json
 import re
 import sys
 
-CLASS = [("window_attn_", "window_attn"), ("stem_conv2", "stem_conv2"), ("linear_tc", "linear"), ("layernorm_nchw", "layernorm_nchw"),
+CLASS = [("window_attn_", "window_attn"), ("stem_conv2", "stem_conv2"), ("mlp_fused", "mlp_fused"), ("linear_tc", "linear"), ("layernorm_nchw", "layernorm_nchw"),
          ("MergeRows", "patch_merge_ln"), ("layernorm_rows", "layernorm"), ("stem_conv1", "stem_conv1")]
 lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
