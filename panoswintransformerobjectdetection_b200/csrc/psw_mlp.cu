@@ -211,24 +211,25 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_consta
       tc_fence_after();
       const int row0 = t * ML_BM + quad * 32;
       float* gx = x + (int64_t)(row0 + t_row) * ML_C + part * 32 + t_piece * 4;
+      // read my 32 D columns first and hand the accumulator back at once: the MMA warp may then start fc2 of the
+      // next tile while this tile's rows are still being added to the residual and stored
+      uint32_t rd[2][16];
+      tmem_ld_x16(tmem + lane_base + ML_COL_D + (uint32_t)(part * 32), rd[0]);
+      tmem_ld_x16(tmem + lane_base + ML_COL_D + (uint32_t)(part * 32 + 16), rd[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tail->d_free);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col = part * 32 + c * 16;
-        uint32_t r[16];
-        tmem_ld_x16(tmem + lane_base + ML_COL_D + (uint32_t)col, r);
+        const uint32_t (&r)[16] = rd[c];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {                      // hand the residual rows to their owners through smem
           const int rr = t_row + 8 * jj;
           *reinterpret_cast<uint4*>(stg + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4)) = resid[4 * c + jj];
         }
-        tmem_ld_wait();
-        if (c == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tail->d_free);
-        } else {
-          __syncwarp();
-        }
+        __syncwarp();
         uint32_t o[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
