@@ -128,6 +128,9 @@ def launch_work(fn, a):
     if fn == "psw_layernorm_fwd":
         rows, C = a[5], a[6]
         return dict(kind="layernorm", shape=f"rows{rows} C{C}", bytes=float(rows * C * (sz[a[9]] + sz[a[10]])), flops=8.0 * rows * C)
+    if fn == "psw_layernorm2_fwd":
+        rows, C = a[8], a[9]
+        return dict(kind="layernorm", shape=f"rows{rows} C{C} x2", bytes=float(rows * C * (sz[a[13]] + 4 + 2)), flops=16.0 * rows * C)
     if fn == "psw_patch_merge_ln_fwd":
         B, H, W, C = a[4], a[5], a[6], a[7]
         rows = B * ((H + 1) // 2) * ((W + 1) // 2)

@@ -63,6 +63,15 @@ PSW_API int psw_layernorm_fwd(const void* x, void* y, const float* gamma, const 
                       int64_t rows, int C, int64_t pos_rows, float eps, int in_dtype, int out_dtype, void* stream);
 
 /*
+ * Two LayerNorms in one pass over the row: y = LN(x) * gamma + beta (+ pos), fp32, and y2 = LN(y) * gamma2 + beta2, bf16.
+ * In the backbone: the stem's patch_norm + absolute position add (the residual stream) followed by the first block's
+ * norm1 (reference :768-771, :925-936, :506).  x may be fp32 or bf16.
+ */
+PSW_API int psw_layernorm2_fwd(const void* x, float* y, const float* gamma, const float* beta, const float* pos,
+                               void* y2, const float* gamma2, const float* beta2, int64_t rows, int C,
+                               int64_t pos_rows, float eps, float eps2, int in_dtype, void* stream);
+
+/*
  * y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]) (+ residual[M,N]).
  * Replaces nn.Linear of attn.qkv (:287), attn.proj (:309) with the block's first residual add (:533),
  * Mlp fc1+GELU / fc2 (:55-61) with the second residual add (:534), and PatchMerging.reduction (:575).

@@ -17,6 +17,7 @@ SIGNATURES = {
     "psw_abi_version": [],
     "psw_check_device": [_i],
     "psw_layernorm_fwd": [_vp, _vp, _fp, _fp, _fp, _i64, _i, _i64, _f, _i, _i, _vp],
+    "psw_layernorm2_fwd": [_vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _i64, _i, _i64, _f, _f, _i, _vp],
     "psw_linear_fwd": [_vp, _vp, _fp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp],
     "psw_linear_ln_fwd": [_vp, _vp, _fp, _vp, _vp, _fp, _fp, _f, _vp, _i64, _i, _i, _vp],
     "psw_linear_ln_nchw_fwd": [_vp, _vp, _fp, _vp, _vp, _fp, _fp, _f, _fp, _i64, _i64, _i, _i, _vp],

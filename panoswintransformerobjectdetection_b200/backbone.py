@@ -533,8 +533,14 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         else:                                                     # [B, Hs, Ws, E] in the compute dtype
             B, Hs, Ws, E = tok.shape
         pos = self._abs_position(Hs, Ws, dev) if (self.pano_mode and self.ape and tok is not None) else None
+        xn_first = None                                       # norm1 of the very first block when the stem LN produces it
         if tok is None:
             pass
+        elif self.patch_embed.norm is not None and cd == torch.bfloat16 and rd == torch.float32 and len(self.layers[0].blocks) > 0:
+            # patch_norm (+ position add) and the first block's norm1 in one pass over the rows
+            n, n1 = self.patch_embed.norm, self.layers[0].blocks[0].norm1
+            x, xn_first = ops.layernorm2(tok.view(B, Hs * Ws, E), self._f(n.weight), self._f(n.bias), n.eps, pos,
+                                         self._f(n1.weight), self._f(n1.bias), n1.eps)
         elif self.patch_embed.norm is not None:
             n = self.patch_embed.norm
             x = ops.layernorm(tok.view(B, Hs * Ws, E), self._f(n.weight), self._f(n.bias), n.eps, rd, pos)
@@ -550,7 +556,7 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             uv = self._const(("uv", H, W), lambda: make_uv_hw2(H, W), dev) if self.pano_mode else None
             # LayerNorm fused into the producing GEMM's epilogue where one tile holds complete rows (C <= 256)
             fuse_ln = cd == torch.bfloat16 and rd == torch.float32 and C % 32 == 0 and C <= 256
-            xn = None                                         # norm1(x) of the current block when already computed
+            xn = xn_first if i == 0 else None                 # norm1(x) of the current block when already computed
             stage_map = None                                  # the stage's NCHW output when the last fc2 produced it
             for j, blk in enumerate(layer.blocks):
                 a = blk.attn

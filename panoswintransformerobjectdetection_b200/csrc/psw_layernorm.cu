@@ -51,6 +51,15 @@ struct MergeRows {
   }
 };
 
+// Optional second LayerNorm of the rows just produced (psw_layernorm2_fwd): y2 = LN(y) * gamma2 + beta2 in bf16 while the
+// row is still in registers -- the stem's patch_norm (+ position add) followed by the first block's norm1.
+struct SecondNorm {
+  bf16* y2;
+  const float* gamma2;
+  const float* beta2;
+  float eps2;
+};
+
 // LPR lanes cooperate on one row (LPR = 8, 16 or 32), each lane owns VPL 4-element vectors at vector indices
 // lane + LPR * k, so a group reads LPR * 16 B contiguous per request and every lane of the warp is busy even for
 // C = 96 (24 vectors: 8 lanes x 3).  A warp works on (32 / LPR) * U rows per iteration; all loads are issued before
@@ -59,7 +68,7 @@ template <int LPR, int VPL, int U, typename TI, typename TO, typename Rows>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_rows_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ pos, int64_t pos_rows,
-                      Rows rows, int Cout, float eps) {
+                      Rows rows, int Cout, float eps, const SecondNorm sn) {
   constexpr int GROUPS = 32 / LPR;                 // rows per warp pass
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -137,6 +146,53 @@ layernorm_rows_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float*
               for (int e = 0; e < 4; ++e) o[e] += pp[e];
             }
             store4(y + r * Cout + (int64_t)vec * 4, o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[u][k][e] = o[e];   // kept for the optional second norm
+          }
+        }
+      }
+    }
+    if (sn.y2 != nullptr) {                                  // second LayerNorm on the values just written (two-pass again)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k)
+          if (sub + LPR * k < nvec) s += (v[u][k][0] + v[u][k][1]) + (v[u][k][2] + v[u][k][3]);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        mean[u] = s * inv_c;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          if (sub + LPR * k < nvec) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float d = v[u][k][e] - mean[u];
+              q += d * d;
+            }
+          }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        rstd[u] = rsqrtf(q * inv_c + sn.eps2);
+      }
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int vec = sub + LPR * k;
+        if (vec < nvec) {
+          float g[4], b[4];
+          load4(sn.gamma2 + vec * 4, g);
+          load4(sn.beta2 + vec * 4, b);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int64_t r = r0 + u * GROUPS + grp;
+            if (r < nrows) {
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = (v[u][k][e] - mean[u]) * rstd[u] * g[e] + b[e];
+              store4(sn.y2 + r * Cout + (int64_t)vec * 4, o);
+            }
           }
         }
       }
@@ -146,7 +202,7 @@ layernorm_rows_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float*
 
 template <typename TI, typename TO, typename Rows>
 static int launch_ln(const TI* x, TO* y, const float* gamma, const float* beta, const float* pos, int64_t pos_rows,
-                     Rows rows, int64_t nrows, int Cout, float eps, cudaStream_t st) {
+                     Rows rows, int64_t nrows, int Cout, float eps, cudaStream_t st, SecondNorm sn = {nullptr, nullptr, nullptr, 0.f}) {
   const int nvec = Cout / 4;
   // lanes per row: the smallest of 8 / 16 / 32 that keeps at most 4 vectors per lane; wider rows use 32 lanes
   int lpr = 8;
@@ -164,7 +220,7 @@ static int launch_ln(const TI* x, TO* y, const float* gamma, const float* beta, 
   if (blocks < 1) blocks = 1;
 #define PSW_LN_LAUNCH(L, V, UU)                                                                                    \
   layernorm_rows_kernel<L, V, UU, TI, TO, Rows><<<blocks, LN_WARPS * 32, 0, st>>>(x, y, gamma, beta, pos, pos_rows, \
-                                                                                 rows, Cout, eps)
+                                                                                 rows, Cout, eps, sn)
   if (lpr == 8) {
     switch (inst) { case 1: PSW_LN_LAUNCH(8, 1, 2); break; case 2: PSW_LN_LAUNCH(8, 2, 2); break;
                     case 3: PSW_LN_LAUNCH(8, 3, 2); break; default: PSW_LN_LAUNCH(8, 4, 2); break; }
@@ -333,6 +389,26 @@ extern "C" PSW_API int psw_layernorm_fwd(const void* x, void* y, const float* ga
   PlainRows pr{rows, C};
   return dispatch_ln(x, y, gamma, beta, pos, pos_rows > 0 ? pos_rows : 1, pr, rows, C, eps, in_dtype, out_dtype,
                      (cudaStream_t)stream);
+}
+
+extern "C" PSW_API int psw_layernorm2_fwd(const void* x, float* y, const float* gamma, const float* beta, const float* pos,
+                                          void* y2, const float* gamma2, const float* beta2, int64_t rows, int C,
+                                          int64_t pos_rows, float eps, float eps2, int in_dtype, void* stream) {
+  PSW_REQUIRE(x && y && gamma && beta && y2 && gamma2 && beta2, PSW_ERR_BAD_ARG, "psw_layernorm2_fwd: null pointer");
+  PSW_REQUIRE(rows > 0 && C > 0, PSW_ERR_BAD_ARG, "psw_layernorm2_fwd: rows=%lld C=%d", (long long)rows, C);
+  PSW_REQUIRE(C % 4 == 0 && C <= 4096, PSW_ERR_UNSUPPORTED, "psw_layernorm2_fwd: C=%d must be a multiple of 4, <= 4096", C);
+  PSW_REQUIRE(aligned16(x) && aligned16(y) && aligned16(y2) && aligned16(gamma) && aligned16(beta) && aligned16(gamma2) &&
+                  aligned16(beta2) && aligned16(pos), PSW_ERR_BAD_ARG, "psw_layernorm2_fwd: pointers must be 16-byte aligned");
+  PSW_REQUIRE(pos == nullptr || pos_rows > 0, PSW_ERR_BAD_ARG, "psw_layernorm2_fwd: pos given but pos_rows <= 0");
+  PlainRows pr{rows, C};
+  const SecondNorm sn = {(bf16*)y2, gamma2, beta2, eps2};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == PSW_F32)
+    return launch_ln((const float*)x, y, gamma, beta, pos, pos_rows > 0 ? pos_rows : 1, pr, rows, C, eps, st, sn);
+  if (in_dtype == PSW_BF16)
+    return launch_ln((const bf16*)x, y, gamma, beta, pos, pos_rows > 0 ? pos_rows : 1, pr, rows, C, eps, st, sn);
+  PSW_REQUIRE(false, PSW_ERR_BAD_ARG, "psw_layernorm2_fwd: unknown dtype %d", in_dtype);
+  return PSW_ERR_BAD_ARG;
 }
 
 extern "C" PSW_API int psw_patch_merge_ln_fwd(const void* x, void* y, const float* gamma, const float* beta, int B, int H,

@@ -97,6 +97,21 @@ def layernorm(x, gamma, beta, eps=1e-5, out_dtype=None, pos=None, out=None):
     return out
 
 
+def layernorm2(x, gamma, beta, eps, pos, gamma2, beta2, eps2):
+    """y = LN(x) * gamma + beta (+ pos) in fp32 and y2 = LN(y) * gamma2 + beta2 in bf16, one pass over the rows."""
+    dev = _chk(x, gamma, beta, pos, gamma2, beta2)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    y2 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    pos_rows = 0 if pos is None else pos.numel() // C
+    with torch.cuda.device(dev):
+        _call("psw_layernorm2_fwd", _ptr(x), _ptr(y), _ptr(_f32(gamma, "gamma")), _ptr(_f32(beta, "beta")), _ptr(_f32(pos, "pos")),
+              _ptr(y2), _ptr(_f32(gamma2, "gamma2")), _ptr(_f32(beta2, "beta2")), rows, C, pos_rows, float(eps), float(eps2),
+              _dt(x), _stream(dev))
+    return y, y2
+
+
 def linear(x, w, bias=None, residual=None, gelu=False, out_dtype=None, out=None):
     """act(x @ w.T + bias) (+ residual).  x [..., K], w [N, K]; fp32 tensors run the CUDA-core parity
     kernel, bf16 tensors the tcgen05 kernel.  Reference: nn.Linear at :287, :309(+:533), :55-61(+:534), :575."""

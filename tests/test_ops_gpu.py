@@ -414,3 +414,23 @@ def test_mlp_fused(ops, M):
     assert torch.isfinite(got).all()
     assert rel_l2(got, want) <= 3e-3                          # the hidden activation is rounded to bf16 once
     assert rel_l2(got - x.to(DEV), want - x.double()) <= 6e-3
+
+
+@pytest.mark.parametrize("rows,C", [(1000, 96), (333, 192), (4096, 128), (77, 768)])
+@pytest.mark.parametrize("with_pos", [True, False])
+def test_layernorm2_dual(ops, rows, C, with_pos):
+    """Stem patch_norm (+ position add) and the first block's norm1 in one pass over the rows."""
+    g = _g(rows + C)
+    x = (torch.randn(rows, C, generator=g) * 1.7 + 0.3).bfloat16()
+    g1, b1 = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    g2, b2 = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    pos = torch.randn(rows // 3 if rows % 3 == 0 else rows, C, generator=g) if with_pos else None
+    want = F.layer_norm(x.double(), (C,), g1.double(), b1.double(), 1e-5)
+    if with_pos:
+        want = want + pos.double().repeat(rows // pos.shape[0], 1)
+    want2 = F.layer_norm(want, (C,), g2.double(), b2.double(), 1e-5)
+    y, y2 = ops.layernorm2(x.to(DEV), g1.to(DEV), b1.to(DEV), 1e-5, None if pos is None else pos.to(DEV), g2.to(DEV), b2.to(DEV), 1e-5)
+    torch.cuda.synchronize()
+    assert y.dtype == torch.float32 and y2.dtype == torch.bfloat16
+    assert rel_l2(y, want) <= 2e-6
+    assert rel_l2(y2.float(), want2) <= 4e-3
