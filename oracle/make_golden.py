@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  Usage (container with /root/reference mounted):
 
-    python -m oracle.make_golden            # writes tests/golden/<case>.npz
+    python -m oracle.make_golden            # writes tests/golden/<case>.npz and tests/golden/fpn_<case>.npz
+    python -m oracle.make_golden --fpn      # only the FPN-neck fixtures
 
 Each fixture stores the case definition (config, parameter seed, image seed/shape/kind) and the
 reference's outputs: full stage features for the small cases, a strided sample plus L2 norms for
@@ -20,6 +21,7 @@ import sys
 import numpy as np
 import torch
 
+from . import fpn_oracle as FO
 from . import panoswin_oracle as O
 from . import ref_loader as R
 
@@ -39,15 +41,43 @@ CASES = {
 }
 SAMPLE_STRIDE = 997          # prime: samples walk through every channel / row / column phase
 PARAM_SEED, IMAGE_SEED = 1, 2
+FPN_CASES = ("tiny_pano", "panoswin_t_512")                 # backbone cases whose outputs also go through the FPN neck
+FPN_SEED, FPN_OUT, FPN_LEVELS = 3, 256, 5
 
 
 def sample(t: torch.Tensor) -> np.ndarray:
     return t.reshape(-1)[::SAMPLE_STRIDE].numpy().copy()
 
 
+def fpn_golden():
+    """tests/golden/fpn_<case>.npz: the unmodified reference FPN on the unmodified reference backbone's outputs."""
+    for name in FPN_CASES:
+        cfg, shape, kind, full = CASES[name]
+        model = R.build_reference_model(cfg, O.make_state_dict(cfg, PARAM_SEED))
+        outs = R.reference_forward(model, O.make_image(shape, IMAGE_SEED, kind))
+        chans = [int(o.shape[1]) for o in outs]
+        fsd = FO.make_fpn_state(chans, FPN_OUT, FPN_SEED)
+        fpn = R.build_reference_fpn(chans, fsd, FPN_OUT, FPN_LEVELS)
+        with torch.no_grad():
+            levels = fpn(tuple(outs))
+        rec = {"meta": np.array(json.dumps(dict(case=name, in_channels=chans, out_channels=FPN_OUT, num_outs=FPN_LEVELS,
+                                               fpn_seed=FPN_SEED, full=full, stride=SAMPLE_STRIDE, n_out=len(levels),
+                                               keys=sorted(fsd.keys()))))}
+        for i, o in enumerate(levels):
+            rec[f"out{i}_shape"] = np.array(o.shape)
+            rec[f"out{i}_norm"] = np.array(float(o.double().norm()))
+            rec[f"out{i}"] = o.numpy() if full else sample(o)
+        path = os.path.join(GOLDEN_DIR, f"fpn_{name}.npz")
+        np.savez_compressed(path, **rec)
+        print(f"fpn_{name}: {len(levels)} levels {[tuple(o.shape) for o in levels]}, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if "--fpn" in sys.argv[1:]:                            # only the FPN fixtures (the others are unchanged)
+        fpn_golden()
+        return
     ref = R.load_reference()
     # --- the reference's own known answers ---------------------------------------------------
     kat = {
@@ -99,6 +129,7 @@ def main():
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **rec)
         print(f"{name}: {len(outs)} outputs, {len(blocks)} blocks, {os.path.getsize(path) / 1024:.0f} KiB")
+    fpn_golden()
 
 
 if __name__ == "__main__":

@@ -139,3 +139,57 @@ def reference_forward(model, img, return_blocks=False):
     for h in hooks:
         h.remove()
     return (outs, blocks) if return_blocks else outs
+
+
+# ----------------------------------------------------------------------------------------------
+# the FPN neck (a caller of the backbone; used only to pin oracle/fpn_oracle.py)
+# ----------------------------------------------------------------------------------------------
+_FPN = "mmdet/models/necks/fpn.py"
+
+
+class _PlainConvModule(nn.Module):
+    """mmcv.cnn.ConvModule for the only configuration FPN builds in the shipped configs: no norm, no
+    activation (conv_cfg / norm_cfg / act_cfg all None, fpn.py:120-141) -> a biased Conv2d held as `.conv`."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, conv_cfg=None, norm_cfg=None,
+                 act_cfg=None, inplace=False):
+        super().__init__()
+        assert conv_cfg is None and norm_cfg is None and act_cfg is None, "stand-in covers the plain-conv FPN only"
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, padding=padding)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+def _xavier_init(module, gain=1, bias=0, distribution="normal"):
+    (nn.init.xavier_uniform_ if distribution == "uniform" else nn.init.xavier_normal_)(module.weight, gain=gain)
+    if getattr(module, "bias", None) is not None:
+        nn.init.constant_(module.bias, bias)
+
+
+_cached_fpn = None
+
+
+def load_reference_fpn():
+    """Executes the unmodified mmdet/models/necks/fpn.py and returns its FPN class."""
+    global _cached_fpn
+    if _cached_fpn is not None:
+        return _cached_fpn
+    if not os.path.isfile(os.path.join(REFERENCE_ROOT, _FPN)):
+        raise FileNotFoundError(f"reference not mounted at {REFERENCE_ROOT}")
+    identity_decorator = lambda *a, **k: (lambda fn: fn)
+    _install("mmcv"); _install("mmcv.cnn", ConvModule=_PlainConvModule, xavier_init=_xavier_init)
+    _install("mmcv.runner", auto_fp16=identity_decorator)
+    for pkg in ("mmdet", "mmdet.models", "mmdet.models.necks"):           # parents of the relative import at fpn.py:8
+        _install(pkg).__path__ = []
+    _install("mmdet.models.builder", NECKS=_Registry("neck"))
+    _cached_fpn = _exec("mmdet.models.necks.fpn", _FPN).FPN
+    return _cached_fpn
+
+
+def build_reference_fpn(in_channels, state_dict, out_channels=256, num_outs=5):
+    fpn = load_reference_fpn()(in_channels=list(in_channels), out_channels=out_channels, num_outs=num_outs)
+    fpn.init_weights()
+    fpn.load_state_dict(state_dict, strict=True)                          # pins the parameter names
+    fpn.eval()
+    return fpn

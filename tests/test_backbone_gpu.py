@@ -86,6 +86,37 @@ def test_panoswin_t_512x1024(kind):
         assert rel_l2(o, o32) <= 2e-2, i
 
 
+@pytest.mark.parametrize("name", ["tiny_pano", "panoswin_t_512"])
+def test_fpn_features_within_tolerance(name):
+    """North star: parity "on block outputs and FPN features".  The FPN neck is a caller of the boundary, so it runs
+    here as plain torch fp32 (oracle/fpn_oracle.py on the GPU, TF32 off) on OUR backbone's maps and is compared with the
+    unmodified reference backbone -> reference FPN (tests/golden/fpn_*.npz).  fp32 mode: 1e-5; bf16 mode: 2e-2 rel-L2."""
+    from oracle import fpn_oracle as FO
+    meta, _ = load_golden(name)
+    fmeta, fz = load_golden("fpn_" + name)
+    cfg = meta["cfg"]
+    sd = O.make_state_dict(cfg, meta["param_seed"])
+    img = O.make_image(meta["shape"], meta["image_seed"], meta["kind"]).to(DEV)
+    fsd = {k: v.to(DEV) for k, v in FO.make_fpn_state(fmeta["in_channels"], fmeta["out_channels"], fmeta["fpn_seed"]).items()}
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        m = _build(cfg, sd, "fp32")
+        # tiny_pano has token maps lower than one window, where the reference's own fp32 haversine is ill-conditioned (fp32_tol)
+        for mode, tol in (("fp32", 1e-5 if name == "panoswin_t_512" else 2e-4), ("bf16", 2e-2)):
+            m.set_compute_dtype(mode)
+            levels = FO.fpn_forward(fsd, m(img), fmeta["num_outs"])
+            torch.cuda.synchronize()
+            assert len(levels) == 5
+            for i, o in enumerate(levels):
+                assert list(o.shape) == list(fz[f"out{i}_shape"])
+                got = o if fmeta["full"] else o.reshape(-1)[::fmeta["stride"]]
+                err = rel_l2(got, torch.from_numpy(fz[f"out{i}"]))
+                assert err <= tol, (name, mode, i, err)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def test_batch_rows_are_independent_and_sharding_is_exact():
     """Images never interact: a batch of 4 equals the concatenation of two batches of 2,
     which is what sharding the batch across GPUs relies on."""
