@@ -552,6 +552,7 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   uint8_t* ones = bufs + 2 * AT_BUF_BYTES + 1024;                        // 1 KB of bf16 1.0: B operand of the row-sum MMA
   uint64_t* full = reinterpret_cast<uint64_t*>(tmem_slot + 2);           // [2] GATHER: q/k/v of a stage have landed
+  uint4* padrow = reinterpret_cast<uint4*>(bufs + 2 * AT_BUF_BYTES + 2048); // [2 item slots][3][4]: bf16 qkv bias of the unit's head
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -635,6 +636,9 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
         t = source_token(g, wr * WS + ri, wc * WS + ci);
       }
       src[(st.ic & 1) * 64 + tid] = t;
+    } else if (tid < 76) {                                 // the unit's head slice of the bf16 qkv bias: [q|k|v][4 x 16 B]
+      const int j = tid - 64;
+      padrow[(st.ic & 1) * 12 + j] = bias_chunk((j >> 2) * C + (st.item % heads) * 32 + (j & 3) * 8);
     }
   };
   int ld_t[2], ld_dst[4];
@@ -683,10 +687,15 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
           cp_async16(dst, grow);
           cp_async16(dst + AT_PART_BYTES, grow + C);
           cp_async16(dst + 2 * AT_PART_BYTES, grow + 2 * C);
-        } else {                                           // padding cell: q/k/v = bias
+        } else if (p.mode == 4) {                          // diagnostics: padding cells straight from the fp32 bias
           *reinterpret_cast<uint4*>(dst) = bias_chunk(bch);
           *reinterpret_cast<uint4*>(dst + AT_PART_BYTES) = bias_chunk(bch + C);
           *reinterpret_cast<uint4*>(dst + 2 * AT_PART_BYTES) = bias_chunk(bch + 2 * C);
+        } else {                                           // padding cell: q/k/v = bias (staged per unit by prep_item)
+          const uint4* pr = padrow + (st.ic & 1) * 12 + lc;
+          *reinterpret_cast<uint4*>(dst) = pr[0];
+          *reinterpret_cast<uint4*>(dst + AT_PART_BYTES) = pr[4];
+          *reinterpret_cast<uint4*>(dst + 2 * AT_PART_BYTES) = pr[8];
         }
       }
     }

@@ -290,14 +290,14 @@ def attn_hc(iters=20):
         bt = ops.window_bias_tables(alpha, beta, 7)
         bf = ops.window_bias_full(alpha, beta, make_uv_hw2(H, W).to(DEV), None, H, W, 7, 3, True)
         res = []
-        for hc in (0, 1, 2, 4, 8, 15):
+        for hc, mode in ((0, 0), (0, 4), (1, 0), (2, 0), (4, 0), (8, 0), (15, 0)):     # mode 4: padding cells from the fp32 bias (old path)
             def run(i):
                 rc = lib.psw_window_attn_fwd_profile(qkv[i].data_ptr(), out[i].data_ptr(), alpha.data_ptr(), beta.data_ptr(),
                                                      bt.data_ptr(), qb.data_ptr(), hav.data_ptr(), bf.data_ptr(), B, H, W, C, heads, 7, 3, 32 ** -0.5, None,
-                                                     hc << 8, torch.cuda.current_stream().cuda_stream)
+                                                     (hc << 8) | mode, torch.cuda.current_stream().cuda_stream)
                 _lib.check(rc, "profile")
-            us = min(time_op(run, nb, iters) for _ in range(2))
-            res.append(f"hc{hc if hc else '-auto'} {us:.1f}")
+            us = min(time_op(run, nb, iters) for _ in range(3))
+            res.append(f"hc{hc if hc else '-auto'}{'-ldgpad' if mode == 4 else ''} {us:.1f}")
         print(f"attn {H}x{W} C{C} h{heads}: " + "  ".join(res), flush=True)
 
 
