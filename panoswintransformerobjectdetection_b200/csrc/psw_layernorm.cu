@@ -64,7 +64,9 @@ struct SecondNorm {
 // lane + LPR * k, so a group reads LPR * 16 B contiguous per request and every lane of the warp is busy even for
 // C = 96 (24 vectors: 8 lanes x 3).  A warp works on (32 / LPR) * U rows per iteration; all loads are issued before
 // the reductions (memory-level parallelism), statistics are two-pass in fp32 from registers.
-template <int LPR, int VPL, int U, typename TI, typename TO, typename Rows>
+// POS: the position rows are fetched together with the input rows (before the reductions) instead of at the point of
+// use -- they come from L2, and with their latency exposed in the output loop the stem LayerNorm ran at half speed.
+template <int LPR, int VPL, int U, typename TI, typename TO, typename Rows, bool POS = false>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_rows_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ pos, int64_t pos_rows,
@@ -97,6 +99,26 @@ layernorm_rows_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float*
           if (off >= 0) load4(x + off, v[u][k]);
         }
       }
+    }
+    const float* prow[U];                                  // position row of each of my rows: one division per row, 32-bit
+#pragma unroll                                             // where it fits (a 64-bit modulo per vector cost more than the loads)
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * GROUPS + grp;
+      prow[u] = nullptr;
+      if (pos) {
+        const int64_t pr = ((r | pos_rows) >> 32) == 0 ? (int64_t)((uint32_t)r % (uint32_t)pos_rows) : r % pos_rows;
+        prow[u] = pos + pr * Cout;
+      }
+    }
+    float pp[POS ? U : 1][POS ? VPL : 1][4];
+    if constexpr (POS) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          pp[u][k][0] = pp[u][k][1] = pp[u][k][2] = pp[u][k][3] = 0.f;
+          if (sub + LPR * k < nvec && r0 + u * GROUPS + grp < nrows) load4(prow[u] + (sub + LPR * k) * 4, pp[u][k]);
+        }
     }
     float mean[U], rstd[U];
 #pragma unroll
@@ -139,11 +161,14 @@ layernorm_rows_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float*
             float o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) o[e] = (v[u][k][e] - mean[u]) * rstd[u] * g[e] + b[e];
-            if (pos) {
-              float pp[4];
-              load4(pos + (r % pos_rows) * Cout + vec * 4, pp);
+            if constexpr (POS) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] += pp[e];
+              for (int e = 0; e < 4; ++e) o[e] += pp[u][k][e];
+            } else if (pos) {
+              float pl[4];
+              load4(prow[u] + vec * 4, pl);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] += pl[e];
             }
             store4(y + r * Cout + (int64_t)vec * 4, o);
 #pragma unroll
@@ -218,9 +243,18 @@ static int launch_ln(const TI* x, TO* y, const float* gamma, const float* beta, 
   int64_t cap = (int64_t)num_sms() * 16;
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
-#define PSW_LN_LAUNCH(L, V, UU)                                                                                    \
-  layernorm_rows_kernel<L, V, UU, TI, TO, Rows><<<blocks, LN_WARPS * 32, 0, st>>>(x, y, gamma, beta, pos, pos_rows, \
-                                                                                 rows, Cout, eps, sn)
+#define PSW_LN_LAUNCH(L, V, UU)                                                                                      \
+  do {                                                                                                               \
+    if constexpr (V * UU <= 8 && sizeof(TO) == 4) {                                                                  \
+      if (pos) {                                                                                                     \
+        layernorm_rows_kernel<L, V, UU, TI, TO, Rows, true><<<blocks, LN_WARPS * 32, 0, st>>>(x, y, gamma, beta, pos, \
+                                                                                             pos_rows, rows, Cout, eps, sn); \
+        break;                                                                                                       \
+      }                                                                                                              \
+    }                                                                                                                \
+    layernorm_rows_kernel<L, V, UU, TI, TO, Rows><<<blocks, LN_WARPS * 32, 0, st>>>(x, y, gamma, beta, pos, pos_rows, \
+                                                                                   rows, Cout, eps, sn);            \
+  } while (0)
   if (lpr == 8) {
     switch (inst) { case 1: PSW_LN_LAUNCH(8, 1, 2); break; case 2: PSW_LN_LAUNCH(8, 2, 2); break;
                     case 3: PSW_LN_LAUNCH(8, 3, 2); break; default: PSW_LN_LAUNCH(8, 4, 2); break; }

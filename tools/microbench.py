@@ -371,3 +371,22 @@ def mlp(iters=20):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "mlp":
     mlp()
+
+
+def ln_stem(iters=20):
+    """Stem LayerNorm (bf16 tokens -> fp32 residual stream, + position rows) alone and with the first norm1 fused."""
+    tok, C = 32768, 96
+    rows = tok * B
+    nb = 3
+    x = [torch.randn(rows, C, device=DEV).bfloat16() for _ in range(nb)]
+    g, bb = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    pos = torch.randn(tok, C, device=DEV)
+    for pp, name in ((None, "no pos"), (pos, "+pos")):
+        us = time_op(lambda i: ops.layernorm(x[i], g, bb, 1e-5, torch.float32, pp), nb, iters)
+        print(f"stem layernorm {name}: {us:8.1f} us  {rows * C * 6 / us / 1e3:7.0f} GB/s", flush=True)
+        us = time_op(lambda i: ops.layernorm2(x[i], g, bb, 1e-5, pp, g, bb, 1e-5), nb, iters)
+        print(f"stem layernorm x2 {name}: {us:8.1f} us  {rows * C * 8 / us / 1e3:7.0f} GB/s", flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "lnstem":
+    ln_stem()
