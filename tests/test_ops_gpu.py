@@ -57,7 +57,9 @@ def test_patch_merge_layernorm(ops, shape, dt):
     assert rel_l2(got.float(), want) <= (1e-6 if dt == torch.float32 else 4e-3)
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 32, 96), (1, 13, 25, 192), (3, 5, 9, 768), (1, 2, 4, 1024)])
+@pytest.mark.parametrize("shape", [(2, 16, 32, 96), (1, 13, 25, 192), (3, 5, 9, 768), (1, 2, 4, 1024),
+                                   (2, 40, 70, 384), (2, 33, 67, 96),            # ragged tiles of the swizzled-tile kernel
+                                   (2, 7, 9, 24), (1, 6, 11, 100)])              # C % 32 != 0: the scalar-tile kernel
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_layernorm_nchw(ops, shape, dt):
     B, H, W, C = shape
