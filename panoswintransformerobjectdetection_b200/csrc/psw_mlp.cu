@@ -297,6 +297,260 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_consta
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// v2: the final epilogue has its own four warps.  In the kernel above the sixteen epilogue warps do GELU chunks AND the
+// final epilogue (+ b2 + residual -> x), one after the other: MMA/loads ~76 us + GELU ~90 us (MUFU-bound) + final epilogue
+// ~160 us (DRAM-bound) add up instead of overlapping.  Here the hidden dimension is cut into FOUR chunks of 96 columns, which
+// frees enough tensor memory for a second accumulator: H0 [0,96) H1 [96,192) P0 [192,240) P1 [256,304) D0 [320,416)
+// D1 [416,512).  fc2 of tile t accumulates into D[t & 1]; warps 14-17 (one per TMEM lane quadrant) drain it during tile
+// t + 1 -- residual rows prefetched three 16-column chunks ahead in registers (four lanes per row, coalesced), handed to
+// the row owners through a 2 KB staging tile, and written back the same way -- while warps 2-13 (three per quadrant, 32
+// columns each) keep the GELU chunks going.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int M2_CH = 96;                        // hidden columns per chunk
+constexpr int M2_NCH = ML_HID / M2_CH;           // 4
+constexpr int M2_GELU_WARPS = 12;
+constexpr int M2_THREADS = 64 + 32 * (M2_GELU_WARPS + 4);
+constexpr uint32_t M2_COL_H = 0, M2_COL_P0 = 192, M2_COL_P1 = 256, M2_COL_D = 320;
+
+struct alignas(16) M2Tail {
+  uint64_t w_full, x_full[2], x_empty[2], h_full[2], h_free[2], p_full[2], p_free[2], d_full[2], d_free[2];
+  uint32_t tmem_base;
+  float b1[ML_HID];
+  float b2[ML_C];
+};
+constexpr size_t M2_SMEM = 1024 + ML_TAIL + sizeof(M2Tail);
+
+__global__ void __launch_bounds__(M2_THREADS, 1)
+mlp_fused_v2_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__ CUtensorMap map_xb,
+                    const __grid_constant__ CUtensorMap map_w1a, const __grid_constant__ CUtensorMap map_w1b,
+                    const __grid_constant__ CUtensorMap map_w2, const float* __restrict__ b1, const float* __restrict__ b2,
+                    float* __restrict__ x, int64_t M, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  M2Tail* tail = reinterpret_cast<M2Tail*>(smem + ML_TAIL);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = (int)((M + ML_BM - 1) / ML_BM);
+
+  for (int i = threadIdx.x; i < ML_HID; i += blockDim.x) tail->b1[i] = b1 ? b1[i] : 0.f;
+  for (int i = threadIdx.x; i < ML_C; i += blockDim.x) tail->b2[i] = b2 ? b2[i] : 0.f;
+  if (threadIdx.x == 0) {
+    mbar_init(&tail->w_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tail->x_full[s], 1);
+      mbar_init(&tail->x_empty[s], 1);
+      mbar_init(&tail->h_full[s], 1);
+      mbar_init(&tail->h_free[s], M2_GELU_WARPS);
+      mbar_init(&tail->p_full[s], M2_GELU_WARPS);
+      mbar_init(&tail->p_free[s], 1);
+      mbar_init(&tail->d_full[s], 1);
+      mbar_init(&tail->d_free[s], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tail->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&tail->w_full, ML_HID * 128 + ML_HID * 64 + 6 * ML_C * 128);
+      for (int j = 0; j < 2; ++j) {
+        tma_load_2d(smem + ML_W1A + j * 192 * 128, &map_w1a, &tail->w_full, 0, j * 192);
+        tma_load_2d(smem + ML_W1B + j * 192 * 64, &map_w1b, &tail->w_full, 64, j * 192);
+      }
+      for (int j = 0; j < 6; ++j) tma_load_2d(smem + ML_W2 + j * ML_C * 128, &map_w2, &tail->w_full, j * 64, 0);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const int s = it & 1;
+        mbar_wait(&tail->x_empty[s], ((it >> 1) & 1) ^ 1);
+        uint8_t* xs = smem + ML_X + s * ML_XSTAGE;
+        mbar_expect_tx(&tail->x_full[s], ML_XSTAGE);
+        tma_load_2d(xs, &map_xa, &tail->x_full[s], 0, t * ML_BM);
+        tma_load_2d(xs + ML_BM * 128, &map_xb, &tail->x_full[s], 64, t * ML_BM);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, M2_CH, 0, 0);          // fc1 chunk and fc2 both have N = 96
+      const uint32_t sb = smem_u32(smem);
+      mbar_wait(&tail->w_full, 0);
+      tc_fence_after();
+      const int my_tiles = (int)blockIdx.x < tiles ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const uint32_t G_total = (uint32_t)M2_NCH * (uint32_t)my_tiles;
+      for (uint32_t G = 0; G <= G_total; ++G) {              // step G: fc1 of chunk G, then fc2 of chunk G - 1
+        if (G < G_total) {
+          const uint32_t ti = G >> 2, h = G & 3;
+          const int s = ti & 1, hb = G & 1;
+          if (h == 0) {
+            mbar_wait(&tail->x_full[s], (ti >> 1) & 1);
+            tc_fence_after();
+          }
+          mbar_wait(&tail->h_free[hb], ((G >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t xa = sb + ML_X + s * ML_XSTAGE, xb = xa + ML_BM * 128;
+          const uint32_t dH = tmem + M2_COL_H + (uint32_t)hb * M2_CH;
+          const uint64_t da = umma_smem_desc(xa, 16, 1024, UMMA_SWIZZLE_128B);
+          const uint64_t dwa = umma_smem_desc(sb + ML_W1A + h * M2_CH * 128, 16, 1024, UMMA_SWIZZLE_128B);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(dH, da + 2 * k, dwa + 2 * k, idesc, k != 0);
+          const uint64_t db = umma_smem_desc(xb, 16, 512, UMMA_SWIZZLE_64B);
+          const uint64_t dwb = umma_smem_desc(sb + ML_W1B + h * M2_CH * 64, 16, 512, UMMA_SWIZZLE_64B);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_ss(dH, db + 2 * k, dwb + 2 * k, idesc, 1);
+          umma_commit(&tail->h_full[hb]);
+          if (h == M2_NCH - 1) umma_commit(&tail->x_empty[s]);
+        }
+        if (G >= 1) {
+          const uint32_t Gp = G - 1, tp = Gp >> 2, hp = Gp & 3;
+          const int pb = Gp & 1, db2 = tp & 1;
+          if (hp == 0) {                                     // D[tp & 1] was last used by tile tp - 2
+            mbar_wait(&tail->d_free[db2], ((tp >> 1) & 1) ^ 1);
+            tc_fence_after();
+          }
+          mbar_wait(&tail->p_full[pb], (Gp >> 1) & 1);
+          tc_fence_after();
+          const uint32_t pcol = pb ? M2_COL_P1 : M2_COL_P0;
+          const uint32_t dD = tmem + M2_COL_D + (uint32_t)db2 * ML_C;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {                      // K = 96 of this chunk: k16 steps 6 hp .. 6 hp + 5 of W2's K-blocks
+            const uint32_t kk = 6 * hp + (uint32_t)i;
+            const uint64_t dw = umma_smem_desc(sb + ML_W2 + (kk >> 2) * (ML_C * 128), 16, 1024, UMMA_SWIZZLE_128B) +
+                                (uint64_t)(2 * (kk & 3));
+            umma_ts(dD, tmem + pcol + (uint32_t)(i * 8), dw, idesc, (hp | (uint32_t)i) != 0);
+          }
+          umma_commit(&tail->p_free[pb]);
+          if (hp == M2_NCH - 1) umma_commit(&tail->d_full[db2]);
+        }
+      }
+    }
+  } else if (warp < 2 + M2_GELU_WARPS) {
+    // ------------------------------- GELU warps ---------------------------------
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int part = ew >> 2;                                // 0..2: hidden columns [32 part, 32 part + 32) of a chunk
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint32_t G = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int h = 0; h < M2_NCH; ++h, ++G) {
+        const int hb = G & 1;
+        mbar_wait(&tail->h_full[hb], (G >> 1) & 1);
+        tc_fence_after();
+        uint32_t r0[32];
+        tmem_ld_x32(tmem + lane_base + M2_COL_H + (uint32_t)hb * M2_CH + (uint32_t)part * 32, r0);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->h_free[hb]);
+        uint32_t pk[16];
+        const float* bb = tail->b1 + h * M2_CH + part * 32;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          pk[i] = mlp_gelu_pair(__uint_as_float(r0[2 * i]) + bb[2 * i], __uint_as_float(r0[2 * i + 1]) + bb[2 * i + 1]);
+        mbar_wait(&tail->p_free[hb], ((G >> 1) & 1) ^ 1);    // fc2 two chunks ago has consumed this P buffer
+        tc_fence_after();
+        ml_tmem_st_x16(tmem + lane_base + (hb ? M2_COL_P1 : M2_COL_P0) + (uint32_t)part * 16, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->p_full[hb]);
+      }
+    }
+  } else {
+    // ------------------------------- final-epilogue warps -----------------------
+    const int quad = warp & 3;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint8_t* stg = smem + ML_STG + quad * 2048;
+    const int sw = (lane >> 1) & 3;
+    const int t_row = lane >> 2, t_piece = lane & 3;
+    uint4 resid[3][4];                                       // residual chunks in flight: [chunk % 3][row group]
+    auto load_chunk = [&](int t, int c, uint4 (&dst)[4]) {   // 16 columns of my 32 rows, four lanes per row
+      const int row0 = t * ML_BM + quad * 32;
+      const float* gx = x + (int64_t)(row0 + t_row) * ML_C + c * 16 + t_piece * 4;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        dst[jj] = make_uint4(0, 0, 0, 0);
+        if (t < tiles && row0 + t_row + 8 * jj < M) dst[jj] = ml_ldg_v4(gx + (int64_t)8 * jj * ML_C);
+      }
+    };
+    uint32_t j = 0;
+    int t = blockIdx.x;
+    if (t < tiles && !(mode & 2)) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) load_chunk(t, c, resid[c]);
+    }
+    for (; t < tiles; t += gridDim.x, ++j) {
+      const int db2 = j & 1;
+      mbar_wait(&tail->d_full[db2], (j >> 1) & 1);
+      tc_fence_after();
+      if (mode & 2) {                                        // diagnostics: no final epilogue traffic
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tail->d_free[db2]);
+        continue;
+      }
+      const int row0 = t * ML_BM + quad * 32;
+      float* gx = x + (int64_t)(row0 + t_row) * ML_C + t_piece * 4;
+      const uint32_t dD = tmem + lane_base + M2_COL_D + (uint32_t)db2 * ML_C;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        uint32_t r[16];
+        tmem_ld_x16(dD + (uint32_t)(c * 16), r);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {                      // hand the residual rows to their owners through smem
+          const int rr = t_row + 8 * jj;
+          *reinterpret_cast<uint4*>(stg + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4)) = resid[c % 3][jj];
+        }
+        // refill the slot: chunk c + 3 of this tile, or chunk c - 3 of my next tile
+        if (c < 3) load_chunk(t, c + 3, resid[c % 3]);
+        else load_chunk(t + (int)gridDim.x, c - 3, resid[c % 3]);
+        tmem_ld_wait();
+        if (c == 5) {                                        // the accumulator has been read completely
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tail->d_free[db2]);
+        } else {
+          __syncwarp();
+        }
+        uint32_t o[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 p4 = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((q ^ sw) << 4));
+          const uint32_t pw[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            o[4 * q + i] = __float_as_uint(__uint_as_float(r[4 * q + i]) + tail->b2[c * 16 + 4 * q + i] + __uint_as_float(pw[i]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw) << 4)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int rr = t_row + 8 * jj;
+          const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4));
+          if (row0 + rr < M) *reinterpret_cast<uint4*>(gx + c * 16 + (int64_t)8 * jj * ML_C) = v;
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace psw
 
 using namespace psw;
@@ -329,6 +583,12 @@ extern "C" PSW_API int psw_mlp_fused_fwd(const void* xn, const void* w1, const f
   if (rc) return rc;
   const int tiles = (int)((M + ML_BM - 1) / ML_BM);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (!(g_mlp_mode & 4)) {                                   // bit 2 (diagnostics): the first version of the kernel
+    PSW_CUDA(cudaFuncSetAttribute(mlp_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M2_SMEM));
+    mlp_fused_v2_kernel<<<grid, M2_THREADS, M2_SMEM, (cudaStream_t)stream>>>(mxa, mxb, mw1a, mw1b, mw2, b1, b2, (float*)x, M,
+                                                                            g_mlp_mode);
+    return launch_status("mlp_fused_v2_kernel");
+  }
   PSW_CUDA(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ML_SMEM));
   mlp_fused_kernel<<<grid, ML_THREADS, ML_SMEM, (cudaStream_t)stream>>>(mxa, mxb, mw1a, mw1b, mw2, b1, b2, (float*)x, M, g_mlp_mode);
   return launch_status("mlp_fused_kernel");
