@@ -15,6 +15,7 @@
 // boundaries; the final epilogue of tile t runs after the first GELU chunk of tile t+1 (its D is complete by then).  warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-17 epilogue.
 #include "psw_common.cuh"
 #include <cuda_fp16.h>
+#include <type_traits>
 
 namespace psw {
 
@@ -304,21 +305,33 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_consta
 // ~160 us (DRAM-bound) add up instead of overlapping.  Here the hidden dimension is cut into FOUR chunks of 96 columns, which
 // frees enough tensor memory for a second accumulator: H0 [0,96) H1 [96,192) P0 [192,240) P1 [256,304) D0 [320,416)
 // D1 [416,512).  fc2 of tile t accumulates into D[t & 1]; warps 14-17 (one per TMEM lane quadrant) drain it during tile
-// t + 1 -- residual rows prefetched three 16-column chunks ahead in registers (four lanes per row, coalesced), handed to
-// the row owners through a 2 KB staging tile, and written back the same way -- while warps 2-13 (three per quadrant, 32
-// columns each) keep the GELU chunks going.
+// t + 1: the accumulator row of a lane goes through a 2 KB staging tile into a four-lanes-per-row layout, where b2 and the
+// residual (prefetched three 16-column chunks ahead in registers, the tile's 48 KB pulled into L2 by the producer with
+// cp.async.bulk.prefetch.L2 when it loads the tile's xn) are added and written with coalesced 16-byte stores -- while
+// warps 2-13 (three per quadrant, 32 columns each) keep the GELU chunks going.  The MMA-issuing thread runs a fully
+// unrolled per-tile schedule with prebuilt descriptors: with run-time chunk indices its instruction stream was the
+// critical path (195 -> 139 us for the MMA / synchronisation skeleton alone).
+// Measured (M = 1 Mi rows): 270 us vs 328 us for the kernel above; 197 us without the final epilogue, 231 us without the
+// GELU arithmetic, 144 us with neither: the final-epilogue warps are bound by bytes in flight x memory latency.
 // ---------------------------------------------------------------------------------------------------------------------
+// The kernel is close to issue-bound (GELU arithmetic), so a warp that waits must not spin at full rate: back off between
+// polls (the producer and the final-epilogue warps are far from the critical path, the GELU warps are given a short nap).
+__device__ __forceinline__ void m2_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
+
 constexpr int M2_CH = 96;                        // hidden columns per chunk
 constexpr int M2_NCH = ML_HID / M2_CH;           // 4
 constexpr int M2_GELU_WARPS = 12;
-constexpr int M2_THREADS = 64 + 32 * (M2_GELU_WARPS + 4);
+constexpr int M2_F_WARPS = 4;                    // final epilogue: one per TMEM lane quadrant
+constexpr int M2_THREADS = 64 + 32 * (M2_GELU_WARPS + M2_F_WARPS);
 constexpr uint32_t M2_COL_H = 0, M2_COL_P0 = 192, M2_COL_P1 = 256, M2_COL_D = 320;
 
 struct alignas(16) M2Tail {
   uint64_t w_full, x_full[2], x_empty[2], h_full[2], h_free[2], p_full[2], p_free[2], d_full[2], d_free[2];
   uint32_t tmem_base;
-  float b1[ML_HID];
-  float b2[ML_C];
+  alignas(16) float b1[ML_HID];
+  alignas(16) float b2[ML_C];
 };
 constexpr size_t M2_SMEM = 1024 + ML_TAIL + sizeof(M2Tail);
 
@@ -345,7 +358,7 @@ mlp_fused_v2_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_con
       mbar_init(&tail->p_full[s], M2_GELU_WARPS);
       mbar_init(&tail->p_free[s], 1);
       mbar_init(&tail->d_full[s], 1);
-      mbar_init(&tail->d_free[s], 4);
+      mbar_init(&tail->d_free[s], M2_F_WARPS);
     }
     mbar_fence_init();
   }
@@ -369,66 +382,88 @@ mlp_fused_v2_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_con
       uint32_t it = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
         const int s = it & 1;
-        mbar_wait(&tail->x_empty[s], ((it >> 1) & 1) ^ 1);
+        m2_wait_backoff(&tail->x_empty[s], ((it >> 1) & 1) ^ 1, 256);
         uint8_t* xs = smem + ML_X + s * ML_XSTAGE;
         mbar_expect_tx(&tail->x_full[s], ML_XSTAGE);
         tma_load_2d(xs, &map_xa, &tail->x_full[s], 0, t * ML_BM);
         tma_load_2d(xs + ML_BM * 128, &map_xb, &tail->x_full[s], 64, t * ML_BM);
+        // the tile's residual rows (48 KB, contiguous) into L2: the final-epilogue warps fetch them a tile or two later with
+        // plain loads, three chunks ahead -- not enough bytes in flight to cover DRAM latency, plenty for L2 latency
+        const int64_t rows = M - (int64_t)t * ML_BM < ML_BM ? M - (int64_t)t * ML_BM : ML_BM;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x + (int64_t)t * ML_BM * ML_C),
+                     "r"((uint32_t)(rows * ML_C * 4)) : "memory");
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // One thread feeds the tensor core, and its instruction stream is the kernel's critical path (with run-time chunk
+      // indices -- descriptor assembly, 64-bit adds, parity arithmetic around every MMA -- the pipe sat idle 70% of the
+      // time waiting for it).  So: every descriptor is built once, the four chunk steps of a tile are unrolled with
+      // compile-time chunk indices (offsets, accumulate flags and most barrier parities become immediates).
       const uint32_t idesc = umma_idesc_bf16(128, M2_CH, 0, 0);          // fc1 chunk and fc2 both have N = 96
       const uint32_t sb = smem_u32(smem);
+      const uint64_t d_xa = umma_smem_desc(sb + ML_X, 16, 1024, UMMA_SWIZZLE_128B);
+      const uint64_t d_xb = umma_smem_desc(sb + ML_X + ML_BM * 128, 16, 512, UMMA_SWIZZLE_64B);
+      const uint64_t d_w1a = umma_smem_desc(sb + ML_W1A, 16, 1024, UMMA_SWIZZLE_128B);
+      const uint64_t d_w1b = umma_smem_desc(sb + ML_W1B, 16, 512, UMMA_SWIZZLE_64B);
+      const uint64_t d_w2 = umma_smem_desc(sb + ML_W2, 16, 1024, UMMA_SWIZZLE_128B);
       mbar_wait(&tail->w_full, 0);
       tc_fence_after();
-      const int my_tiles = (int)blockIdx.x < tiles ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-      const uint32_t G_total = (uint32_t)M2_NCH * (uint32_t)my_tiles;
-      for (uint32_t G = 0; G <= G_total; ++G) {              // step G: fc1 of chunk G, then fc2 of chunk G - 1
-        if (G < G_total) {
-          const uint32_t ti = G >> 2, h = G & 3;
-          const int s = ti & 1, hb = G & 1;
-          if (h == 0) {
-            mbar_wait(&tail->x_full[s], (ti >> 1) & 1);
-            tc_fence_after();
-          }
-          mbar_wait(&tail->h_free[hb], ((G >> 1) & 1) ^ 1);
+      const uint32_t my_tiles = (int)blockIdx.x < tiles ? (uint32_t)((tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1) : 0u;
+      // chunk h of the CTA's j-th tile is chunk G = 4 j + h of its sequence: buffer G & 1 = h & 1, parity (G >> 1) & 1 = (h >> 1) & 1
+      auto fc1 = [&](uint32_t j, auto hc) {
+        constexpr int h = decltype(hc)::value;
+        const uint32_t s = j & 1;
+        if (h == 0) {
+          mbar_wait(&tail->x_full[s], (j >> 1) & 1);
           tc_fence_after();
-          const uint32_t xa = sb + ML_X + s * ML_XSTAGE, xb = xa + ML_BM * 128;
-          const uint32_t dH = tmem + M2_COL_H + (uint32_t)hb * M2_CH;
-          const uint64_t da = umma_smem_desc(xa, 16, 1024, UMMA_SWIZZLE_128B);
-          const uint64_t dwa = umma_smem_desc(sb + ML_W1A + h * M2_CH * 128, 16, 1024, UMMA_SWIZZLE_128B);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(dH, da + 2 * k, dwa + 2 * k, idesc, k != 0);
-          const uint64_t db = umma_smem_desc(xb, 16, 512, UMMA_SWIZZLE_64B);
-          const uint64_t dwb = umma_smem_desc(sb + ML_W1B + h * M2_CH * 64, 16, 512, UMMA_SWIZZLE_64B);
-#pragma unroll
-          for (int k = 0; k < 2; ++k) umma_ss(dH, db + 2 * k, dwb + 2 * k, idesc, 1);
-          umma_commit(&tail->h_full[hb]);
-          if (h == M2_NCH - 1) umma_commit(&tail->x_empty[s]);
         }
-        if (G >= 1) {
-          const uint32_t Gp = G - 1, tp = Gp >> 2, hp = Gp & 3;
-          const int pb = Gp & 1, db2 = tp & 1;
-          if (hp == 0) {                                     // D[tp & 1] was last used by tile tp - 2
-            mbar_wait(&tail->d_free[db2], ((tp >> 1) & 1) ^ 1);
-            tc_fence_after();
-          }
-          mbar_wait(&tail->p_full[pb], (Gp >> 1) & 1);
+        mbar_wait(&tail->h_free[h & 1], ((h >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t da = d_xa + (uint64_t)(s * (ML_XSTAGE >> 4)), db = d_xb + (uint64_t)(s * (ML_XSTAGE >> 4));
+        const uint32_t dH = tmem + M2_COL_H + (uint32_t)(h & 1) * M2_CH;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(dH, da + 2 * k, d_w1a + (uint64_t)(h * (M2_CH * 128 >> 4) + 2 * k), idesc, k != 0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) umma_ss(dH, db + 2 * k, d_w1b + (uint64_t)(h * (M2_CH * 64 >> 4) + 2 * k), idesc, 1);
+        umma_commit(&tail->h_full[h & 1]);
+        if (h == M2_NCH - 1) umma_commit(&tail->x_empty[s]);
+      };
+      auto fc2 = [&](uint32_t jp, auto hc) {
+        constexpr int hp = decltype(hc)::value;
+        const uint32_t db2 = jp & 1;
+        if (hp == 0) {                                       // D[jp & 1] was last used by tile jp - 2
+          mbar_wait(&tail->d_free[db2], ((jp >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t pcol = pb ? M2_COL_P1 : M2_COL_P0;
-          const uint32_t dD = tmem + M2_COL_D + (uint32_t)db2 * ML_C;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {                      // K = 96 of this chunk: k16 steps 6 hp .. 6 hp + 5 of W2's K-blocks
-            const uint32_t kk = 6 * hp + (uint32_t)i;
-            const uint64_t dw = umma_smem_desc(sb + ML_W2 + (kk >> 2) * (ML_C * 128), 16, 1024, UMMA_SWIZZLE_128B) +
-                                (uint64_t)(2 * (kk & 3));
-            umma_ts(dD, tmem + pcol + (uint32_t)(i * 8), dw, idesc, (hp | (uint32_t)i) != 0);
-          }
-          umma_commit(&tail->p_free[pb]);
-          if (hp == M2_NCH - 1) umma_commit(&tail->d_full[db2]);
         }
+        mbar_wait(&tail->p_full[hp & 1], (hp >> 1) & 1);
+        tc_fence_after();
+        const uint32_t pA = tmem + ((hp & 1) ? M2_COL_P1 : M2_COL_P0);
+        const uint32_t dD = tmem + M2_COL_D + db2 * ML_C;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {                        // K = 96 of this chunk: k16 steps 6 hp .. 6 hp + 5 of W2's K-blocks
+          constexpr int dummy = 0; (void)dummy;
+          const int kk = 6 * hp + i;
+          umma_ts(dD, pA + (uint32_t)(i * 8), d_w2 + (uint64_t)((kk >> 2) * (ML_C * 128 >> 4) + 2 * (kk & 3)), idesc, (hp | i) != 0);
+        }
+        umma_commit(&tail->p_free[hp & 1]);
+        if (hp == M2_NCH - 1) umma_commit(&tail->d_full[db2]);
+      };
+      using C0 = std::integral_constant<int, 0>;
+      using C1 = std::integral_constant<int, 1>;
+      using C2 = std::integral_constant<int, 2>;
+      using C3 = std::integral_constant<int, 3>;
+      for (uint32_t j = 0; j < my_tiles; ++j) {              // step: fc1 of a chunk, then fc2 of the chunk before it
+        fc1(j, C0{});
+        if (j > 0) fc2(j - 1, C3{});
+        fc1(j, C1{});
+        fc2(j, C0{});
+        fc1(j, C2{});
+        fc2(j, C1{});
+        fc1(j, C3{});
+        fc2(j, C2{});
       }
+      if (my_tiles) fc2(my_tiles - 1, C3{});
     }
   } else if (warp < 2 + M2_GELU_WARPS) {
     // ------------------------------- GELU warps ---------------------------------
@@ -440,7 +475,7 @@ mlp_fused_v2_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_con
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
       for (int h = 0; h < M2_NCH; ++h, ++G) {
         const int hb = G & 1;
-        mbar_wait(&tail->h_full[hb], (G >> 1) & 1);
+        m2_wait_backoff(&tail->h_full[hb], (G >> 1) & 1, 32);
         tc_fence_after();
         uint32_t r0[32];
         tmem_ld_x32(tmem + lane_base + M2_COL_H + (uint32_t)hb * M2_CH + (uint32_t)part * 32, r0);
@@ -450,10 +485,15 @@ mlp_fused_v2_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_con
         if (lane == 0) mbar_arrive(&tail->h_free[hb]);
         uint32_t pk[16];
         const float* bb = tail->b1 + h * M2_CH + part * 32;
+        if (mode & 8) {                                      // diagnostics: no GELU arithmetic (plain bf16 rounding)
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pk[i] = mlp_gelu_pair(__uint_as_float(r0[2 * i]) + bb[2 * i], __uint_as_float(r0[2 * i + 1]) + bb[2 * i + 1]);
-        mbar_wait(&tail->p_free[hb], ((G >> 1) & 1) ^ 1);    // fc2 two chunks ago has consumed this P buffer
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            pk[i] = mlp_gelu_pair(__uint_as_float(r0[2 * i]) + bb[2 * i], __uint_as_float(r0[2 * i + 1]) + bb[2 * i + 1]);
+        }
+        m2_wait_backoff(&tail->p_free[hb], ((G >> 1) & 1) ^ 1, 32);    // fc2 two chunks ago has consumed this P buffer
         tc_fence_after();
         ml_tmem_st_x16(tmem + lane_base + (hb ? M2_COL_P1 : M2_COL_P0) + (uint32_t)part * 16, pk);
         tmem_st_wait();
@@ -464,9 +504,11 @@ mlp_fused_v2_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_con
     }
   } else {
     // ------------------------------- final-epilogue warps -----------------------
+    // (Eight such warps -- two per quadrant, the whole next tile's residual in flight -- drain faster on their own, 213 vs
+    // 231 us without the GELU arithmetic, but the 80-register cap of 704 threads costs the GELU warps more: 282 vs 270 us.)
     const int quad = warp & 3;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    uint8_t* stg = smem + ML_STG + quad * 2048;
+    uint8_t* stg = smem + ML_STG + quad * 4096;             // two 2 KB staging tiles
     const int sw = (lane >> 1) & 3;
     const int t_row = lane >> 2, t_piece = lane & 3;
     uint4 resid[3][4];                                       // residual chunks in flight: [chunk % 3][row group]
@@ -487,7 +529,7 @@ mlp_fused_v2_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_con
     }
     for (; t < tiles; t += gridDim.x, ++j) {
       const int db2 = j & 1;
-      mbar_wait(&tail->d_full[db2], (j >> 1) & 1);
+      m2_wait_backoff(&tail->d_full[db2], (j >> 1) & 1, 64);
       tc_fence_after();
       if (mode & 2) {                                        // diagnostics: no final epilogue traffic
         tc_fence_before();
@@ -498,47 +540,43 @@ mlp_fused_v2_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_con
       const int row0 = t * ML_BM + quad * 32;
       float* gx = x + (int64_t)(row0 + t_row) * ML_C + t_piece * 4;
       const uint32_t dD = tmem + lane_base + M2_COL_D + (uint32_t)db2 * ML_C;
+      // Per 16-column chunk: my accumulator row (lane = row) goes through a 2 KB staging tile into the four-lanes-per-row
+      // layout of the residual registers, where b2 and the residual are added and the 16-byte stores are coalesced.
+      // One shared-memory round trip and one __syncwarp per chunk (two staging tiles), the TMEM load one chunk ahead.
+      uint32_t ra[16], rb[16];
+      tmem_ld_x16(dD, ra);
 #pragma unroll
       for (int c = 0; c < 6; ++c) {
-        uint32_t r[16];
-        tmem_ld_x16(dD + (uint32_t)(c * 16), r);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {                      // hand the residual rows to their owners through smem
-          const int rr = t_row + 8 * jj;
-          *reinterpret_cast<uint4*>(stg + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4)) = resid[c % 3][jj];
-        }
-        // refill the slot: chunk c + 3 of this tile, or chunk c - 3 of my next tile
-        if (c < 3) load_chunk(t, c + 3, resid[c % 3]);
-        else load_chunk(t + (int)gridDim.x, c - 3, resid[c % 3]);
+        uint32_t (&r)[16] = (c & 1) ? rb : ra;
+        uint8_t* sbuf = stg + (c & 1) * 2048;
         tmem_ld_wait();
-        if (c == 5) {                                        // the accumulator has been read completely
+        if (c < 5) {
+          tmem_ld_x16(dD + (uint32_t)((c + 1) * 16), (c & 1) ? ra : rb);
+        } else {                                             // the accumulator has been read completely
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tail->d_free[db2]);
-        } else {
-          __syncwarp();
         }
-        uint32_t o[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 p4 = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((q ^ sw) << 4));
-          const uint32_t pw[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            o[4 * q + i] = __float_as_uint(__uint_as_float(r[4 * q + i]) + tail->b2[c * 16 + 4 * q + i] + __uint_as_float(pw[i]));
-        }
-        __syncwarp();
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw) << 4)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((q ^ sw) << 4)) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+        const float4 bias4 = *reinterpret_cast<const float4*>(tail->b2 + c * 16 + t_piece * 4);
         __syncwarp();
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int rr = t_row + 8 * jj;
-          const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4));
+          const uint4 d4 = *reinterpret_cast<const uint4*>(sbuf + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4));
+          const uint4 x4 = resid[c % 3][jj];
+          uint4 v;
+          v.x = __float_as_uint(__uint_as_float(d4.x) + bias4.x + __uint_as_float(x4.x));
+          v.y = __float_as_uint(__uint_as_float(d4.y) + bias4.y + __uint_as_float(x4.y));
+          v.z = __float_as_uint(__uint_as_float(d4.z) + bias4.z + __uint_as_float(x4.z));
+          v.w = __float_as_uint(__uint_as_float(d4.w) + bias4.w + __uint_as_float(x4.w));
           if (row0 + rr < M) *reinterpret_cast<uint4*>(gx + c * 16 + (int64_t)8 * jj * ML_C) = v;
         }
-        __syncwarp();
+        // refill the slot: chunk c + 3 of this tile, or chunk c - 3 of my next tile
+        if (c < 3) load_chunk(t, c + 3, resid[c % 3]);
+        else load_chunk(t + (int)gridDim.x, c - 3, resid[c % 3]);
       }
     }
   }

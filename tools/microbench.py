@@ -362,7 +362,7 @@ def mlp(iters=20):
     print(f"MLP M{M}: fc1 {us1:.1f} us + fc2 {us2:.1f} us = {us1 + us2:.1f}   fused {us3:.1f} us  {byt / us3 / 1e3:.0f} GB/s", flush=True)
     from panoswintransformerobjectdetection_b200 import _lib
     lib = _lib.load()
-    for mode, name in ((2, "no-final-epilogue"), (4, "v1 kernel"), (6, "v1 no-final-epilogue")):
+    for mode, name in ((2, "no-final-epilogue"), (8, "no-gelu-math"), (10, "no-gelu-math no-final-epilogue"), (4, "v1 kernel"), (6, "v1 no-final-epilogue")):
         lib.psw_debug_mlp_mode(mode)
         us = time_op(lambda i: ops.mlp_fused(xn[i], w1, b1, w2, b2, x[i]), nb, iters)
         lib.psw_debug_mlp_mode(0)
