@@ -251,7 +251,8 @@ PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, const float*
  * bit3 skip the proxy fence, bit4 cycle counters;
  * bits [8,12) cap the pipeline stage count, bits [16,25) force the tile width. */
 PSW_API int psw_debug_linear_mode(int mode);
-/* Same for the fused MLP kernel: bit1 skips the final epilogue (results are garbage). */
+/* Same for the fused MLP kernel: bit1 skips the final epilogue, bit3 the GELU arithmetic (results are then garbage);
+ * bit2 selects the first version of the kernel (correct results; kept as the comparison point). */
 PSW_API int psw_debug_mlp_mode(int mode);
 /* With mode bit 4 set, CTA 0 of the last bf16 GEMM launch accumulated SM-cycle totals; copies them to the HOST
  * array host_out16[16] (synchronises): {producer wait-empty, mma wait-tempty, mma wait-full, mma issue, epilogue

@@ -593,7 +593,7 @@ mlp_fused_v2_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_con
 
 using namespace psw;
 
-static int g_mlp_mode = 0;   // diagnostics (psw_debug_mlp_mode): bit1 no final epilogue
+static int g_mlp_mode = 0;   // diagnostics (psw_debug_mlp_mode): bit1 no final epilogue, bit2 first kernel version, bit3 no GELU arithmetic
 extern "C" PSW_API int psw_debug_mlp_mode(int mode) {
   const int old = g_mlp_mode;
   g_mlp_mode = mode;

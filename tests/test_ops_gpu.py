@@ -400,8 +400,21 @@ def test_linear_layernorm_nchw_fused(ops, B, H, W, N, K):
 
 
 @pytest.mark.parametrize("M", [128, 300, 4096, 20000, 148 * 128 * 3 + 77])
-def test_mlp_fused(ops, M):
-    """fc1 + GELU + fc2 + shortcut in one kernel (C = 96, hidden = 384) against fp64 with the bf16-rounded hidden."""
+@pytest.mark.parametrize("version", [2, 1])
+def test_mlp_fused(ops, M, version):
+    """fc1 + GELU + fc2 + shortcut in one kernel (C = 96, hidden = 384) against fp64 with the bf16-rounded hidden.
+    version 2 = the production kernel (dedicated final-epilogue warps), 1 = the first kernel kept behind
+    psw_debug_mlp_mode bit 2 as the comparison point."""
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    lib.psw_debug_mlp_mode(4 if version == 1 else 0)
+    try:
+        _check_mlp_fused(ops, M)
+    finally:
+        lib.psw_debug_mlp_mode(0)
+
+
+def _check_mlp_fused(ops, M):
     g = _g(M)
     C, Hd = 96, 384
     xn = torch.randn(M, C, generator=g).bfloat16()
