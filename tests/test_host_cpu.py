@@ -48,6 +48,14 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert b"null" in lib.psw_last_error_string()
     hp, wp = C.c_int(), C.c_int()
     assert lib.psw_debug_source_map(4, 8, 7, 7, 1, None, 0, C.byref(hp), C.byref(wp)) == -1   # shift >= window
+    # every entry point validates before it touches the device: null pointers, unsupported shapes
+    assert lib.psw_layernorm2_fwd(None, None, None, None, None, None, None, None, 4, 96, 0, 1e-5, 1e-5, 1, None) == -1
+    assert b"psw_layernorm2_fwd" in lib.psw_last_error_string()
+    assert lib.psw_mlp_fused_fwd(None, None, None, None, None, None, 128, 96, 384, None) == -1
+    assert b"psw_mlp_fused_fwd" in lib.psw_last_error_string()
+    fake = C.c_void_p(1 << 20)                                   # never dereferenced: the shape check comes first
+    assert lib.psw_mlp_fused_fwd(fake, fake, None, fake, None, fake, 128, 192, 768, None) == -2
+    assert b"C = 96" in lib.psw_last_error_string()
 
 
 def _source_map(lib, H, W, ws, s, pano):
