@@ -95,21 +95,20 @@ class ClockSampler:
 def launch_work(fn, a):
     sz = {0: 4, 1: 2}
     if fn == "psw_window_attn_fwd":
-        B, H, W, C = a[9], a[10], a[11], a[12]
-        heads, ws = a[13], a[14]
+        B, H, W, C, heads, ws, shift, pano = a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14]
         tok = B * H * W
-        es = sz[a[18]]
-        nwin_h = -(-(2 * H if a[16] else H) // ws)
-        nwin_w = -(-(((W + 1) // 2) if a[16] else W) // ws)
+        es = sz[a[16]]
+        nwin_h = -(-(2 * H if pano else H) // ws)
+        nwin_w = -(-(((W + 1) // 2) if pano else W) // ws)
         flops = 4.0 * (ws * ws) ** 2 * (C // heads) * B * nwin_h * nwin_w * heads
-        return dict(kind="window_attn", shape=f"B{B} {H}x{W} C{C} h{heads} s{a[15]}", bytes=4.0 * tok * C * es, flops=flops)
+        return dict(kind="window_attn_generic", shape=f"B{B} {H}x{W} C{C} h{heads} s{shift}", bytes=4.0 * tok * C * es, flops=flops)
     if fn == "psw_window_attn_full_fwd":
-        B, H, W, C, heads, ws, pano = a[5], a[6], a[7], a[8], a[9], a[10], a[12]
+        B, H, W, C, heads, ws, shift, pano = a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]
         tok = B * H * W
         nwin_h = -(-(2 * H if pano else H) // ws)
         nwin_w = -(-(((W + 1) // 2) if pano else W) // ws)
         flops = 4.0 * (ws * ws) ** 2 * (C // heads) * B * nwin_h * nwin_w * heads
-        return dict(kind="window_attn", shape=f"B{B} {H}x{W} C{C} h{heads} s{a[11]}", bytes=8.0 * tok * C, flops=flops)
+        return dict(kind="window_attn", shape=f"B{B} {H}x{W} C{C} h{heads} s{shift}", bytes=8.0 * tok * C, flops=flops)
     if fn == "psw_linear_fwd":
         M, N, K = a[5], a[6], a[7]
         es, eo = sz[a[9]], sz[a[10]]
@@ -151,11 +150,6 @@ def launch_work(fn, a):
         tok = B * (H // ph) * (W // pw)
         return dict(kind="patch_conv", shape=f"B{B} {H}x{W} {cin}->{cout} /{ph}", bytes=float(B * H * W * cin * 2 + tok * cout * 2),
                     flops=2.0 * tok * cout * ph * pw * cin)
-    if fn == "psw_patch_conv_ln_fwd":
-        B, H, W, cin, cout, ph, pw = a[9], a[10], a[11], a[12], a[13], a[14], a[15]
-        tok = B * (H // ph) * (W // pw)
-        return dict(kind="patch_conv", shape=f"B{B} {H}x{W} {cin}->{cout} /{ph} +LN+pos", bytes=float(B * H * W * cin * 2 + tok * cout * 4),
-                    flops=2.0 * tok * cout * ph * pw * cin)
     return dict(kind=fn, shape="", bytes=0.0, flops=0.0)
 
 
@@ -183,19 +177,54 @@ class Tracer:
             out[k] = dict(ms_per_step=g["ms"] / steps, launches_per_step=g["launches"] / steps, gbs=gbs, tflops=tfs,
                           bound="hbm" if hbm_bound else "tensor",
                           frac=(gbs / peaks["hbm_gbs"]) if hbm_bound else (tfs / peaks["bf16_tflops"]),
-                          shapes={sh: dict(ms=s["ms"] / s["n"], gbs=s["bytes"] / (s["ms"] * 1e-3) / 1e9,
-                                           tflops=s["flops"] / (s["ms"] * 1e-3) / 1e12) for sh, s in g["shapes"].items()})
+                          shapes={sh: self._shape_row(s, peaks, ridge) for sh, s in g["shapes"].items()})
+            # a class whose shapes sit on both sides of the ridge has no single meaningful fraction: report the
+            # time-weighted mean of the per-shape fractions (each against ITS bound) instead of a mixed aggregate
+            rows = out[k]["shapes"].values()
+            if len({r["bound"] for r in rows}) > 1:
+                tot = sum(r["ms"] * r["n"] for r in rows)
+                out[k]["bound"] = "mixed"
+                out[k]["frac"] = sum(r["frac"] * r["ms"] * r["n"] for r in rows) / max(tot, 1e-12)
         return out
+
+    @staticmethod
+    def _shape_row(s, peaks, ridge):
+        gbs = s["bytes"] / (s["ms"] * 1e-3) / 1e9
+        tfs = s["flops"] / (s["ms"] * 1e-3) / 1e12
+        hbm = (s["flops"] / max(s["bytes"], 1.0)) < ridge
+        return dict(ms=s["ms"] / s["n"], n=s["n"], gbs=gbs, tflops=tfs, bound="hbm" if hbm else "tensor",
+                    frac=(gbs / peaks["hbm_gbs"]) if hbm else (tfs / peaks["bf16_tflops"]))
 
 
 # ------------------------------------------------------------------------------------------------
-def build_model(device, residual="fp32"):
+def randomize_(model, seed=1):
+    """Random-init weights of the benchmarked model (there are no checkpoints offline): every tensor non-trivial --
+    biases, LayerNorm / BatchNorm affine and statistics, alpha / beta tables -- so that no term of the path is
+    multiplied by zero.  Product-side only: the GPU arm does not import oracle/."""
     import torch
-    from oracle import panoswin_oracle as O
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, t in list(model.named_parameters()) + list(model.named_buffers()):
+            if not t.is_floating_point() or name.endswith("np_uv"):
+                continue
+            if name.endswith("running_var"):
+                t.copy_(torch.rand(t.shape, generator=g) + 0.5)
+            elif name.endswith("running_mean") or name.endswith(".bias"):
+                t.copy_(torch.randn(t.shape, generator=g) * 0.1)
+            elif "_table_Te" in name:
+                t.copy_(torch.randn(t.shape, generator=g) * 0.5)
+            elif t.ndim == 1:                               # norm weights
+                t.copy_(1.0 + torch.randn(t.shape, generator=g) * 0.1)
+            else:                                           # linear / conv weights
+                fan_in = t[0].numel()
+                t.copy_(torch.randn(t.shape, generator=g) / fan_in ** 0.5)
+    return model
+
+
+def build_model(device, residual="fp32", cfg=None):
     import panoswintransformerobjectdetection_b200 as P
-    m = P.SimplePanoSwinTransformer(**{k: v for k, v in PANOSWIN_T.items()}, drop_path_rate=0.0)
-    cfg = O.make_config()                                   # PanoSwin-T; random-init weights (no checkpoints offline)
-    m.load_state_dict(O.make_state_dict(cfg, 1), strict=True)
+    m = P.SimplePanoSwinTransformer(**{k: v for k, v in (cfg or PANOSWIN_T).items()}, drop_path_rate=0.0)
+    randomize_(m, 1)                                        # random-init weights (no checkpoints offline)
     m.to(device)
     m.eval()
     m.set_compute_dtype("bf16")
@@ -260,7 +289,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    strong = args.scaling == "strong"
+    if strong and args.batch % world != 0:
+        raise SystemExit(f"--scaling strong needs the global batch {args.batch} to be divisible by {world} GPUs")
+    B = args.batch // world if strong else args.batch       # images per GPU per step
     model = build_model(dev, args.residual)
     g = torch.Generator().manual_seed(1234 + rank)
     host_img = torch.rand(B, 3, IMG_H, IMG_W, generator=g).pin_memory()
@@ -316,6 +348,19 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
+    # the other scaling curve as an extra key: SURVEY.md §8(d) config 2 asks for both the same GLOBAL batch sharded
+    # (strong: 32 / N images per GPU) and 32 images per GPU (weak)
+    other = None
+    if world > 1 and not args.eager and args.batch % world == 0:
+        Bo = args.batch if strong else args.batch // world
+        go = GraphedForward(model, (Bo,) + tuple(dev_img.shape[1:]), dev)
+        go.static_in.copy_(dev_img[:Bo] if Bo <= B else dev_img.repeat((Bo + B - 1) // B, 1, 1, 1)[:Bo])
+        for _ in range(max(args.warmup, 3)):
+            go.replay()
+        ms_o = timed(lambda: go.replay(), args.steps) / args.steps
+        other = {"scaling": "weak" if strong else "strong", "images_per_gpu": Bo, "global_batch": world * Bo,
+                 "value": world * Bo / (ms_o * 1e-3), "unit": UNIT, "ms_per_step": ms_o}
+        del go
     def step_device():                                      # noqa: F811  (eager again for the per-launch trace)
         keep[:] = [model(dev_img)]
 
@@ -346,17 +391,32 @@ def run_ours(args):
         return
 
     dominant = max(kern.items(), key=lambda kv: kv[1]["ms_per_step"])
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    ncu_traffic = {}
+    if os.path.isfile(tpath):                              # ncu dram__bytes_read+write per launch (tools/ncu_traffic.py)
+        with open(tpath) as fh:
+            ncu_traffic = json.load(fh)
+
     def roof(name, k):
-        hb = k["bound"] == "hbm"
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.isfile(tpath):                          # ncu dram__bytes_read+write per launch (tools/ncu_traffic.py)
-            with open(tpath) as fh:
-                traffic = (json.load(fh).get(name) or {}).get("dram_bytes_per_launch")
-        return {"kernel": name, "bound": k["bound"], "achieved": k["gbs"] if hb else k["tflops"],
-                "peak": peaks["hbm_gbs"] if hb else peaks["bf16_tflops"], "unit": "GB/s" if hb else "TFLOP/s",
-                "frac": k["frac"], "traffic": traffic, "ms_per_step": k["ms_per_step"],
-                "share_of_step": k["ms_per_step"] / ms_traced, "peak_source": peaks["source"]}
+        """Roofline object of one kernel class.  A class whose launches sit on both sides of the ridge (the GEMM:
+        HBM-bound at C = 96 / 192, tensor-bound at C >= 384) is reported through its heaviest SHAPE against that
+        shape's own bound, with every shape listed in `per_shape`; `class_frac` is the time-weighted mean."""
+        rows = sorted(k["shapes"].items(), key=lambda kv: -kv[1]["ms"] * kv[1]["n"])
+        per_shape = [{"shape": sh, "launches_per_step": r["n"] / args.steps, "ms": round(r["ms"], 4), "bound": r["bound"],
+                      "achieved": round(r["gbs"] if r["bound"] == "hbm" else r["tflops"], 1),
+                      "unit": "GB/s" if r["bound"] == "hbm" else "TFLOP/s", "frac": round(r["frac"], 4)} for sh, r in rows]
+        if k["bound"] == "mixed":
+            sh, r = rows[0]
+            hb = r["bound"] == "hbm"
+            head = {"kernel": name, "shape": sh, "bound": r["bound"], "achieved": r["gbs"] if hb else r["tflops"], "frac": r["frac"]}
+        else:
+            hb = k["bound"] == "hbm"
+            head = {"kernel": name, "bound": k["bound"], "achieved": k["gbs"] if hb else k["tflops"], "frac": k["frac"]}
+        head.update({"peak": peaks["hbm_gbs"] if hb else peaks["bf16_tflops"], "unit": "GB/s" if hb else "TFLOP/s",
+                     "traffic": (ncu_traffic.get(name) or {}).get("dram_bytes_per_launch"), "class_frac": k["frac"],
+                     "ms_per_step": k["ms_per_step"], "share_of_step": k["ms_per_step"] / ms_traced,
+                     "peak_source": peaks["source"], "per_shape": per_shape})
+        return head
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -366,7 +426,7 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"PanoSwin-T backbone inference (BASELINE.json configs[1]), batch {B}x3x{IMG_H}x{IMG_W} per GPU, "
                                f"bf16 activations / {args.residual} residual stream, random-init weights",
@@ -383,6 +443,7 @@ def run_ours(args):
         "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items() if kk != "shapes"}
                     for k, v in kern.items()},
         "ms_per_step_traced": ms_traced, "ms_our_kernels_per_step": ours_ms,
+        "other_scaling": other,
         "cpu_baseline": cpu,
     }
     if args.detail:
@@ -399,7 +460,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step (weak scaling) / global batch (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch images per GPU; strong: --batch images in total, sharded over the GPUs")
     ap.add_argument("--chunk", type=int, default=8, help="images per pipelined chunk on the end-to-end path")
     ap.add_argument("--residual", default="fp32", choices=["fp32", "bf16"], help="residual-stream storage in bf16 mode")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of a CUDA-graph replay")

@@ -12,7 +12,9 @@
  *   - returns 0 on success, a NEGATIVE psw_status on argument errors, a POSITIVE cudaError_t when the
  *     CUDA runtime refused the launch; psw_last_error_string() describes the last failure of the
  *     calling thread;
- *   - stateless and thread-safe; there is NO CPU fallback: without a B200 the launch fails loudly.
+ *   - stateless and thread-safe (kernel selection depends on the arguments only; the profiling switches of
+ *     include/panoswin_b200_debug.h exist only in a -DPSW_DIAGNOSTICS build of the library);
+ *   - there is NO CPU fallback: without a B200 the launch fails loudly.
  *   - dtype arguments: PSW_F32 selects the fp32 parity path (CUDA-core FMA, 1e-5 vs the reference),
  *     PSW_BF16 the throughput path (bf16 storage, tcgen05 tensor cores, fp32 accumulate/softmax).
  */
@@ -25,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PSW_ABI_VERSION 1
+#define PSW_ABI_VERSION 2   /* bumped with every change of a prototype below */
 
 #if defined(__GNUC__)
 #define PSW_API __attribute__((visibility("default")))
@@ -44,7 +46,9 @@ enum psw_status {
 };
 
 /* epilogue flags of psw_linear_fwd */
-#define PSW_EPI_GELU 1       /* exact erf GELU after the bias add (nn.GELU, reference :51,:57)  */
+#define PSW_EPI_GELU 1       /* GELU after the bias add (nn.GELU, reference :51,:57).  PSW_F32: exact erff.
+                              * PSW_BF16: 0.5 x (1 + tanh(x p(x^2))) with a fitted cubic p, evaluated in packed fp16;
+                              * max abs deviation from the erf GELU 5e-5, i.e. far below the bf16 output rounding */
 
 PSW_API int psw_abi_version(void);
 PSW_API const char* psw_last_error_string(void);
@@ -109,22 +113,20 @@ PSW_API int psw_linear_ln_nchw_fwd(const void* x, const void* w, const float* bi
  *   qkv      [B, H, W, 3C]  output of the qkv linear on UN-shifted tokens, channel order (3, heads, hd)
  *   out      [B, H, W, C]   attention output (before proj), un-shifted token order
  *   alpha, beta [(2*window-1)^2, heads] fp32 tables (sphere_position_{alpha,beta}_table_Te)
- *   bias_tables alpha/beta packed per head by psw_window_bias_tables() — required by the PSW_BF16 path (one
- *            contiguous 2 KB block per head, fp16 pairs); weights are static at inference, so callers cache it
- *            per block.  Ignored (may be NULL) on the PSW_F32 path, which reads alpha / beta directly
  *   qkv_bias [3C] fp32 or NULL — q/k/v of a zero (padding) token: padded cells take part as keys/values
- *   uv       [H, W, 2] fp32 token coordinates (make_uv_hw2 :153-189); used by the PSW_F32 path in pano mode
- *   hav_table fp16 great-circle distances of every window of one image, from psw_window_hav_table(); used by
- *            the PSW_BF16 path in pano mode (it depends on H, W, window, shift only, so callers cache it)
+ *   uv       [H, W, 2] fp32 token coordinates (make_uv_hw2 :153-189); required in pano mode
  *   mask     [nW, window^2, window^2] fp32 additive mask or NULL (planar mode, shifted blocks only)
  *   pano_mode 1: attention runs on the (2H, ceil(W/2)) north-south layout; 0: planar Swin roll(-s,-s)
- * PSW_BF16 requires window^2 <= 64 and C / heads == 32 (every shipped PanoSwin config).
+ *
+ * This entry is the GENERIC route: CUDA-core kernel, one CTA per (window, head), ANY window size and head_dim
+ * (shared memory permitting: window 12 x head_dim 32 fits).  dtype = PSW_F32 is the parity path (<= 1e-5 of the
+ * reference); dtype = PSW_BF16 (bf16 qkv / out, fp32 math) serves the configurations the tcgen05 kernel below is not
+ * instantiated for (psw_window_attn_full_supported() == 0), e.g. window 12 of Swin-B/384-style models.
  */
 PSW_API int psw_window_attn_fwd(const void* qkv, void* out, const float* alpha, const float* beta,
-                        const void* bias_tables, const float* qkv_bias, const float* uv, const void* hav_table,
-                        const float* mask,
-                        int B, int H, int W, int C, int heads, int window, int shift, int pano_mode,
-                        float scale, int dtype, void* stream);
+                                const float* qkv_bias, const float* uv, const float* mask,
+                                int B, int H, int W, int C, int heads, int window, int shift, int pano_mode,
+                                float scale, int dtype, void* stream);
 
 /*
  * Windows per column / row of the shifted, padded map the attention runs on (pano: ceil(2H/window) x
@@ -133,25 +135,17 @@ PSW_API int psw_window_attn_fwd(const void* qkv, void* out, const float* alpha, 
 PSW_API int psw_window_grid(int H, int W, int window, int pano_mode, int* nwh, int* nww);
 
 /*
- * Great-circle distance table for pano mode: table[win][i][j] = haversine22(uv_i, uv_j)
- * (lzx/models/great_circle.py:71-86) for the window^2 tokens of every window of ONE image, padding tokens at
- * uv = (0, 0) (reference :486-491, :344-347).  fp16, layout [nwh*nww][window^2][56] (row pitch 56 halfs).
- * Depends on (H, W, window, shift) only — not on batch, heads or weights (uv carries no gradient).
+ * Host-only: the gather map of WindowTransition.forward + pad_x as every kernel of this library evaluates it
+ * (closed form, psw::source_token): map[i * wp + j] = flat source token h*W + w of cell (i, j) of the shifted, padded
+ * map, or -1 for a zero-padding cell; *hp / *wp = padded height / width.  map may be NULL to query the size.
  */
-/*
- * (alpha, beta) [(2w-1)^2, heads] fp32 -> tables [heads][508] fp16x2 words (alpha, beta): entry (r, c) of the
- * (2w-1) x (2w-1) table at word r*39 + c, zero padded — the per-head shared-memory image of the PSW_BF16 attention
- * kernel.  2032 bytes per head.
- */
-PSW_API int psw_window_bias_tables(const float* alpha, const float* beta, void* tables, int heads, int window,
-                                   void* stream);
-
-PSW_API int psw_window_hav_table(const float* uv, void* table, int H, int W, int window, int shift, void* stream);
+PSW_API int psw_window_source_map(int H, int W, int window, int shift, int pano_mode, int* map, int capacity,
+                                  int* hp, int* wp);
 
 /*
  * The whole MLP of a block in one kernel (Mlp.forward + shortcut, reference :44-61, :534):
  * x <- x + fc2(GELU(fc1(xn))), xn [M, C] bf16 (= norm2(x)), x [M, C] fp32 updated in place; w1 [hidden, C], w2 [C, hidden]
- * bf16, b1 [hidden], b2 [C] fp32 (or NULL).  The hidden activation never leaves the SM: both weight matrices stay in
+ * bf16, b1 [hidden], b2 [C] fp32 (both required).  The hidden activation never leaves the SM: both weight matrices stay in
  * shared memory, fc1 chunks accumulate in tensor memory, GELU writes bf16 back to tensor memory, fc2 consumes it from
  * there.  Instantiated for C = 96, hidden = 384 (stage 0 of the embed_dim-96 models); other widths return
  * PSW_ERR_UNSUPPORTED and the caller uses two psw_linear_fwd calls.
@@ -160,22 +154,23 @@ PSW_API int psw_mlp_fused_fwd(const void* xn, const void* w1, const float* b1, c
                               void* x, int64_t M, int C, int hidden, void* stream);
 
 /*
- * Production bf16 path.  psw_window_bias_full() evaluates EVERY additive term of the attention logits of one block at
- * one resolution — hav(uv_i, uv_j) * alpha[idx] + beta[idx] (_sphere_bias, reference :241-272, fp32 math) and, in planar
- * mode, the shifted-window mask (:621-643; mask may be NULL) — for every window of ONE image and every head:
- * table fp32 [windows][heads][13][64][4], element (i, j) at chunk j/4, row i, lane j%4; psw_window_bias_full_bytes()
- * is its size.  It depends on the geometry and the block's alpha / beta only (not on the batch): build it once per
- * block and resolution; the kernel reads it with 13 coalesced 16-byte loads per row (it stays L2-resident across the
- * images of a batch).  psw_window_attn_full_fwd() is psw_window_attn_fwd(PSW_BF16) taking that table instead of
- * alpha / beta / uv / hav_table / bias_tables / mask.  qkv_rows = B*H*W, or B*H*W + 1 when the qkv tensor carries one
- * extra row holding the bf16 qkv bias (what the qkv GEMM produces for an all-zero extra input row): padding cells then
- * gather that row and the kernel loads q/k/v with TMA (tile::gather4) instead of per-thread cp.async.
+ * Production bf16 path (tcgen05 / TMEM).  psw_window_bias_full() evaluates EVERY additive term of the attention logits
+ * of one block at one resolution — hav(uv_i, uv_j) * alpha[idx] + beta[idx] (_sphere_bias, reference :241-272, fp32
+ * math) and, in planar mode, the shifted-window mask (:621-643; mask may be NULL) — for every window of ONE image and
+ * every head, multiplied by log2(e) (the kernel's softmax uses exp2): table fp32 [windows][heads][13][64][4], element
+ * (i, j) at chunk j/4, row i, lane j%4; psw_window_bias_full_bytes() is its size.  It depends on the geometry and the
+ * block's alpha / beta only (not on the batch): build it once per block and resolution; the kernel reads it with 13
+ * coalesced 16-byte loads per row (it stays L2-resident across the images of a batch).
+ * psw_window_attn_full_fwd() is psw_window_attn_fwd(PSW_BF16) taking that table instead of alpha / beta / uv / mask.
+ * Instantiated for window 7 and head_dim 32 (every shipped PanoSwin config): psw_window_attn_full_supported() tells;
+ * other shapes return PSW_ERR_UNSUPPORTED and belong on psw_window_attn_fwd.
  */
+PSW_API int psw_window_attn_full_supported(int window, int head_dim);
 PSW_API int64_t psw_window_bias_full_bytes(int H, int W, int heads, int window, int pano_mode);
 PSW_API int psw_window_bias_full(const float* alpha, const float* beta, const float* uv, const float* mask, void* table,
                                  int H, int W, int heads, int window, int shift, int pano_mode, void* stream);
 PSW_API int psw_window_attn_full_fwd(const void* qkv, void* out, const void* bias_full, const float* qkv_bias,
-                                     int64_t qkv_rows, int B, int H, int W, int C, int heads, int window, int shift,
+                                     int B, int H, int W, int C, int heads, int window, int shift,
                                      int pano_mode, float scale, void* stream);
 
 /*
@@ -221,50 +216,8 @@ PSW_API int psw_stem_conv3x3_c32_relu_fwd(const void* x, const void* w_taps, con
 PSW_API int psw_patch_conv_fwd(const void* x, const void* w, const float* bias, void* out, int B, int H, int W,
                                int cin, int cout, int patch_h, int patch_w, void* stream);
 
-/*
- * The whole tail of the stem in one kernel: psw_patch_conv_fwd + patch_norm LayerNorm + absolute position add
- * (PatchEmbed.forward :768-771, SimplePanoSwinTransformer.forward :925-936):
- * out fp32 [B * H/ph * W/pw, cout] = LN(conv(x) + bias) * ln_gamma + ln_beta + pos[token % pos_rows].
- * pos [pos_rows, cout] fp32 or NULL.  cout % 32 == 0, cout <= 256.
- */
-PSW_API int psw_patch_conv_ln_fwd(const void* x, const void* w, const float* bias, const float* ln_gamma,
-                                  const float* ln_beta, float ln_eps, const float* pos, int64_t pos_rows, void* out,
-                                  int B, int H, int W, int cin, int cout, int patch_h, int patch_w, void* stream);
-
 /* dtype conversion helper for activations entering / leaving the bf16 path: n elements. */
 PSW_API int psw_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
-
-/*
- * Diagnostics (used by tests / profiling only; same arguments as psw_window_attn_fwd, bf16 storage):
- *   _simt_bf16  : the CUDA-core kernel on bf16 tensors (cross-check of the tensor-core kernel).
- */
-/* The bf16 pano kernel with per-phase SM-cycle totals of CTA 0 in phase_cycles[6] (device, int64):
- * {wait-for-loads, S MMA, softmax, P.V MMA, store, steps} (NULL allowed).  mode 1 = memory skeleton only: the same
- * gathers and stores without MMA / softmax (output = q rows), to measure what the access pattern alone sustains. */
-PSW_API int psw_window_attn_fwd_profile(const void* qkv, void* out, const float* alpha, const float* beta,
-                                        const void* bias_tables, const float* qkv_bias, const void* hav_table,
-                                        const void* bias_full, int B, int H, int W,
-                                        int C, int heads, int window, int shift, float scale,
-                                        long long* phase_cycles, int mode, void* stream);
-/* Process-wide diagnostic switch of the bf16 GEMM kernel (profiling only; 0 = normal operation, returns the previous
- * value): bit0 skip the output stores, bit1 skip the operand loads, bit2 skip the MMAs (results are then garbage);
- * bit3 skip the proxy fence, bit4 cycle counters;
- * bits [8,12) cap the pipeline stage count, bits [16,25) force the tile width. */
-PSW_API int psw_debug_linear_mode(int mode);
-/* Same for the fused MLP kernel: bit1 skips the final epilogue, bit3 the GELU arithmetic (results are then garbage);
- * bit2 selects the first version of the kernel (correct results; kept as the comparison point). */
-PSW_API int psw_debug_mlp_mode(int mode);
-/* With mode bit 4 set, CTA 0 of the last bf16 GEMM launch accumulated SM-cycle totals; copies them to the HOST
- * array host_out16[16] (synchronises): {producer wait-empty, mma wait-tempty, mma wait-full, mma issue, epilogue
- * wait-tfull, tmem-ld, math+stage, store-issue, tiles}. */
-PSW_API int psw_debug_linear_cycles(long long* host_out16);
-/* Host-only: dump the kernels' window geometry (see psw_api.cu); map may be NULL to query hp / wp. */
-PSW_API int psw_debug_source_map(int H, int W, int window, int shift, int pano_mode, int* map, int capacity,
-                                 int* hp, int* wp);
-PSW_API int psw_window_attn_fwd_simt_bf16(const void* qkv, void* out, const float* alpha, const float* beta,
-                                          const float* qkv_bias, const float* uv, const float* mask,
-                                          int B, int H, int W, int C, int heads, int window, int shift,
-                                          int pano_mode, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,12 @@ CASES = {
                (2, 3, 45, 123), "rand", True),
     "planar_tall": (O.make_config(embed_dim=32, depths=(2, 2), num_heads=(1, 2), out_indices=(0, 1), pano_mode=False, ape=True),
                     (1, 3, 78, 64), "randn", True),
+    # planar mode with ODD depths: every stage ends in a PitchAttentionModule (the reference default depths=[2,2,7,2]
+    # path; it only executes in planar mode)
+    "planar_odd": (O.make_config(embed_dim=32, depths=(3, 1, 2), num_heads=(1, 2, 4), out_indices=(0, 1, 2), pano_mode=False,
+                                 ape=False), (2, 3, 60, 100), "rand", True),
+    # BASELINE.json configs[3] family (embed_dim 128, heads 4-8-16-32) at a size the CPU reference finishes quickly
+    "panoswin_b_shaped": (O.make_config(embed_dim=128, depths=(2, 2, 2, 2), num_heads=(4, 8, 16, 32)), (1, 3, 224, 448), "rand", False),
     "panoswin_t_512": (O.PANOSWIN_T, (1, 3, 512, 1024), "rand", False),
     "panoswin_t_512_randn": (O.PANOSWIN_T, (1, 3, 512, 1024), "randn", False),
 }
@@ -78,7 +84,11 @@ def main():
     if "--fpn" in sys.argv[1:]:                            # only the FPN fixtures (the others are unchanged)
         fpn_golden()
         return
+    only = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--only=")]
     ref = R.load_reference()
+    if only:                                                # regenerate just the named end-to-end cases
+        end_to_end(only)
+        return
     # --- the reference's own known answers ---------------------------------------------------
     kat = {
         "rel_index_3": ref.make_relative_position_index(3).numpy(),
@@ -109,8 +119,14 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN_DIR, "known_answers.npz"), **kat)
     print("known_answers.npz:", sorted(kat))
 
+    end_to_end(list(CASES))
+    fpn_golden()
+
+
+def end_to_end(names):
     # --- end-to-end cases --------------------------------------------------------------------
-    for name, (cfg, shape, kind, full) in CASES.items():
+    for name in names:
+        cfg, shape, kind, full = CASES[name]
         sd = O.make_state_dict(cfg, PARAM_SEED)
         model = R.build_reference_model(cfg, sd)            # strict=True: pins key names
         img = O.make_image(shape, IMAGE_SEED, kind)
@@ -129,7 +145,6 @@ def main():
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **rec)
         print(f"{name}: {len(outs)} outputs, {len(blocks)} blocks, {os.path.getsize(path) / 1024:.0f} KiB")
-    fpn_golden()
 
 
 if __name__ == "__main__":

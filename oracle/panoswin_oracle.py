@@ -222,6 +222,30 @@ def block(x: Tensor, uv_hw2: Tensor, p, prefix, H, W, heads, ws, shift, scale, p
     return x + mlp(layer_norm(x, p, prefix + "norm2."), p, prefix + "mlp.")
 
 
+def pitch_attention_block_planar(x: Tensor, p, prefix, H, W, heads, ws, scale) -> Tensor:
+    """PitchAttentionModule.forward with pano_mode=False (simple_panoswin_transformer.py:1143-1209, _attention
+    :1212-1237): the "rotated" map is the map itself (:1177-1179), so every un-shifted window attends to itself with
+    separate q / k / v linears, the beta-only bias (:257-258) and no mask.  Reference quirk reproduced on purpose: the
+    shortcut is a VIEW of the input taken before norm1 is written back in place (:1163-1164), so the residual added
+    after the attention is norm1(x), not x."""
+    B, S, c = x.shape
+    xn = layer_norm(x, p, prefix + "norm1.")
+    Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
+    xw = _windows(F.pad(xn.view(B, H, W, c), (0, 0, 0, Wp - W, 0, Hp - H)), ws)          # zero features on padded cells
+    n, N, _ = xw.shape
+    hd = c // heads
+    def lin(name):
+        return F.linear(xw, p[prefix + name + ".weight"], p.get(prefix + name + ".bias")).view(n, N, heads, hd).transpose(1, 2)
+    q, k, v = lin("q_linear") * scale, lin("k_linear"), lin("v_linear")
+    idx = relative_position_index(ws).reshape(-1)
+    beta = p[prefix + "sphere_position_beta_table_Te"][idx].view(N, N, heads).permute(2, 0, 1)
+    prob = torch.softmax(q @ k.transpose(-1, -2) + beta[None], dim=-1)
+    yw = F.linear((prob @ v).transpose(1, 2).reshape(n, N, c), p[prefix + "proj.weight"], p[prefix + "proj.bias"])
+    y = _unwindows(yw, ws, B, Hp, Wp)[:, :H, :W].reshape(B, S, c)
+    x = xn + y                                               # the in-place norm1 made the shortcut norm1(x)
+    return x + mlp(layer_norm(x, p, prefix + "norm2."), p, prefix + "mlp.")
+
+
 def patch_merging(x: Tensor, p, prefix, H, W) -> Tensor:
     """2x2 gather (order: (0,0), (1,0), (0,1), (1,1)) -> LN(4c) -> Linear(4c -> 2c, no bias)
     (PatchMerging.forward, simple_panoswin_transformer.py:551-576)."""
@@ -286,13 +310,16 @@ def backbone_forward(p: Dict[str, Tensor], cfg: dict, img: Tensor, return_blocks
         heads = cfg["num_heads"][li]
         scale = cfg["qk_scale"] or (c // heads) ** -0.5
         depth = cfg["depths"][li]
-        if depth % 2:
+        if depth % 2 and pano:
             raise NotImplementedError("odd depths add PitchAttentionModule, which the reference cannot "
                                       "execute in pano mode (simple_panoswin_transformer.py:1038)")
         uv = uv_grid(H, W) if pano else torch.zeros(H, W, 2)
-        for bi in range(depth):
+        for bi in range(depth - depth % 2):
             shift = 0 if bi % 2 == 0 else ws // 2
             x = block(x, uv, p, f"layers.{li}.blocks.{bi}.", H, W, heads, ws, shift, scale, pano)
+            blocks.append(x)
+        if depth % 2:                                        # trailing PitchAttentionModule (:636-647), planar mode
+            x = pitch_attention_block_planar(x, p, f"layers.{li}.blocks.{depth - 1}.", H, W, heads, ws, scale)
             blocks.append(x)
         if li in cfg["out_indices"]:
             o = layer_norm(x, p, f"norm{li}.")
@@ -345,7 +372,20 @@ def make_state_dict(cfg: dict, seed: int = 0) -> Dict[str, Tensor]:
     for li, (depth, heads) in enumerate(zip(cfg["depths"], cfg["num_heads"])):
         c = E * 2 ** li
         hidden = int(c * cfg["mlp_ratio"])
-        for bi in range(depth):
+        if depth % 2:                                        # PitchAttentionModule parameters (:990-1022), last block
+            pre = f"layers.{li}.blocks.{depth - 1}."
+            sd[pre + "relative_position_index_OO"] = relative_position_index(ws)
+            sd[pre + "np_uv"] = torch.tensor([1.0, -0.0001]) * math.pi
+            linear(pre + "proj", c, c)
+            sd[pre + "sphere_position_alpha_table_Te"] = normal(((2 * ws - 1) ** 2, heads), 0.5)
+            sd[pre + "sphere_position_beta_table_Te"] = normal(((2 * ws - 1) ** 2, heads), 0.5)
+            linear(pre + "mlp.fc1", c, hidden)
+            linear(pre + "mlp.fc2", hidden, c)
+            norm(pre + "norm2", c)
+            norm(pre + "norm1", c)
+            for nm in ("q_linear", "k_linear", "v_linear"):
+                linear(pre + nm, c, c, bias=cfg["qkv_bias"])
+        for bi in range(depth - depth % 2):
             pre = f"layers.{li}.blocks.{bi}."
             norm(pre + "norm1", c)
             sd[pre + "attn.relative_position_index_OO"] = relative_position_index(ws)

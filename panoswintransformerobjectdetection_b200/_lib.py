@@ -12,6 +12,8 @@ PSW_EPI_GELU = 1
 
 _vp, _fp, _i, _i64, _f = C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float
 
+ABI_VERSION = 2            # must equal PSW_ABI_VERSION of include/panoswin_b200.h (bumped with every prototype change)
+
 # name -> argtypes, exactly the prototypes of include/panoswin_b200.h
 SIGNATURES = {
     "psw_abi_version": [],
@@ -22,29 +24,31 @@ SIGNATURES = {
     "psw_linear_ln_fwd": [_vp, _vp, _fp, _vp, _vp, _fp, _fp, _f, _vp, _i64, _i, _i, _vp],
     "psw_linear_ln_nchw_fwd": [_vp, _vp, _fp, _vp, _vp, _fp, _fp, _f, _fp, _i64, _i64, _i, _i, _vp],
     "psw_mlp_fused_fwd": [_vp, _vp, _fp, _vp, _fp, _vp, _i64, _i, _i, _vp],
-    "psw_window_attn_fwd": [_vp, _vp, _fp, _fp, _vp, _fp, _fp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
-    "psw_window_bias_tables": [_fp, _fp, _vp, _i, _i, _vp],
+    "psw_window_attn_fwd": [_vp, _vp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
     "psw_window_grid": [_i, _i, _i, _i, _vp, _vp],
-    "psw_window_hav_table": [_fp, _vp, _i, _i, _i, _i, _vp],
+    "psw_window_source_map": [_i, _i, _i, _i, _i, _vp, _i, _vp, _vp],
+    "psw_window_attn_full_supported": [_i, _i],
     "psw_window_bias_full_bytes": [_i, _i, _i, _i, _i],
     "psw_window_bias_full": [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    "psw_window_attn_full_fwd": [_vp, _vp, _vp, _fp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
+    "psw_window_attn_full_fwd": [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
     "psw_patch_merge_ln_fwd": [_vp, _vp, _fp, _fp, _i, _i, _i, _i, _f, _i, _i, _vp],
     "psw_layernorm_nchw_fwd": [_vp, _vp, _fp, _fp, _i, _i64, _i, _f, _i, _vp],
     "psw_stem_conv3x3_relu_fwd": [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],
     "psw_stem_conv3x3_c32_relu_fwd": [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _vp],
     "psw_patch_conv_fwd": [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "psw_patch_conv_ln_fwd": [_vp, _vp, _fp, _fp, _fp, _f, _fp, _i64, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "psw_cast": [_vp, _vp, _i64, _i, _i, _vp],
-    "psw_window_attn_fwd_profile": [_vp, _vp, _fp, _fp, _vp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _vp],
-    "psw_debug_linear_mode": [_i],
-    "psw_debug_mlp_mode": [_i],
-    "psw_debug_linear_cycles": [_vp],
-    "psw_debug_source_map": [_i, _i, _i, _i, _i, _vp, _i, _vp, _vp],
-    "psw_window_attn_fwd_simt_bf16": [_vp, _vp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp],
+}
+# include/panoswin_b200_debug.h: present only in the -DPSW_DIAGNOSTICS build (load(diagnostics=True))
+DIAG_SIGNATURES = {
+    "psw_diag_window_attn_full": [_vp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _i, _i, _vp],
+    "psw_diag_linear_mode": [_i],
+    "psw_diag_linear_cycles": [_vp],
+    "psw_diag_mlp_mode": [_i],
 }
 
-_lib = None
+_libs = {}
+# tools/microbench.py sets PSW_DIAGNOSTICS=1 before importing the package: every call then goes to the diagnostics build
+_DEFAULT_DIAG = os.environ.get("PSW_DIAGNOSTICS") == "1"
 
 
 class PanoSwinB200Error(RuntimeError):
@@ -55,24 +59,39 @@ def library_path() -> str:
     return _build.LIB_PATH
 
 
-def load(build_if_missing: bool = True) -> C.CDLL:
-    """Load (building first when the .so is absent and nvcc is available) and type the library."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    path = library_path()
-    if not os.path.isfile(path):
-        if not build_if_missing:
+def load(build_if_missing: bool = True, diagnostics: bool = None) -> C.CDLL:
+    """Load and type the library.  When nvcc is available the (cheap) source fingerprint is checked first and a stale
+    or missing library is rebuilt (file-locked: torchrun ranks do not race); without nvcc a stale stamp raises.  The
+    ABI version of the loaded binary must equal ABI_VERSION (a stale .so called through new argtypes would corrupt
+    memory silently).  `diagnostics=True` loads the -DPSW_DIAGNOSTICS build used by the profiling tools."""
+    if diagnostics is None:
+        diagnostics = _DEFAULT_DIAG
+    if diagnostics in _libs:
+        return _libs[diagnostics]
+    path = _build.DIAG_LIB_PATH if diagnostics else library_path()
+    if not _build.is_current(diagnostics):
+        have_nvcc = _build._nvcc(required=False) is not None
+        if have_nvcc and build_if_missing:
+            _build.build(diagnostics=diagnostics)
+        elif not os.path.isfile(path):
             raise PanoSwinB200Error(f"{path} not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
-        _build.build()
+        elif not have_nvcc:
+            raise PanoSwinB200Error(f"{path} does not match the sources (stale build) and nvcc is not available to rebuild it")
     lib = C.CDLL(path)
-    for name, argtypes in SIGNATURES.items():
+    lib.psw_abi_version.argtypes = []
+    lib.psw_abi_version.restype = C.c_int
+    if lib.psw_abi_version() != ABI_VERSION:
+        raise PanoSwinB200Error(f"{path}: ABI version {lib.psw_abi_version()} != {ABI_VERSION} expected by the Python binding")
+    sigs = dict(SIGNATURES)
+    if diagnostics:
+        sigs.update(DIAG_SIGNATURES)
+    for name, argtypes in sigs.items():
         fn = getattr(lib, name)            # AttributeError here = header / library mismatch
         fn.argtypes = argtypes
         fn.restype = C.c_int64 if name == "psw_window_bias_full_bytes" else C.c_int
     lib.psw_last_error_string.argtypes = []
     lib.psw_last_error_string.restype = C.c_char_p
-    _lib = lib
+    _libs[diagnostics] = lib
     return lib
 
 

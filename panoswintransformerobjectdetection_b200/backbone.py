@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import math
 import warnings
+from collections import OrderedDict
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -185,6 +186,43 @@ class PanoSwinTransformerBlock(nn.Module, DoubleModeModule):
         self.pano_mode = pano_mode
 
 
+class PitchAttentionModule(nn.Module, DoubleModeModule):
+    """Parameter container of the reference's PitchAttentionModule (:990-1022; BasicWindowAttention members :224-239):
+    the trailing block of a stage with an odd depth.  In planar mode its "rotated" map is the map itself (:1177-1179):
+    every un-shifted window attends to itself through separate q / k / v linears -- that forward runs on the same
+    kernels as a regular block (backbone._pitch_block).  In pano mode the reference itself cannot execute it
+    (:1038 calls pano_rotate_image(..., with_uv=True), which lzx/pano_rotate.py:169 does not accept), so there is no
+    behaviour to reproduce and the forward raises."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0.0, np_v=-0.0001,
+                 norm_layer=nn.LayerNorm, drop_path=0.0, mlp_ratio=4.0, drop=0.0, act_layer=nn.GELU, pano_mode=True):
+        nn.Module.__init__(self)
+        DoubleModeModule.__init__(self, pano_mode=pano_mode)
+        self.dim = dim
+        self.window_size = (window_size, window_size) if isinstance(window_size, int) else tuple(window_size)
+        self.num_heads = num_heads
+        self.scale = qk_scale or (dim // num_heads) ** -0.5
+        self.shift_size = 0
+        self.register_buffer("relative_position_index_OO", make_relative_position_index(self.window_size))
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(drop)
+        tsize = (2 * self.window_size[0] - 1) * (2 * self.window_size[1] - 1)
+        first = _trunc_normal_(torch.zeros(tsize, num_heads), std=0.02)
+        self.sphere_position_alpha_table_Te = nn.Parameter(first.clone())
+        self.sphere_position_beta_table_Te = nn.Parameter(first.clone())
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self.norm2 = norm_layer(dim)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm1 = norm_layer(dim)
+        self.q_linear = nn.Linear(dim, dim, bias=qkv_bias)
+        self.k_linear = nn.Linear(dim, dim, bias=qkv_bias)
+        self.v_linear = nn.Linear(dim, dim, bias=qkv_bias)
+        self.register_buffer("np_uv", torch.tensor([1.0, np_v]) * math.pi)
+        self.H = None
+        self.W = None
+
+
 class PatchMerging(nn.Module):
     def __init__(self, dim, norm_layer=nn.LayerNorm):
         super().__init__()
@@ -202,20 +240,19 @@ class BasicLayer(nn.Module, DoubleModeModule):
         self.shift_size = window_size // 2
         self.depth = depth
         self.use_checkpoint = use_checkpoint
-        if depth % 2:
-            # reference :636-647 appends PitchAttentionModule, which cannot execute in pano mode as shipped
-            # (simple_panoswin_transformer.py:1038 vs lzx/pano_rotate.py:169); out of scope
-            raise NotImplementedError(
-                f"odd stage depth {depth} needs PitchAttentionModule, which the reference itself cannot run in pano "
-                "mode; use even depths (every shipped config does)")
-        self.blocks = nn.ModuleList([
+        blocks = [
             PanoSwinTransformerBlock(
                 dim=dim, num_heads=num_heads, window_size=window_size,
                 shift_size=0 if (i % 2 == 0) else window_size // 2, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
                 qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
                 drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path, norm_layer=norm_layer,
                 pano_mode=pano_mode)
-            for i in range(depth)])
+            for i in range(depth - depth % 2)]
+        if depth % 2:                                       # reference :636-647
+            blocks.append(PitchAttentionModule(dim=dim, num_heads=num_heads, window_size=window_size, qkv_bias=qkv_bias,
+                                               qk_scale=qk_scale, attn_drop=attn_drop, mlp_ratio=mlp_ratio,
+                                               norm_layer=norm_layer, drop=drop))
+        self.blocks = nn.ModuleList(blocks)
         self.downsample = downsample(dim=dim, norm_layer=norm_layer) if downsample is not None else None
         DoubleModeModule.__init__(self, pano_mode=pano_mode)
 
@@ -279,7 +316,13 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         self._compute_dtype = torch.bfloat16
         self._residual_dtype = torch.float32
         self._fused_conv_relu = None
-        self._const_cache: Dict[tuple, torch.Tensor] = {}
+        # Resolution-dependent constants (uv grids, planar masks, position rows, the per-block bias tables of the bf16
+        # attention kernel: ~150 MB per resolution for PanoSwin-T at 512x1024) live in an LRU keyed by the input
+        # resolution: multi-scale inputs (the shipped configs train at 480-800) recycle the oldest entry instead of
+        # growing without bound.  Converted weights (bf16 copies, folded stem) are resolution-independent.
+        self.max_cached_resolutions = 2
+        self._res_cache: "OrderedDict[tuple, Dict[tuple, object]]" = OrderedDict()
+        self._cur_res: Dict[tuple, object] = {}
         self._weight_cache: Dict[tuple, tuple] = {}
         DoubleModeModule.__init__(self, pano_mode=pano_mode)
 
@@ -335,13 +378,36 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         return self
 
     # ---- cached constants / converted weights -------------------------------------------------
+    def _enter_resolution(self, H, W, device):
+        """Select (creating / evicting as needed) the constants of one input resolution; called once per forward."""
+        key = (int(H), int(W), bool(self.pano_mode), str(device))
+        ent = self._res_cache.get(key)
+        if ent is None:
+            ent = {}
+            self._res_cache[key] = ent
+            while len(self._res_cache) > max(1, int(self.max_cached_resolutions)):
+                self._res_cache.popitem(last=False)        # a CUDA graph that captured these tensors keeps its own references
+        else:
+            self._res_cache.move_to_end(key)
+        self._cur_res = ent
+        return ent
+
     def _const(self, key, builder, device):
-        k = key + (str(device),)
-        t = self._const_cache.get(k)
+        t = self._cur_res.get(key)
         if t is None:
             t = builder().to(device).contiguous()
-            self._const_cache[k] = t
+            self._cur_res[key] = t
         return t
+
+    def cache_signature(self):
+        """Everything a captured CUDA graph of the forward bakes in besides the input buffer: parameter / buffer
+        versions and addresses, the compute and residual dtypes, pano mode and train / eval.  runtime.GraphedForward
+        compares it before every replay and re-captures when it changed."""
+        sig = [self._compute_dtype, self._residual_dtype, bool(self.pano_mode), bool(self.training)]
+        for t in list(self.parameters()) + list(self.buffers()):
+            sig.append(t._version)
+            sig.append(t.data_ptr())
+        return tuple(sig)
 
     def _w(self, p: torch.Tensor, dtype) -> torch.Tensor:
         """Parameter in the compute dtype (bf16 copies are cached until the parameter changes)."""
@@ -355,28 +421,17 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         self._weight_cache[k] = (p._version, p.data_ptr(), conv)
         return conv
 
-    def _bias_tables(self, attn, ws):
-        """Per-head (alpha, beta) layout for the bf16 attention kernel, cached until either table changes."""
-        al, be = attn.sphere_position_alpha_table_Te, attn.sphere_position_beta_table_Te
-        k = ("btab", id(attn))
-        ver = (al._version, be._version, al.data_ptr(), be.data_ptr())
-        hit = self._weight_cache.get(k)
-        if hit is None or hit[0] != ver:
-            hit = (ver, ops.window_bias_tables(al.detach().contiguous(), be.detach().contiguous(), ws))
-            self._weight_cache[k] = hit
-        return hit[1]
-
     def _bias_full(self, attn, uv, mask, H, W, ws, shift):
         """Full additive-bias table of one block at one resolution for the bf16 attention kernel (great-circle +
         relative-position bias, planar shift mask), cached until alpha / beta change."""
         al, be = attn.sphere_position_alpha_table_Te, attn.sphere_position_beta_table_Te
-        k = ("bfull", id(attn), H, W, ws, shift, self.pano_mode)
+        k = ("bfull", id(attn), H, W, ws, shift)
         ver = (al._version, be._version, al.data_ptr(), be.data_ptr())
-        hit = self._weight_cache.get(k)
+        hit = self._cur_res.get(k)
         if hit is None or hit[0] != ver:
             hit = (ver, ops.window_bias_full(al.detach().contiguous(), be.detach().contiguous(), uv, mask, H, W, ws, shift,
                                              self.pano_mode))
-            self._weight_cache[k] = hit
+            self._cur_res[k] = hit
         return hit[1]
 
     @staticmethod
@@ -384,9 +439,10 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         return None if p is None else p.detach().contiguous()
 
     # ---- stem ---------------------------------------------------------------------------------
-    def _stem(self, x: torch.Tensor, fuse_tail: bool = False):
-        """conv-BN-ReLU x2 + patch conv -> NHWC tokens [B, Hs, Ws, E].  Library convolutions (cuDNN through
-        torch) for now — SURVEY.md §8 f-2 lists the stem as the next row after the attention path."""
+    def _stem(self, x: torch.Tensor):
+        """conv-BN-ReLU x2 + patch conv -> NHWC tokens [B, Hs, Ws, E] (reference PatchEmbed.forward :756-773).
+        bf16 mode: eval-mode BatchNorm folded into the convolutions, all three on libpanoswin_b200 (tcgen05) for the
+        stem widths the kernels are instantiated for; fp32 mode and other widths: see the branches below."""
         pe = self.patch_embed
         ph, pw = pe.patch_size
         _, _, H, W = x.shape
@@ -439,14 +495,6 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                     hit = (k3, conv3.weight.detach().permute(0, 2, 3, 1).to(torch.bfloat16).contiguous(),
                            None if conv3.bias is None else conv3.bias.detach().float().contiguous())
                     self._weight_cache["stem3"] = hit
-                E = conv3.out_channels
-                if fuse_tail and pe.norm is not None and E % 32 == 0 and E <= 256:
-                    # patch conv + patch_norm + absolute position in one kernel: fp32 residual stream [B, Hs*Ws, E]
-                    Hs, Ws = y.shape[1] // ph, y.shape[2] // pw
-                    pos = self._abs_position(Hs, Ws, y.device) if (self.pano_mode and self.ape) else None
-                    xres = ops.patch_conv_layernorm(y, hit[1], hit[2], pe.patch_size, self._f(pe.norm.weight),
-                                                    self._f(pe.norm.bias), pe.norm.eps, pos)
-                    return xres, (Hs, Ws)
                 return ops.patch_conv(y, hit[1], hit[2], pe.patch_size)                                  # [B, Hs, Ws, E]
             y = F.conv2d(y.permute(0, 3, 1, 2), w3, b3, stride=pe.patch_size)
             return y.permute(0, 2, 3, 1).contiguous()      # no copy when the conv output is channels-last
@@ -483,11 +531,11 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             u, v = uv[..., 0], uv[..., 1]
             return torch.stack([torch.sin(u) * torch.sin(v), torch.cos(u) * torch.sin(v), torch.cos(v), u, v], -1).reshape(-1, 5)
         xyzuv = self._const(("xyzuv", Hs, Ws), build, device)
-        k = ("pos", Hs, Ws, str(device))
-        hit = self._weight_cache.get(k)
+        k = ("pos", Hs, Ws)
+        hit = self._cur_res.get(k)
         if hit is None or hit[0] != ver:
             pos = ops.linear(xyzuv, self._f(self.abs_encoder.weight), self._f(self.abs_encoder.bias))
-            self._weight_cache[k] = hit = (ver, pos)
+            self._cur_res[k] = hit = (ver, pos)
         return hit[1]
 
     # ---- forward ------------------------------------------------------------------------------
@@ -501,12 +549,15 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         with torch.no_grad():
             return self._forward_tokens(x_bchw.float())
 
-    def forward_streamed(self, x_bchw, on_output):
+    def forward_streamed(self, x_bchw, on_output=None, on_block=None):
         """forward() that additionally calls `on_output(k, feature_map)` as soon as the k-th output map has been
-        enqueued, so a caller can start consuming (e.g. copying out) early stages while later ones still run."""
+        enqueued, so a caller can start consuming (e.g. copying out) early stages while later ones still run, and
+        `on_block(n, tokens)` after the n-th PanoSwinTransformerBlock with its output tokens [B, H*W, C] (the residual
+        stream; it is updated in place by the following kernels, so a consumer must copy what it keeps) -- the
+        equivalent of a forward hook on `layers[i].blocks[j]` of the reference (:493-536) minus the uv channels."""
         self._check_forward(x_bchw)
         with torch.no_grad():
-            return self._forward_tokens(x_bchw.float(), on_output)
+            return self._forward_tokens(x_bchw.float(), on_output, on_block)
 
     def _check_forward(self, x_bchw):
         if not x_bchw.is_cuda:
@@ -518,25 +569,59 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             raise AttributeError("pano_mode=True requires ape=True: the reference builds abs_encoder only when ape is set "
                                  "(simple_panoswin_transformer.py:841-842) and always calls it in pano mode (:934)")
 
-    def _forward_tokens(self, img: torch.Tensor, on_output=None) -> Tuple[torch.Tensor, ...]:
+    def _pitch_block(self, blk, x, xn, B, H, W, C, cd, rd):
+        """PitchAttentionModule.forward (:1143-1209) in planar mode: un-shifted windows attend to themselves with
+        separate q / k / v linears (one GEMM on the concatenated weights), beta-only bias, no mask.  The reference takes
+        its shortcut as a view BEFORE writing norm1 back in place (:1163-1164), so the residual is norm1(x): reproduced."""
+        if self.pano_mode:
+            raise NotImplementedError(
+                "PitchAttentionModule (odd stage depth) cannot run in pano mode: the reference itself fails there "
+                "(simple_panoswin_transformer.py:1038 passes with_uv=True to lzx.pano_rotate.pano_rotate_image, which "
+                "lzx/pano_rotate.py:169 does not accept), so there is no behaviour to match; use even depths (every "
+                "shipped config does) or planar mode")
+        ws = blk.window_size[0]
+        ver = tuple((p._version, p.data_ptr()) for l in (blk.q_linear, blk.k_linear, blk.v_linear) for p in l.parameters())
+        hit = self._weight_cache.get(("pam_qkv", id(blk), cd))
+        if hit is None or hit[0] != ver:
+            w = torch.cat([blk.q_linear.weight, blk.k_linear.weight, blk.v_linear.weight], 0).detach()
+            b = None
+            if blk.q_linear.bias is not None:
+                b = torch.cat([blk.q_linear.bias, blk.k_linear.bias, blk.v_linear.bias], 0).detach().float().contiguous()
+            hit = (ver, ops.cast(w.contiguous(), cd) if cd != w.dtype else w.contiguous(), b)
+            self._weight_cache[("pam_qkv", id(blk), cd)] = hit
+        _, wqkv, bqkv = hit
+        xr = ops.layernorm(x, self._f(blk.norm1.weight), self._f(blk.norm1.bias), blk.norm1.eps, rd)     # the new residual
+        xn = xr if rd == cd else ops.cast(xr, cd)
+        qkv = ops.linear(xn, wqkv, bqkv)
+        if cd == torch.bfloat16 and ops.window_attention_full_supported(ws, C // blk.num_heads):
+            k = ("bfull_pam", id(blk), H, W, ws)
+            al, be = blk.sphere_position_alpha_table_Te, blk.sphere_position_beta_table_Te
+            ver = (al._version, be._version, al.data_ptr(), be.data_ptr())
+            bf = self._cur_res.get(k)
+            if bf is None or bf[0] != ver:
+                bf = (ver, ops.window_bias_full(self._f(al), self._f(be), None, None, H, W, ws, 0, False))
+                self._cur_res[k] = bf
+            att = ops.window_attention_full(qkv.view(B, H, W, 3 * C), bf[1], bqkv, blk.num_heads, ws, 0, False, blk.scale)
+        else:
+            att = ops.window_attention(qkv.view(B, H, W, 3 * C), self._f(blk.sphere_position_alpha_table_Te),
+                                       self._f(blk.sphere_position_beta_table_Te), bqkv, None, None, blk.num_heads, ws, 0,
+                                       False, blk.scale)
+        x = ops.linear(att.view(B, H * W, C), self._w(blk.proj.weight, cd), self._f(blk.proj.bias), residual=xr, out=xr)
+        xn2 = ops.layernorm(x, self._f(blk.norm2.weight), self._f(blk.norm2.bias), blk.norm2.eps, cd)
+        hid = ops.linear(xn2, self._w(blk.mlp.fc1.weight, cd), self._f(blk.mlp.fc1.bias), gelu=True)
+        return ops.linear(hid, self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), residual=x, out=x)
+
+    def _forward_tokens(self, img: torch.Tensor, on_output=None, on_block=None) -> Tuple[torch.Tensor, ...]:
         cd = self._compute_dtype
         rd = torch.float32 if cd == torch.float32 else self._residual_dtype      # residual-stream storage
         dev = img.device
         ws = self.window_size
-        # fuse_tail (patch conv + patch_norm + position add in one kernel, ops.patch_conv_layernorm) is correct but
-        # measured slower than the two kernels (0.64 vs 0.36 + 0.23 ms at 32x512x1024): off
-        tok = self._stem(img, fuse_tail=False)
-        if isinstance(tok, tuple):                                # the stem already produced the residual stream
-            x, (Hs, Ws) = tok
-            B, E = x.shape[0], x.shape[2]
-            tok = None
-        else:                                                     # [B, Hs, Ws, E] in the compute dtype
-            B, Hs, Ws, E = tok.shape
-        pos = self._abs_position(Hs, Ws, dev) if (self.pano_mode and self.ape and tok is not None) else None
+        tok = self._stem(img)                                     # [B, Hs, Ws, E] in the compute dtype
+        B, Hs, Ws, E = tok.shape
+        self._enter_resolution(Hs, Ws, dev)
+        pos = self._abs_position(Hs, Ws, dev) if (self.pano_mode and self.ape) else None
         xn_first = None                                       # norm1 of the very first block when the stem LN produces it
-        if tok is None:
-            pass
-        elif self.patch_embed.norm is not None and cd == torch.bfloat16 and rd == torch.float32 and len(self.layers[0].blocks) > 0:
+        if self.patch_embed.norm is not None and cd == torch.bfloat16 and rd == torch.float32 and len(self.layers[0].blocks) > 0:
             # patch_norm (+ position add) and the first block's norm1 in one pass over the rows
             n, n1 = self.patch_embed.norm, self.layers[0].blocks[0].norm1
             x, xn_first = ops.layernorm2(tok.view(B, Hs * Ws, E), self._f(n.weight), self._f(n.bias), n.eps, pos,
@@ -551,6 +636,7 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             x = x.to(rd).contiguous()
         H, W = Hs, Ws
         outs = []
+        n_block = 0
         for i, layer in enumerate(self.layers):
             C = self.num_features[i]
             uv = self._const(("uv", H, W), lambda: make_uv_hw2(H, W), dev) if self.pano_mode else None
@@ -559,6 +645,13 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             xn = xn_first if i == 0 else None                 # norm1(x) of the current block when already computed
             stage_map = None                                  # the stage's NCHW output when the last fc2 produced it
             for j, blk in enumerate(layer.blocks):
+                if isinstance(blk, PitchAttentionModule):
+                    x = self._pitch_block(blk, x, xn, B, H, W, C, cd, rd)
+                    xn = None
+                    if on_block is not None:
+                        on_block(n_block, x)
+                    n_block += 1
+                    continue
                 a = blk.attn
                 shift = blk.shift_size
                 mask = None
@@ -567,11 +660,12 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                 if xn is None:
                     xn = ops.layernorm(x, self._f(blk.norm1.weight), self._f(blk.norm1.bias), blk.norm1.eps, cd)
                 qkv = ops.linear(xn, self._w(a.qkv.weight, cd), self._f(a.qkv.bias))
-                full_ok = cd == torch.bfloat16 and ws == 7 and C // a.num_heads == 32
-                if full_ok:                                  # tcgen05 kernel, all additive logit terms precomputed
+                if cd == torch.bfloat16 and ops.window_attention_full_supported(ws, C // a.num_heads):
+                    # tcgen05 kernel, all additive logit terms precomputed
                     att = ops.window_attention_full(qkv.view(B, H, W, 3 * C), self._bias_full(a, uv, mask, H, W, ws, shift),
                                                     self._f(a.qkv.bias), a.num_heads, ws, shift, self.pano_mode, a.scale)
                 else:
+                    # generic CUDA-core kernel: the fp32 parity path, and bf16 for other window sizes / head dims
                     att = ops.window_attention(qkv.view(B, H, W, 3 * C), self._f(a.sphere_position_alpha_table_Te),
                                                self._f(a.sphere_position_beta_table_Te), self._f(a.qkv.bias), uv, mask,
                                                a.num_heads, ws, shift, self.pano_mode, a.scale)
@@ -587,6 +681,9 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                     x = ops.mlp_fused(xn2, self._w(blk.mlp.fc1.weight, cd), self._f(blk.mlp.fc1.bias),
                                       self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), x)
                     xn = None
+                    if on_block is not None:
+                        on_block(n_block, x)
+                    n_block += 1
                     continue
                 hid = ops.linear(xn2, self._w(blk.mlp.fc1.weight, cd), self._f(blk.mlp.fc1.bias), gelu=True)
                 if fuse_ln and nxt is not None:               # fc2 + shortcut -> the next block's norm1
@@ -600,6 +697,9 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                 else:
                     x = ops.linear(hid, self._w(blk.mlp.fc2.weight, cd), self._f(blk.mlp.fc2.bias), residual=x, out=x)
                     xn = None
+                if on_block is not None:
+                    on_block(n_block, x)
+                n_block += 1
             if i in self.out_indices:
                 n = getattr(self, f"norm{i}")
                 outs.append(stage_map if stage_map is not None else

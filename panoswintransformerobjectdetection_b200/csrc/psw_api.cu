@@ -16,17 +16,24 @@ void set_error(const char* fmt, ...) {
 }
 
 EncodeTiledFn get_encode_tiled() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // function-local static: initialised exactly once, thread-safe (C++11 magic static)
+  static const EncodeTiledFn fn = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
+      return reinterpret_cast<EncodeTiledFn>(p);
+    return static_cast<EncodeTiledFn>(nullptr);
+  }();
   return fn;
+}
+
+// SM count of the CURRENT device (queried per call: a process may drive several devices)
+int num_sms() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    n = 148;
+  return n;
 }
 
 int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
@@ -95,23 +102,6 @@ extern "C" PSW_API int psw_check_device(int dev) {
   cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
   PSW_REQUIRE(major == 10, PSW_ERR_NO_DEVICE, "device %d is sm_%d%d; libpanoswin_b200 is built for sm_100a only",
               dev, major, minor);
-  return 0;
-}
-
-// Host-only diagnostic: the window geometry used by the attention kernels (psw::source_token).
-// Fills map[(nWh*ws) * (nWw*ws)] with the flat source token of every cell of the padded shifted map
-// (-1 = zero padding) and returns the padded height / width through hp / wp.  No GPU involved.
-extern "C" PSW_API int psw_debug_source_map(int H, int W, int window, int shift, int pano_mode, int* map, int capacity,
-                                            int* hp, int* wp) {
-  PSW_REQUIRE(H > 0 && W > 0 && window > 0 && shift >= 0 && shift < window && hp && wp, PSW_ERR_BAD_ARG,
-              "psw_debug_source_map: bad arguments");
-  WinGeom g = make_geom(H, W, window, shift, pano_mode);
-  *hp = g.nWh * window;
-  *wp = g.nWw * window;
-  if (!map) return 0;
-  PSW_REQUIRE(capacity >= *hp * *wp, PSW_ERR_BAD_ARG, "psw_debug_source_map: capacity %d < %d", capacity, *hp * *wp);
-  for (int i = 0; i < *hp; ++i)
-    for (int j = 0; j < *wp; ++j) map[i * *wp + j] = source_token(g, i, j);
   return 0;
 }
 

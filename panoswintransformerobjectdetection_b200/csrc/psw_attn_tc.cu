@@ -3,25 +3,26 @@
 // BasicWindowAttention core / window_reverse of the reference
 // (simple_panoswin_transformer.py:376-409, :486-491, :64-92, :290-308) in one pass over HBM.
 //
-// Work decomposition.  A "unit" is one (window, head): 49 tokens x head_dim 32.  The tensor-core tile has
-// 128 rows = two units: the SAME head of two consecutive windows (w0 = 2k, w1 = 2k+1).  A work item is a
-// window pair x a chunk of HC heads, so everything that depends only on the windows (token maps, the
-// great-circle distance rows) is fetched once per item and reused by its HC steps:
+// A "unit" is one (window, head): 49 tokens x head_dim 32.  The tensor-core tile has 128 rows = two units:
 //   S[128x128] = [Q_u0;Q_u1] . [K_u0;K_u1]^T      tcgen05.mma M=128 N=128 K=32; only the two diagonal 64x64
 //                                                 blocks are used (the tensor pipe is far from the bound)
-//   O[128x64]  = P[128x64 keys] . [V_u0 | V_u1]   tcgen05.mma M=128 N=64 K=64, P read from TMEM (bf16),
+//   O[128x64]  = P[128x64 keys] . [V_u0 | V_u1]   tcgen05.mma M=128 N=64 K=64, P read from TMEM (16-bit),
 //                                                 V consumed MN-major straight from its [key][dim] rows;
 //                                                 rows of unit u use output columns [32u, 32u+32)
-// Thread r owns tile row r (TMEM lane r): tcgen05.ld of its 49 logits, + d(i,j)*alpha[idx]+beta[idx]
-// (d from the fp16 distance table staged in shared memory, tables per head in shared memory), softmax in
-// registers (exp2, fp32), un-normalised bf16 P back to TMEM, finally O row * 1/sum stored with 128-bit
-// stores at the token's UN-shifted position.  q/k/v rows are gathered with cp.async (16 B) straight from the
-// un-shifted [B,H,W,3C] qkv tensor into the 64B-swizzled UMMA layout: pano shift with longitude wrap-around,
-// the odd-W zero column, window padding (padding tokens = qkv bias) and partition are address arithmetic
-// (psw::source_token).  q/k/v
-// buffers are double-buffered per CTA: the whole next step is prefetched while the S MMA of the current one runs,
-// the row's bias is computed in the same window; 4 CTAs per SM (TMEM 4 x 128 columns) overlap each other's
-// MMA / softmax / store phases.
+// Thread r owns tile row r (TMEM lane r): tcgen05.ld of its 49 logits, t = S * (scale * log2 e) + bias (every
+// additive term -- great-circle bias, relative-position bias, planar shift mask -- comes precomputed and already
+// multiplied by log2 e from psw_window_bias_full), row maximum, exp2, un-normalised 16-bit P back to TMEM, finally
+// the O row * 1/sum stored with 128-bit stores at the token's UN-shifted position.  q/k/v rows are gathered with
+// cp.async (16 B) straight from the un-shifted [B,H,W,3C] qkv tensor into the 64B-swizzled UMMA layout: pano shift
+// with longitude wrap-around, the odd-W zero column, window padding (padding tokens = qkv bias) and partition are
+// address arithmetic (psw::source_token).  q/k/v are double-buffered per CTA: the whole next step is prefetched
+// while the S MMA of the current one runs; 4 CTAs per SM (TMEM 4 x 128 columns) overlap each other's phases.
+//
+// Two schedules:
+//   window_attn_bi_kernel    (batches >= 4) the two units of a tile are the SAME window position and head of TWO
+//                            images; the token map and the thread's bias row are fetched once per unit of work and
+//                            reused for a chunk of image pairs
+//   window_attn_pair_kernel  (batches < 4)  two adjacent windows of one image per tile, one head per item
 //
 // Algorithmic HBM bytes per unit: 49 * 32 * 2 B * 4 (q, k, v read + o written) = 12,544 B.
 #include <cuda_fp16.h>
@@ -30,23 +31,32 @@
 
 namespace psw {
 
-int attn_debug_hc();          // diagnostics: force the heads-per-item choice (0 = heuristic)
-
+#ifdef PSW_DIAGNOSTICS
+constexpr bool kDiag = true;
+#else
+constexpr bool kDiag = false;
+#endif
 
 constexpr int AT_THREADS = 128;
 constexpr int AT_PART_BYTES = 128 * 64;            // 128 rows x 64 B (32 bf16), SWIZZLE_64B
 constexpr int AT_BUF_BYTES = 3 * AT_PART_BYTES;    // q, k, v
-constexpr int AT_HAV_PITCH = 56;                   // halfs per distance-table row (112 B = 7 x 16 B)
 constexpr int AT_TMEM_COLS = 128;
-constexpr int AT_P_COL = 0;                        // P (bf16x2 packed): TMEM columns [0, 32)
+constexpr int AT_P_COL = 0;                        // P (16-bit pairs): TMEM columns [0, 32)
 constexpr int AT_O_COL = 32;                       // O (fp32): TMEM columns [32, 96)
 constexpr int AT_SUM_COL = 96;                     // row sums of P (fp32, batch-innermost kernel): TMEM columns [96, 112)
-constexpr int AT_CTAS_PER_SM = 4;                 // 128 registers per thread (no spills), 4 x 128 TMEM columns
-constexpr int AT_TAB_PITCH = 39;                   // half2 (alpha, beta) words per table row: 13 used; 39 = 7 mod 32 makes
-                                                   // the row-per-lane lookups bank-conflict-free
-constexpr int AT_TAB_WORDS = 508;                  // 13 * 39 = 507 words per head, padded to a multiple of 4 (16 B)
+constexpr int AT_CTAS_PER_SM = 4;                  // 128 registers per thread (no spills), 4 x 128 TMEM columns
 constexpr int AT_FULL_CHUNKS = 13;                 // float4 chunks per bias row: 49 logits padded to 52
 constexpr float LOG2E = 1.4426950408889634f;
+
+// how exp2 of the shifted logits is evaluated and what the probabilities are stored as (A operand of the P.V MMA)
+enum : int {
+  AT_EXP_F32 = 0,      // ex2.approx.ftz.f32 per element, pairs packed to bf16x2
+  AT_EXP_BF16X2 = 1,   // (t - max) packed to bf16x2, ex2.approx.ftz.bf16x2: one MUFU op per PAIR, result is P
+  AT_EXP_F16X2 = 2     // (t - max) packed to f16x2, ex2.approx.f16x2; P is fp16 (kind::f16 MMA with A = f16, B = bf16)
+};
+#ifndef PSW_ATTN_EXP
+#define PSW_ATTN_EXP AT_EXP_F32
+#endif
 
 __device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
@@ -72,64 +82,85 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+// two exp2 per MUFU op: pack (lo, hi) to a 16-bit pair, evaluate, the result IS the packed probability pair
+__device__ __forceinline__ uint32_t exp2_pair_bf16(float lo, float hi) {
+  uint32_t x, y;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(hi), "f"(lo));
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t exp2_pair_f16(float lo, float hi) {
+  uint32_t x, y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(hi), "f"(lo));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+// kind::f16 instruction descriptor with independent A / B element formats (0 = f16, 1 = bf16), fp32 accumulate
+__host__ __device__ inline uint32_t umma_idesc_16(int M, int N, int a_fmt, int b_fmt, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= (uint32_t)(a_fmt & 7) << 7;
+  d |= (uint32_t)(b_fmt & 7) << 10;
+  d |= (uint32_t)(a_mn_major & 1) << 15;
+  d |= (uint32_t)(b_mn_major & 1) << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// Great-circle distance table: hav[win][i][j] = haversine22(uv_i, uv_j) for the 49 tokens of every window
-// of ONE image (it depends on the window position only, not on batch / head / weights), fp16, row pitch 56.
-// Built once per (H, W, shift) by the host and kept L2-resident; padding tokens sit at uv = (0, 0)
-// (reference :486-491, :344-347).  Formula and evaluation order: lzx/models/great_circle.py:82-86, fp32.
-// ---------------------------------------------------------------------------------------------------
-__global__ void hav_table_kernel(const float* __restrict__ uv, __half* __restrict__ table, WinGeom g) {
-  const int ws = g.ws, N = ws * ws;
-  __shared__ float su[64], sv[64], scv[64];
-  const int wi = blockIdx.x;
-  const int wr = wi / g.nWw, wc = wi - wr * g.nWw;
-  for (int t = threadIdx.x; t < N; t += blockDim.x) {
-    const int r = t / ws, c = t - r * ws;
-    const int s = source_token(g, wr * ws + r, wc * ws + c);
-    float uu = 0.f, vv = 0.f;
-    if (s >= 0) { uu = uv[2 * s]; vv = uv[2 * s + 1]; }
-    su[t] = uu; sv[t] = vv; scv[t] = cosf(vv);
-  }
-  __syncthreads();
-  __half* out = table + (size_t)wi * N * AT_HAV_PITCH;
-  for (int q = threadIdx.x; q < N * AT_HAV_PITCH; q += blockDim.x) {
-    const int i = q / AT_HAV_PITCH, j = q - i * AT_HAV_PITCH;
-    float d = 0.f;
-    if (j < N) {
-      const float sdv = sinf(0.5f * fabsf(sv[j] - sv[i]));
-      const float sdu = sinf(0.5f * (su[j] - su[i]));
-      const float a = sdv * sdv + (scv[j] * scv[i]) * (sdu * sdu);
-      d = asinf(sqrtf(fminf(a, 1.0f))) * 2.0f;
+// bias + softmax numerator of one row: sr = the 49 raw logits of TMEM, bias = the row's additive terms (x log2 e),
+// scale_l2 = scale * log2 e.  Writes the un-normalised probabilities as 16-bit pairs (key columns 49..63 zero) and, for
+// the fp32 schedule that needs it, returns their fp32 sum.  Rows that do not exist (tile rows 49..63 of a unit, the
+// second unit of an odd tail) are NOT zeroed: a row of P only feeds the same row of O, which is never stored.
+template <int EXPM, int N>
+__device__ __forceinline__ float softmax_row(const uint32_t (&sr)[N], const float* bias, float scale_l2, uint32_t (&pk)[32]) {
+  float t[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) t[j] = fmaf(__uint_as_float(sr[j]), scale_l2, bias[j]);
+  float mx = t[N - 1];
+#pragma unroll
+  for (int j = 0; j + 1 < N; j += 2) mx = fmax3(mx, t[j], t[j + 1]);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    uint32_t w = 0u;
+    if (2 * k < N) {
+      const float x0 = t[2 * k] - mx;
+      const float x1 = (2 * k + 1 < N) ? t[2 * k + 1] - mx : -INFINITY;
+      if constexpr (EXPM == AT_EXP_F32) {
+        const float p0 = fast_exp2(x0);
+        const float p1 = (2 * k + 1 < N) ? fast_exp2(x1) : 0.f;
+        sum += p0 + p1;
+        w = pack_bf16x2(p0, p1);
+      } else if constexpr (EXPM == AT_EXP_BF16X2) {
+        w = exp2_pair_bf16(x0, x1);
+      } else {
+        w = exp2_pair_f16(x0, x1);
+      }
     }
-    out[q] = __float2half_rn(d);
+    pk[k] = w;
   }
+  return sum;
 }
 
 struct AttnParams {
   const bf16* qkv;
   bf16* out;
-  const float* alpha;
-  const float* beta;
-  const __half2* tables;  // [heads][AT_TAB_WORDS] packed (alpha, beta) from psw_window_bias_tables
-  const float4* bias_full; // FULL kernels: [windows per image][heads][AT_FULL_CHUNKS][64 rows] x 4 fp32 from psw_window_bias_full
+  const float4* bias_full; // [windows per image][heads][AT_FULL_CHUNKS][64 rows] x 4 fp32 (x log2 e) from psw_window_bias_full
   const float* qkv_bias;
-  const __half* hav;      // [wpi][N][56] or nullptr (planar mode: d == 0)
-  const float* mask;
   WinGeom g;
   int B, C, heads;
-  int hc;                 // heads per work item (divides heads)
+  int hc;                 // pair kernel: heads per work item; batch-innermost kernel: image pairs per unit
   int n_windows;          // B * windows per image
-  int n_items;            // ceil(n_windows / 2) * (heads / hc)
-  float scale;
-  long long* dbg;         // diagnostics: per-phase cycle totals of CTA 0 (nullptr in production)
-  int mode;               // diagnostics: 0 = normal, 1 = memory skeleton (same gathers and stores, no MMA / softmax)
+  int n_items;            // work items / units
+  int nch;                // batch-innermost kernel: chunks per (window position, head)
+  uint32_t magic_heads, magic_nch, magic_nww;   // multiply-high reciprocals of heads / nch / windows per row (0 = divisor 1)
+  float scale_l2;         // scale * log2(e)
+  long long* dbg;         // diagnostics build: per-phase cycle totals of CTA 0 (nullptr otherwise)
+  int mode;               // diagnostics build: 0 normal, 1 memory skeleton, 2 no bias loads, 3 no q/k/v loads
 };
 
-// One pipeline step = one head of one window pair.
+// One pipeline step of the window-pair kernel = one head of one window pair.
 struct Step {
   int item;               // work item index (for range checks)
   int wp;                 // window pair: windows 2*wp, 2*wp + 1
@@ -138,26 +169,18 @@ struct Step {
   int n;                  // running step count of this CTA (parity selects the buffers)
 };
 
-// FULL: the whole additive bias of a (window, head) -- great-circle term, relative-position term and, in planar mode,
-// the shift mask -- comes precomputed from p.bias_full (psw_window_bias_full): 13 coalesced 16-byte loads per row
-// instead of ~300 instructions of table lookups per row and step.
-template <int WS, bool HAS_MASK, bool FULL>
+template <int WS, int EXPM>
 __global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
-window_attn_tc_kernel(const AttnParams p) {
+window_attn_pair_kernel(const AttnParams p) {
   constexpr int N = WS * WS;                     // tokens per window (<= 64)
-  constexpr int TW = 2 * WS - 1;                 // relative-position table width (13)
-  constexpr int TAB = TW * TW;
-  constexpr int TP = AT_TAB_PITCH;               // smem row pitch of the table: bank-conflict-free for row-per-lane reads
-  constexpr int TABS = AT_TAB_WORDS;             // half2 words per table slot
-  static_assert(N <= 64, "window too large for the 64-row unit tile");
-  static_assert(TP >= TW, "table pitch too small");
+  static_assert(N == 49, "TMEM row load below is written for 49 logits");
+  constexpr int P_FMT = EXPM == AT_EXP_F16X2 ? 0 : 1;
 
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B by OFFSETTING the __shared__ array (keeps the shared address space: LDS/STS, not generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* bufs = smem;                                                  // [2 stages][3][128 x 64 B]
-  __half2* tab = reinterpret_cast<__half2*>(bufs + 2 * AT_BUF_BYTES);    // [2 stages][TABS] packed (alpha, beta)
-  int* src = reinterpret_cast<int*>(tab + 2 * TABS);                     // [3 slots][2 units][64]: this, next, next-next pair
+  int* src = reinterpret_cast<int*>(bufs + 2 * AT_BUF_BYTES);            // [3 slots][2 units][64]: this, next, next-next pair
   uint64_t* bars = reinterpret_cast<uint64_t*>(src + 3 * 2 * 64);        // [2]: S ready, O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
@@ -177,10 +200,7 @@ window_attn_tc_kernel(const AttnParams p) {
     mbar_init(&bars[1], 1);
     mbar_fence_init();
   }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(AT_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  if (warp == 0) tmem_alloc<AT_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -226,7 +246,7 @@ window_attn_tc_kernel(const AttnParams p) {
     if (s.e + 1 < heads) { ++s.e; } else { s.e = 0; ++s.wp; }
     return s;
   };
-  // token maps of both windows of pair `wp` -> src[wp & 3] (thread = (unit, token)); entry = global token index
+  // token maps of both windows of pair `wp` -> src[wp % 3] (thread = (unit, token)); entry = global token index
   // b*H*W + h*W + w of the cell's source token, or -1 for a padding cell
   auto prep_src = [&](int wp) {
     const int w = 2 * wp + unit;
@@ -249,7 +269,7 @@ window_attn_tc_kernel(const AttnParams p) {
     const int row = (k >> 1) * 64 + t;
     ld_dst[k] = row * 64 + ((lc ^ ((row >> 1) & 3)) << 4);
   }
-  // gather all q/k/v rows and the per-head tables of step `st` into stage (st.n & 1)
+  // gather all q/k/v rows of step `st` into stage (st.n & 1)
   auto issue_loads = [&](const Step& st) {
     uint8_t* base = bufs + (st.n & 1) * AT_BUF_BYTES;
     const int* smap = src + (st.wp % 3) * 128;
@@ -272,8 +292,6 @@ window_attn_tc_kernel(const AttnParams p) {
         }
       }
     }
-    // per-head tables: one contiguous 2032-byte block, 127 x 16 B
-    if (!FULL && tid < TABS / 4) cp_async16(tab + (st.n & 1) * TABS + 4 * tid, p.tables + (size_t)st.e * TABS + 4 * tid);
   };
 
   Step cur = first_step(item_begin);
@@ -288,36 +306,27 @@ window_attn_tc_kernel(const AttnParams p) {
   }
   cp_async_commit();
 
-  uint4 hreg[AT_HAV_PITCH / 8];                            // my distance-table row (fp16), kept across the item's heads
-#pragma unroll
-  for (int k = 0; k < AT_HAV_PITCH / 8; ++k) hreg[k] = make_uint4(0, 0, 0, 0);
-  int hav_wp = -1;
-
-  // FULL: my row of the precomputed bias of a step, requested one step ahead (right after the previous softmax has
+  // my row of the precomputed bias of a step, requested one step ahead (right after the previous softmax has
   // consumed the registers) so the L2 latency hides behind the P.V MMA, the store and the next S MMA
-  float bfull[FULL ? 4 * AT_FULL_CHUNKS : 1];
+  float bfull[4 * AT_FULL_CHUNKS];
   auto load_bias = [&](const Step& st) {
-    if constexpr (FULL) {
-      const int w = 2 * st.wp + unit;
-      if (ti < N && w < p.n_windows && p.mode != 2) {        // mode 2 (diagnostics): bias loads skipped
-        const float4* brow = p.bias_full + ((size_t)(w % wpi) * heads + st.e) * (AT_FULL_CHUNKS * 64) + ti;
+    const int w = 2 * st.wp + unit;
+    if (ti < N && w < p.n_windows && !(kDiag && p.mode == 2)) {
+      const float4* brow = p.bias_full + ((size_t)(w % wpi) * heads + st.e) * (AT_FULL_CHUNKS * 64) + ti;
 #pragma unroll
-        for (int k = 0; k < AT_FULL_CHUNKS; ++k) {
-          const float4 b4 = __ldg(brow + k * 64);
-          bfull[4 * k] = b4.x; bfull[4 * k + 1] = b4.y; bfull[4 * k + 2] = b4.z; bfull[4 * k + 3] = b4.w;
-        }
+      for (int k = 0; k < AT_FULL_CHUNKS; ++k) {
+        const float4 b4 = __ldg(brow + k * 64);
+        bfull[4 * k] = b4.x; bfull[4 * k + 1] = b4.y; bfull[4 * k + 2] = b4.z; bfull[4 * k + 3] = b4.w;
       }
     }
   };
-  if constexpr (FULL) {
 #pragma unroll
-    for (int k = 0; k < 4 * AT_FULL_CHUNKS; ++k) bfull[k] = 0.f;
-    if (item_begin < item_end) load_bias(cur);
-  }
+  for (int k = 0; k < 4 * AT_FULL_CHUNKS; ++k) bfull[k] = 0.f;
+  if (item_begin < item_end) load_bias(cur);
 
   uint32_t par = 0;
   long long ph[6] = {0, 0, 0, 0, 0, 0};
-  const bool prof = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  const bool prof = kDiag && p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
   while (cur.item < item_end) {
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     if (prof) c0 = clock64();
@@ -325,14 +334,14 @@ window_attn_tc_kernel(const AttnParams p) {
     const bool has_next = nxt.item < item_end;
     const int my_w = 2 * cur.wp + unit;
     const bool row_valid = (ti < N) && (my_w < p.n_windows);
-    // ---- 1. this step's q/k/v + tables (requested one step ago) have landed; one barrier orders them, the
-    //         previous step's TMEM reads and the token maps prepared during the previous step
+    // ---- 1. this step's q/k/v (requested one step ago) have landed; one barrier orders them, the previous step's
+    //         TMEM reads and the token maps prepared during the previous step
     cp_async_wait<0>();
     fence_async_shared();
     __syncthreads();
 
     if (prof) c1 = clock64();
-    if (p.mode == 1) {
+    if (kDiag && p.mode == 1) {
       // memory skeleton: prefetch as usual, then copy my row's q chunk to the output position (64 B per row)
       if (has_next) issue_loads(nxt);
       cp_async_commit();
@@ -363,53 +372,19 @@ window_attn_tc_kernel(const AttnParams p) {
       umma_commit(&bars[0]);
     }
     // while the MMA runs: prefetch the WHOLE next step into the other stage (released by the previous step's PV
-    // MMA, which every thread has waited for) and fetch my distance row when the window pair changed
+    // MMA, which every thread has waited for)
     if (has_next) issue_loads(nxt);
     cp_async_commit();
-    if (!FULL && p.hav != nullptr && hav_wp != cur.wp) {
-      hav_wp = cur.wp;
-      if (row_valid) {
-        const uint4* grow = reinterpret_cast<const uint4*>(p.hav + ((size_t)(my_w % wpi) * N + ti) * AT_HAV_PITCH);
-#pragma unroll
-        for (int k = 0; k < AT_HAV_PITCH / 8; ++k) hreg[k] = __ldg(grow + k);
-      }
-    }
-    // still inside the MMA window: my row's bias d(i,j) * alpha[idx] + beta[idx] (+ mask) — independent of S.
-    // Table entries of one key row are fetched as a batch of 7 before they are consumed (LDS latency overlaps).
-    float bia[FULL ? 1 : N];
-    if constexpr (FULL) {
-      bia[0] = 0.f;
-    } else {
-      const __half2* trow = tab + (cur.n & 1) * TABS + (ri + WS - 1) * TP + (ci + WS - 1);
-      const float* mrow = nullptr;
-      if constexpr (HAS_MASK) mrow = p.mask + ((int64_t)((my_w < p.n_windows ? my_w : 0) % wpi) * N + ic) * N;
-      const uint32_t* hw = reinterpret_cast<const uint32_t*>(hreg);
-#pragma unroll
-      for (int rj = 0; rj < WS; ++rj) {
-        __half2 ab[WS];
-#pragma unroll
-        for (int cj = 0; cj < WS; ++cj) ab[cj] = trow[-(rj * TP + cj)];
-#pragma unroll
-        for (int cj = 0; cj < WS; ++cj) {
-          const int j = rj * WS + cj;
-          const __half2 hh = *reinterpret_cast<const __half2*>(&hw[j >> 1]);
-          const float hv = (j & 1) ? __high2float(hh) : __low2float(hh);
-          bia[j] = fmaf(hv, __low2float(ab[cj]), __high2float(ab[cj]));
-          if constexpr (HAS_MASK) bia[j] += __ldg(mrow + j);
-        }
-      }
-    }
     mbar_wait(&bars[0], par);
     tc_fence_after();
 
     if (prof) c2 = clock64();
     // ---- 3. bias + softmax on my row
-    float sum = 1.f;
+    float sum;
     {
       uint32_t sr[N];
       const uint32_t s_addr = tmem_base + lane_base + (uint32_t)(unit * 64);
       {
-        static_assert(N == 49, "TMEM row load below is written for 49 logits");
         uint32_t t32[32], t16[16], t1;
         tmem_ld_x32(s_addr, t32);
         tmem_ld_x16(s_addr + 32, t16);
@@ -421,27 +396,12 @@ window_attn_tc_kernel(const AttnParams p) {
         for (int k = 0; k < 16; ++k) sr[32 + k] = t16[k];
         sr[48] = t1;
       }
-      float t[N];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < N; ++j) {
-        t[j] = fmaf(__uint_as_float(sr[j]), p.scale, FULL ? bfull[j] : bia[j]);
-        mx = fmaxf(mx, t[j]);
-      }
-      const float mneg = -mx * LOG2E;
-      sum = 0.f;
       uint32_t pk[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        float p0 = 0.f, p1 = 0.f;
-        if (2 * k < N) { p0 = fast_exp2(fmaf(t[2 * k], LOG2E, mneg)); sum += p0; }
-        if (2 * k + 1 < N) { p1 = fast_exp2(fmaf(t[2 * k + 1], LOG2E, mneg)); sum += p1; }
-        pk[k] = row_valid ? pack_bf16x2(p0, p1) : 0u;
-      }
+      sum = softmax_row<AT_EXP_F32, N>(sr, bfull, p.scale_l2, pk);   // fp32 sums: this schedule has no sum MMA
       tmem_st_x32(tmem_base + lane_base + AT_P_COL, pk);
       tmem_st_wait();
     }
-    if (FULL && has_next) load_bias(nxt);                  // the bias registers are free again
+    if (has_next) load_bias(nxt);                          // the bias registers are free again
     tc_fence_before();
     __syncthreads();
 
@@ -497,62 +457,56 @@ window_attn_tc_kernel(const AttnParams p) {
   }
   if (prof)
     for (int k = 0; k < 6; ++k) p.dbg[k] = ph[k];
+  (void)P_FMT;
 
   cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(AT_TMEM_COLS) : "memory");
+    tmem_dealloc<AT_TMEM_COLS>(tmem_base);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Batch-innermost variant (production path for batches of 4 images or more, FULL bias only).
+// Batch-innermost schedule (production path for batches of 4 images or more).
 // The 128-row tile holds the SAME window position and head of TWO images; a work item is (window position, head)
 // and its steps walk over the image pairs.  Everything that depends on the geometry or the head only -- the token
 // map of the window and the thread's 49-entry bias row -- is fetched once per item and kept (shared memory /
 // registers) for all of its steps, so a step is nothing but the q/k/v gather, the two MMAs, the softmax and the
-// store.  An item is cut into units of p.hc image pairs (chosen by the host for balance); units are numbered (window, chunk, head) with the
-// head fastest and CTA c runs units c, c + grid, c + 2 grid, ...: at any moment the resident CTAs work on ALL heads of
-// the same windows and images, so the head slices sharing a 128-byte line of the qkv rows meet in L2 (a contiguous
-// range per CTA separates them by ~40 us and doubles the DRAM reads -- measured).
+// store.  An item is cut into units of p.hc image pairs (chosen by the host for balance); units are numbered
+// (window, chunk, head) with the head fastest and CTA c runs units c, c + grid, c + 2 grid, ...: at any moment the
+// resident CTAs work on ALL heads of the same windows and images, so the head slices sharing a 128-byte line of the
+// qkv rows meet in L2 (a contiguous range per CTA separates them by ~40 us and doubles the DRAM reads -- measured).
 // ---------------------------------------------------------------------------------------------------
-struct BiStep {
+// Unit iterator of the batch-innermost schedule.  All threads of a CTA hold the same state; advancing costs a handful
+// of instructions (the unit index is decoded with multiply-high "magic" divisions only when a unit ends).
+struct BiIt {
   int u;                  // unit index: (window position * chunks + chunk) * heads + head
-  int item;               // window position * heads + head
+  int e;                  // head
+  int wi;                 // window position inside an image
   int bp;                 // image pair: images 2*bp, 2*bp + 1
   int bp_end;             // end of the unit's image-pair range
-  int n;                  // running step count of this CTA (parity selects the q/k/v stage)
-  int ic;                 // running unit count of this CTA (parity selects the token-map slot)
+  int ic;                 // running unit count of this CTA (parity selects the per-unit shared-memory slot)
 };
 
-// GATHER: the q/k/v rows are fetched by TMA (cp.async.bulk.tensor tile::gather4: four 64-byte token rows per
-// instruction, written with the 64-byte swizzle the MMA descriptors expect; tools/probes/tma_gather4_probe.cu) instead
-// of per-thread cp.async: 78 instructions per step, no address arithmetic per 16-byte chunk, no proxy fence, and only
-// the MMA-issuing thread waits for the data.  Needs the qkv tensor to carry one extra row (index B*H*W) holding the
-// bf16 qkv bias, which padding cells gather (psw_window_attn_full_fwd: qkv_rows == B*H*W + 1).
-__device__ __forceinline__ void tma_gather4(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int col, int r0, int r1,
-                                            int r2, int r3) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
-}
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic) { return magic ? __umulhi(x, magic) : x; }
 
-template <int WS, bool GATHER>
+template <int WS, int EXPM>
 __global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
-window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap map_qkv) {
+window_attn_bi_kernel(const AttnParams p) {
   constexpr int N = WS * WS;
   static_assert(N == 49, "TMEM row load below is written for 49 logits");
+  constexpr int P_FMT = EXPM == AT_EXP_F16X2 ? 0 : 1;      // element format of P: 0 = f16, 1 = bf16
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* bufs = smem;                                                  // [2 stages][3][128 x 64 B]
-  int* src = reinterpret_cast<int*>(bufs + 2 * AT_BUF_BYTES);            // [2 item slots][64]: token index in the image or -1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(src + 2 * 64);            // [2]: S ready, O ready
+  int* src = reinterpret_cast<int*>(bufs + 2 * AT_BUF_BYTES);            // [2 unit slots][64]: token index in the image or -1
+  int* soff = src + 2 * 64;                                              // [2 unit slots][64]: token index * 3C (element offset of the qkv row)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(soff + 2 * 64);           // [2]: S ready, O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  uint8_t* ones = bufs + 2 * AT_BUF_BYTES + 1024;                        // 1 KB of bf16 1.0: B operand of the row-sum MMA
-  uint64_t* full = reinterpret_cast<uint64_t*>(tmem_slot + 2);           // [2] GATHER: q/k/v of a stage have landed
-  uint4* padrow = reinterpret_cast<uint4*>(bufs + 2 * AT_BUF_BYTES + 2048); // [2 item slots][3][4]: bf16 qkv bias of the unit's head
+  uint8_t* ones = bufs + 2 * AT_BUF_BYTES + 2048;                        // 1 KB of bf16 1.0: B operand of the row-sum MMA
+  uint4* padrow = reinterpret_cast<uint4*>(bufs + 2 * AT_BUF_BYTES + 3072); // [2 unit slots][3][4]: bf16 qkv bias of the unit's head
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -560,6 +514,7 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
   const WinGeom g = p.g;
   const int64_t HW = (int64_t)g.H * g.W;
   const int BP = (p.B + 1) / 2;                            // steps per item
+  const int G = gridDim.x;
 
   for (int i = tid; i < 2 * AT_BUF_BYTES / 16; i += AT_THREADS)
     reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0, 0, 0, 0);          // padding rows must stay finite
@@ -567,16 +522,9 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
-    if (GATHER) tma_prefetch_desc(&map_qkv);
     mbar_fence_init();
   }
-  if (GATHER) fence_async_shared();                        // zero-filled stages / ones tile vs. the async proxy
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(AT_TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
+  if (warp == 0) tmem_alloc<AT_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -594,7 +542,7 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
 
   const int n_units = p.n_items;                           // (window positions) x chunks x heads
   const int CH = p.hc;                                     // image pairs per unit
-  const int NCH = (BP + CH - 1) / CH;
+  const int NCH = p.nch;                                   // chunks per (window position, head)
 
   const int unit = tid >> 6;                               // warp-uniform: which image of the pair
   const int ti = tid & 63;
@@ -603,108 +551,76 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
   const int lc = tid & 3;
   const int lt0 = tid >> 2;
 
-  auto decode = [&](BiStep& st) {                          // unit index -> item and image-pair range
-    const int e = st.u % heads;
-    const int wc = st.u / heads;
-    const int chunk = wc % NCH;
-    st.item = (wc / NCH) * heads + e;
-    st.bp = chunk * CH;
-    st.bp_end = st.bp + CH < BP ? st.bp + CH : BP;
+  auto decode = [&](BiIt& it) {                            // unit index -> head, window position, image-pair range
+    const uint32_t wc = fast_div((uint32_t)it.u, p.magic_heads);
+    it.e = it.u - (int)wc * heads;
+    const uint32_t w = fast_div(wc, p.magic_nch);
+    it.wi = (int)w;
+    it.bp = ((int)wc - (int)w * NCH) * CH;
+    it.bp_end = it.bp + CH < BP ? it.bp + CH : BP;
   };
-  auto first_step = [&](int u) {
-    BiStep st;
-    st.u = u; st.n = 0; st.ic = 0;
-    decode(st);
-    return st;
+  auto advance = [&](BiIt& it) {
+    if (++it.bp < it.bp_end) return;
+    it.u += G;
+    ++it.ic;
+    if (it.u < n_units) decode(it);
   };
-  auto next_step = [&](BiStep st) {
-    ++st.n;
-    if (++st.bp == st.bp_end) {
-      st.u += gridDim.x;
-      ++st.ic;
-      if (st.u < n_units) decode(st);
-    }
-    return st;
-  };
-  // token map of the item's window position -> src[ic & 1] (threads 0..63)
-  auto prep_item = [&](const BiStep& st) {
+  // per-unit data -> shared-memory slot (ic & 1): token map of the window position (threads 0..63) and the head's
+  // slice of the bf16 qkv bias for padding cells (threads 64..75)
+  auto prep_item = [&](const BiIt& it) {
     if (tid < 64) {
       int t = -1;
       if (tid < N) {
-        const int wi = st.item / heads;
-        const int wr = wi / g.nWw, wc = wi - wr * g.nWw;
+        const int wr = (int)fast_div((uint32_t)it.wi, p.magic_nww), wc = it.wi - wr * g.nWw;
         t = source_token(g, wr * WS + ri, wc * WS + ci);
       }
-      src[(st.ic & 1) * 64 + tid] = t;
-    } else if (tid < 76) {                                 // the unit's head slice of the bf16 qkv bias: [q|k|v][4 x 16 B]
+      src[(it.ic & 1) * 64 + tid] = t;
+      soff[(it.ic & 1) * 64 + tid] = t * C3;
+    } else if (tid < 76) {                                 // [q|k|v][4 x 16 B]
       const int j = tid - 64;
-      padrow[(st.ic & 1) * 12 + j] = bias_chunk((j >> 2) * C + (st.item % heads) * 32 + (j & 3) * 8);
+      padrow[(it.ic & 1) * 12 + j] = bias_chunk((j >> 2) * C + it.e * 32 + (j & 3) * 8);
     }
   };
-  int ld_t[2], ld_dst[4];
+  // loader role of this thread: 16-byte chunk lc of tokens lt0 and lt0 + 32 of both images
+  const bool ld_ok1 = lt0 + 32 < N;                        // token lt0 (< 32) always exists; lt0 + 32 only below 49
+  uint32_t ld_dst[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int t = lt0 + 32 * (k & 1);
-    if (k < 2) ld_t[k] = t < N ? t : -1;
-    const int row = (k >> 1) * 64 + t;
-    ld_dst[k] = row * 64 + ((lc ^ ((row >> 1) & 3)) << 4);
+    const int row = (k >> 1) * 64 + lt0 + 32 * (k & 1);
+    ld_dst[k] = (uint32_t)(row * 64 + ((lc ^ ((row >> 1) & 3)) << 4));
   }
-  // GATHER loader role: thread j < 78 fetches token slots 4*grp .. 4*grp+3 of image `gu` for part `gpart` (q / k / v)
-  const int gpart = tid / 26, grem = tid - gpart * 26;
-  const int gu = grem / 13, ggrp = grem - gu * 13;
-  const int bias_row = p.B * (int)HW;                      // the extra row of the qkv tensor: bf16 qkv bias
-  auto issue_loads = [&](const BiStep& st) {
-    if constexpr (GATHER) {
-      uint64_t* fb = &full[st.n & 1];
-      if (tid == 0) mbar_expect_tx(fb, 78 * 256);
-      if (tid < 78) {
-        const int4 t4 = *reinterpret_cast<const int4*>(src + (st.ic & 1) * 64 + 4 * ggrp);   // slots >= 49 hold -1
-        const int b = 2 * st.bp + gu;
-        const int base_row = b * (int)HW;
-        const bool bv = b < p.B;
-        const int r0 = (bv && t4.x >= 0) ? base_row + t4.x : bias_row;
-        const int r1 = (bv && t4.y >= 0) ? base_row + t4.y : bias_row;
-        const int r2 = (bv && t4.z >= 0) ? base_row + t4.z : bias_row;
-        const int r3 = (bv && t4.w >= 0) ? base_row + t4.w : bias_row;
-        uint8_t* dst = bufs + (st.n & 1) * AT_BUF_BYTES + gpart * AT_PART_BYTES + (gu * 64 + 4 * ggrp) * 64;
-        tma_gather4(dst, &map_qkv, fb, gpart * C + (st.item % heads) * 32, r0, r1, r2, r3);
-      }
-      return;
-    }
-    uint8_t* base = bufs + (st.n & 1) * AT_BUF_BYTES;
-    const int* smap = src + (st.ic & 1) * 64;
-    const int e = st.item % heads;
-    const bf16* gq = p.qkv + e * 32 + lc * 8;
-    const int bch = e * 32 + lc * 8;
+  const int64_t img_stride = HW * C3;                      // elements per image of the qkv tensor
+  auto issue_loads = [&](const BiIt& it, int stage) {
+    uint8_t* base = bufs + stage * AT_BUF_BYTES;
+    const int* so = soff + (it.ic & 1) * 64;
+    const int o0 = so[lt0];
+    const int o1 = ld_ok1 ? so[lt0 + 32] : 0;
+    const bf16* g0 = p.qkv + (int64_t)(2 * it.bp) * img_stride + it.e * 32 + lc * 8;
+    const bool img1 = 2 * it.bp + 1 < p.B;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int b = 2 * st.bp + (k >> 1);
-      if (ld_t[k & 1] >= 0 && b < p.B) {
-        const int t = smap[ld_t[k & 1]];
-        uint8_t* dst = base + ld_dst[k];
-        if (t >= 0) {
-          const bf16* grow = gq + ((int64_t)b * HW + t) * C3;
-          cp_async16(dst, grow);
-          cp_async16(dst + AT_PART_BYTES, grow + C);
-          cp_async16(dst + 2 * AT_PART_BYTES, grow + 2 * C);
-        } else if (p.mode == 4) {                          // diagnostics: padding cells straight from the fp32 bias
-          *reinterpret_cast<uint4*>(dst) = bias_chunk(bch);
-          *reinterpret_cast<uint4*>(dst + AT_PART_BYTES) = bias_chunk(bch + C);
-          *reinterpret_cast<uint4*>(dst + 2 * AT_PART_BYTES) = bias_chunk(bch + 2 * C);
-        } else {                                           // padding cell: q/k/v = bias (staged per unit by prep_item)
-          const uint4* pr = padrow + (st.ic & 1) * 12 + lc;
-          *reinterpret_cast<uint4*>(dst) = pr[0];
-          *reinterpret_cast<uint4*>(dst + AT_PART_BYTES) = pr[4];
-          *reinterpret_cast<uint4*>(dst + 2 * AT_PART_BYTES) = pr[8];
-        }
+      if ((k & 1) && !ld_ok1) continue;
+      if ((k >> 1) && !img1) continue;
+      const int o = (k & 1) ? o1 : o0;
+      uint8_t* dst = base + ld_dst[k];
+      if (o >= 0) {
+        const bf16* grow = g0 + ((k >> 1) ? img_stride : 0) + o;
+        cp_async16(dst, grow);
+        cp_async16(dst + AT_PART_BYTES, grow + C);
+        cp_async16(dst + 2 * AT_PART_BYTES, grow + 2 * C);
+      } else {                                             // padding cell: q/k/v = bias (staged per unit by prep_item)
+        const uint4* pr = padrow + (it.ic & 1) * 12 + lc;
+        *reinterpret_cast<uint4*>(dst) = pr[0];
+        *reinterpret_cast<uint4*>(dst + AT_PART_BYTES) = pr[4];
+        *reinterpret_cast<uint4*>(dst + 2 * AT_PART_BYTES) = pr[8];
       }
     }
   };
-  // my row of the item's precomputed bias: [window][head][chunk][row] float4
+  // my row of the unit's precomputed bias: [window][head][chunk][row] float4
   float bias[4 * AT_FULL_CHUNKS];
-  auto load_bias = [&](const BiStep& st) {
-    if (ti < N && p.mode != 2) {
-      const float4* brow = p.bias_full + (size_t)st.item * (AT_FULL_CHUNKS * 64) + ti;
+  auto load_bias = [&](const BiIt& it) {
+    if (ti < N && !(kDiag && p.mode == 2)) {
+      const float4* brow = p.bias_full + ((size_t)it.wi * heads + it.e) * (AT_FULL_CHUNKS * 64) + ti;
 #pragma unroll
       for (int k = 0; k < AT_FULL_CHUNKS; ++k) {
         const float4 b4 = __ldg(brow + k * 64);
@@ -715,39 +631,40 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
 #pragma unroll
   for (int k = 0; k < 4 * AT_FULL_CHUNKS; ++k) bias[k] = 0.f;
 
-  BiStep cur = first_step(blockIdx.x);
+  // software pipeline over steps: cur (computed now), nxt (its q/k/v are in flight), nn (its unit data is prepared)
+  BiIt cur, nxt, nn;
+  cur.u = blockIdx.x; cur.ic = 0; cur.e = 0; cur.wi = 0; cur.bp = 0; cur.bp_end = 0;
+  if (cur.u < n_units) decode(cur);
+  nxt = cur;
+  advance(nxt);
+  nn = nxt;
+  advance(nn);
   if (cur.u < n_units) {
     prep_item(cur);
-    const BiStep n1 = next_step(cur);
-    if (n1.u < n_units && n1.ic != cur.ic) prep_item(n1);
+    if (nxt.u < n_units && nxt.ic != cur.ic) prep_item(nxt);
     __syncthreads();
-    issue_loads(cur);
+    issue_loads(cur, 0);
     load_bias(cur);
   }
   cp_async_commit();
 
   uint32_t par = 0;
   long long ph[6] = {0, 0, 0, 0, 0, 0};
-  const bool prof = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+  const bool prof = kDiag && p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
   while (cur.u < n_units) {
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     if (prof) c0 = clock64();
-    const BiStep nxt = next_step(cur);
     const bool has_next = nxt.u < n_units;
     const int my_b = 2 * cur.bp + unit;
-    const bool row_valid = (ti < N) && (my_b < p.B);
-    const int e = cur.item % heads;
     // ---- 1. this step's q/k/v (requested one step ago) have landed
-    if constexpr (!GATHER) {
-      cp_async_wait<0>();
-      fence_async_shared();
-    }
+    cp_async_wait<0>();
+    fence_async_shared();
     __syncthreads();
+    const int ts = src[(cur.ic & 1) * 64 + ic];            // my token (read now: the slot may be re-used for `nn` below)
     if (prof) c1 = clock64();
     // ---- 2. S = Q . K^T (both images at once, block diagonal)
-    const uint32_t sq = smem_u32(bufs + (cur.n & 1) * AT_BUF_BYTES);
+    const uint32_t sq = smem_u32(bufs + (par & 1) * AT_BUF_BYTES);
     if (tid == 0) {
-      if constexpr (GATHER) mbar_wait(&full[cur.n & 1], (uint32_t)(cur.n >> 1) & 1);
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
       const uint64_t dq = umma_smem_desc(sq, 16, 512, UMMA_SWIZZLE_64B);
@@ -756,7 +673,7 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
       umma_ss(tmem_base, dq + 2, dk + 2, idesc, 1);
       umma_commit(&bars[0]);
     }
-    if (has_next && p.mode != 3) issue_loads(nxt);         // whole next step into the other stage (mode 3: diagnostics, no loads)
+    if (has_next && !(kDiag && p.mode == 3)) issue_loads(nxt, (par & 1) ^ 1);   // whole next step into the other stage
     cp_async_commit();
     mbar_wait(&bars[0], par);
     tc_fence_after();
@@ -777,21 +694,8 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
         for (int k = 0; k < 16; ++k) sr[32 + k] = t16[k];
         sr[48] = t1;
       }
-      float t[N];
-#pragma unroll
-      for (int j = 0; j < N; ++j) t[j] = fmaf(__uint_as_float(sr[j]), p.scale, bias[j]);
-      float mx = t[N - 1];
-#pragma unroll
-      for (int j = 0; j + 1 < N; j += 2) mx = fmax3(mx, t[j], t[j + 1]);
-      const float mneg = -mx * LOG2E;
       uint32_t pk[32];                                     // the row sum comes from the tensor core (P . ones)
-#pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        float p0 = 0.f, p1 = 0.f;
-        if (2 * k < N) p0 = fast_exp2(fmaf(t[2 * k], LOG2E, mneg));
-        if (2 * k + 1 < N) p1 = fast_exp2(fmaf(t[2 * k + 1], LOG2E, mneg));
-        pk[k] = row_valid ? pack_bf16x2(p0, p1) : 0u;
-      }
+      (void)softmax_row<EXPM, N>(sr, bias, p.scale_l2, pk);
       tmem_st_x32(tmem_base + lane_base + AT_P_COL, pk);
       tmem_st_wait();
     }
@@ -802,8 +706,8 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
     // ---- 4. O = P . [V_img0 | V_img1]
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);
-      const uint32_t idesc1 = umma_idesc_bf16(128, 16, 0, 1);    // row sums: P . ones[keys][16]
+      const uint32_t idesc = umma_idesc_16(128, 64, P_FMT, 1, 0, 1);
+      const uint32_t idesc1 = umma_idesc_16(128, 16, P_FMT, 1, 0, 1);    // row sums: P . ones[keys][16]
       const uint32_t sv = sq + 2 * AT_PART_BYTES;
       const uint64_t d1 = umma_smem_desc(smem_u32(ones), 4096, 512, UMMA_SWIZZLE_64B);
 #pragma unroll
@@ -814,11 +718,9 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
       }
       umma_commit(&bars[1]);
     }
-    // while the MMA runs: token map of the item after next's first step (its loader runs after the next barriers)
-    if (has_next) {
-      const BiStep nn = next_step(nxt);
-      if (nn.u < n_units && nn.ic != nxt.ic) prep_item(nn);
-    }
+    // while the MMA runs: unit data of the step after next when it starts a new unit (its loader runs after the
+    // next barriers)
+    if (nn.u < n_units && nn.ic != nxt.ic) prep_item(nn);
     mbar_wait(&bars[1], par);
     tc_fence_after();
     if (prof) c4 = clock64();
@@ -828,10 +730,9 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
       tmem_ld_x32(tmem_base + lane_base + AT_O_COL + (uint32_t)(unit * 32), orow);
       tmem_ld_x1(tmem_base + lane_base + AT_SUM_COL, osum);
       tmem_ld_wait();
-      const int ts = src[(cur.ic & 1) * 64 + ic];
-      if (row_valid && ts >= 0) {
+      if (ti < N && my_b < p.B && ts >= 0) {
         const float inv = 1.0f / __uint_as_float(osum);
-        uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)my_b * HW + ts) * C + e * 32);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)my_b * HW + ts) * C + cur.e * 32);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 v;
@@ -850,6 +751,8 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
     }
     par ^= 1;
     cur = nxt;
+    nxt = nn;
+    advance(nn);
   }
   if (prof)
     for (int k = 0; k < 6; ++k) p.dbg[k] = ph[k];
@@ -859,45 +762,26 @@ window_attn_bi_kernel(const AttnParams p, const __grid_constant__ CUtensorMap ma
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(AT_TMEM_COLS) : "memory");
+    tmem_dealloc<AT_TMEM_COLS>(tmem_base);
   }
 }
 
-static size_t attn_tc_smem_bytes(int ws, int C) {
-  const int TW = 2 * ws - 1;
+static size_t attn_tc_smem_bytes() {
   size_t b = 1024;                                   // alignment slack
   b += 2 * AT_BUF_BYTES;
-  b += (size_t)2 * AT_TAB_WORDS * 4;
-  (void)TW;
-  b += 3 * 2 * 64 * 4;
-  b += 2 * 8 + 16;
-  (void)C;
+  b += 3072 + 512;                                   // token maps + row offsets / barriers / TMEM slot (2 KB), ones tile (1 KB), padding rows
   // keep the CTA count per SM at AT_CTAS_PER_SM (register budget 65536 / (3 * 128) = 170 per thread)
   const size_t floor_bytes = (size_t)(233472 / (AT_CTAS_PER_SM + 1)) - 1024 + 16;
   return b < floor_bytes ? floor_bytes : b;
 }
 
-// (alpha, beta)[idx][head] fp32 -> tables[head][AT_TAB_WORDS] half2 (alpha, beta): entry (r, c) of the (2w-1)^2
-// table sits at word r * AT_TAB_PITCH + c — exactly the shared-memory image the attention kernel copies per head
-__global__ void bias_tables_kernel(const float* __restrict__ alpha, const float* __restrict__ beta,
-                                   __half2* __restrict__ out, int heads, int tw) {
-  const int n = heads * AT_TAB_WORDS;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int e = i / AT_TAB_WORDS;
-    const int o = i - e * AT_TAB_WORDS;
-    const int r = o / AT_TAB_PITCH, c = o - r * AT_TAB_PITCH;
-    float a = 0.f, b = 0.f;
-    if (r < tw && c < tw) { a = alpha[(r * tw + c) * heads + e]; b = beta[(r * tw + c) * heads + e]; }
-    out[i] = __floats2half2_rn(a, b);
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Full additive bias of every (window of one image, head): bias[i][j] = hav(uv_i, uv_j) * alpha[idx(i,j)][head] +
-// beta[idx(i,j)][head] (+ mask[window][i][j] in planar mode), fp32, laid out for the kernel's row-per-lane reads:
-// [window][head][chunk k = j / 4][row i (64)][j % 4].  Depends on the geometry and on the block's alpha / beta, not
-// on the batch: built once per block and resolution, read (L2-resident) by every image.  Same formulas and fp32
-// evaluation order as the parity kernel (lzx/models/great_circle.py:82-86, reference :241-272).
+// beta[idx(i,j)][head] (+ mask[window][i][j] in planar mode), fp32, MULTIPLIED BY log2(e) (the kernels evaluate
+// softmax with exp2), laid out for the kernels' row-per-lane reads: [window][head][chunk k = j / 4][row i (64)][j % 4].
+// Depends on the geometry and on the block's alpha / beta, not on the batch: built once per block and resolution,
+// read (L2-resident) by every image.  Same formulas and fp32 evaluation order as the parity kernel
+// (lzx/models/great_circle.py:82-86, reference :241-272).
 // ---------------------------------------------------------------------------------------------------
 __global__ void bias_full_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ uv,
                                  const float* __restrict__ mask, float* __restrict__ table, WinGeom g, int heads) {
@@ -929,6 +813,7 @@ __global__ void bias_full_kernel(const float* __restrict__ alpha, const float* _
       const int idx = (ri - rj + ws - 1) * tw + (ci - cj + ws - 1);
       b = fmaf(d, alpha[idx * heads + e], beta[idx * heads + e]);
       if (mask != nullptr) b += mask[((size_t)wi * N + i) * N + j];
+      b *= LOG2E;
     }
     out[q] = b;
   }
@@ -943,98 +828,73 @@ int window_bias_full(const float* alpha, const float* beta, const float* uv, con
   return launch_status("bias_full_kernel");
 }
 
-int window_bias_tables(const float* alpha, const float* beta, void* tables, int heads, int window, cudaStream_t st) {
-  const int tw = 2 * window - 1;
-  PSW_REQUIRE(tw * AT_TAB_PITCH <= AT_TAB_WORDS, PSW_ERR_UNSUPPORTED, "psw_window_bias_tables: window %d too large", window);
-  const int n = heads * AT_TAB_WORDS;
-  bias_tables_kernel<<<(n + 255) / 256, 256, 0, st>>>(alpha, beta, (__half2*)tables, heads, tw);
-  return launch_status("bias_tables_kernel");
-}
-
-int window_attn_tc(const bf16* qkv, bf16* out, const float* alpha, const float* beta, const void* tables,
-                   const float* qkv_bias, const void* hav_table, const float* mask, const void* bias_full,
-                   bool bias_row_present, int B, int H, int W, int C, int heads, int window, int shift, int pano, float scale,
-                   long long* dbg, int mode, cudaStream_t st) {
-  PSW_REQUIRE(window == 7, PSW_ERR_UNSUPPORTED,
-              "psw_window_attn_fwd(bf16): the tcgen05 kernel is instantiated for window 7 (every shipped PanoSwin config); got %d",
-              window);
-  PSW_REQUIRE(bias_full != nullptr || tables != nullptr, PSW_ERR_BAD_ARG,
-              "psw_window_attn_fwd(bf16): needs the per-head bias tables (psw_window_bias_tables)");
-  PSW_REQUIRE(bias_full != nullptr || !pano || hav_table, PSW_ERR_BAD_ARG,
-              "psw_window_attn_fwd(bf16): pano mode needs the great-circle table (psw_window_hav_table)");
-  AttnParams p;
-  p.qkv = qkv; p.out = out; p.alpha = alpha; p.beta = beta; p.qkv_bias = qkv_bias;
-  p.tables = (const __half2*)tables;
-  p.bias_full = (const float4*)bias_full;
-  p.hav = pano ? (const __half*)hav_table : nullptr;
-  p.mask = mask;
-  p.g = make_geom(H, W, window, shift, pano);
-  p.B = B; p.C = C; p.heads = heads; p.scale = scale; p.dbg = dbg; p.mode = mode;
-  p.n_windows = B * p.g.nWh * p.g.nWw;
-  // heads per work item: one.  Sharing a window pair's token maps / distance rows between the heads of a wider
-  // item saves little (measured: equal at stage 0), while single-head items balance the small launches of the late
-  // stages better (items are dealt out in contiguous ranges: a CTA runs ceil(items / CTAs) of them; -10% at stage 3).
-  p.hc = 1;
-  if (attn_debug_hc() > 0 && heads % attn_debug_hc() == 0) p.hc = attn_debug_hc();
-  p.n_items = ((p.n_windows + 1) / 2) * (heads / p.hc);
-  const size_t smem = attn_tc_smem_bytes(window, C);
-  PSW_REQUIRE(smem <= 220 * 1024, PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd(bf16): C=%d too large", C);
-  PSW_REQUIRE((int64_t)B * H * W < (1ll << 31) / 1, PSW_ERR_UNSUPPORTED, "psw_window_attn_fwd(bf16): too many tokens");
-  const bool batch_inner = bias_full != nullptr && B >= 4 && attn_debug_hc() != 15 && mode != 1;
-  if (batch_inner) {
-    // image pairs per unit: as many as possible (the bias row and the token map are fetched once per unit) while the
-    // units still spread evenly over the resident CTAs (CTA c runs units c, c + grid, ...)
-    const int bp_total = (B + 1) / 2, ctas = num_sms() * AT_CTAS_PER_SM;
-    const int wh = p.g.nWh * p.g.nWw * heads;
-    double best = -1.0;
-    p.hc = 1;
-    for (int ch = 4; ch >= 1; ch >>= 1) {                 // measured: 8 is not better than 4 where both balance
-      const int64_t units = (int64_t)wh * ((bp_total + ch - 1) / ch);
-      const double steps_max = (double)((units + ctas - 1) / ctas) * ch;             // steps of the busiest CTA (upper bound)
-      const double eff = (double)wh * bp_total / ctas / steps_max;
-      const int forced = attn_debug_hc();
-      if (forced ? ch == forced : (best < 0.9 && eff > best + 1e-9)) { best = eff; p.hc = ch; }
-    }
-    p.n_items = wh * ((bp_total + p.hc - 1) / p.hc);                                // units: (window, chunk, head)
-  }
-  if (batch_inner) {
-    const bool gather = bias_row_present && attn_debug_hc() != 14;
-    CUtensorMap map_qkv;
-    if (gather) {
-      const uint64_t dims[2] = {(uint64_t)(3 * C), (uint64_t)((int64_t)B * H * W + 1)};
-      const uint64_t strides[1] = {(uint64_t)(3 * C) * 2};
-      const uint32_t box[2] = {32, 1};
-      int rc = make_tensor_map_nd(&map_qkv, qkv, 2, dims, strides, box, 2, CU_TENSOR_MAP_SWIZZLE_64B);
-      if (rc) return rc;
-    } else {
-      memset(&map_qkv, 0, sizeof(map_qkv));
-    }
-    auto kern = gather ? window_attn_bi_kernel<7, true> : window_attn_bi_kernel<7, false>;
-    PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int grid = num_sms() * AT_CTAS_PER_SM;
-    if (grid > p.n_items) grid = p.n_items;
-    kern<<<grid, AT_THREADS, smem, st>>>(p, map_qkv);
-    return launch_status("window_attn_bi_kernel");
-  }
-  auto kern = bias_full ? window_attn_tc_kernel<7, false, true>
-                        : (mask ? window_attn_tc_kernel<7, true, false> : window_attn_tc_kernel<7, false, false>);
+template <typename K>
+static int launch_attn(K kern, const AttnParams& p, size_t smem, cudaStream_t st, const char* name) {
   PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   int grid = num_sms() * AT_CTAS_PER_SM;
   if (grid > p.n_items) grid = p.n_items;
   kern<<<grid, AT_THREADS, smem, st>>>(p);
-  return launch_status("window_attn_tc_kernel");
+  return launch_status(name);
 }
 
-static int g_attn_hc = 0;
-int attn_debug_hc() { return g_attn_hc; }
-void attn_debug_set_hc(int hc) { g_attn_hc = hc; }
-
-int window_hav_table(const float* uv, void* table, int H, int W, int window, int shift, cudaStream_t st) {
-  WinGeom g = make_geom(H, W, window, shift, 1);
-  hav_table_kernel<<<g.nWh * g.nWw, 128, 0, st>>>(uv, (__half*)table, g);
-  return launch_status("hav_table_kernel");
+// `variant` (diagnostics build only; 0 in production): bits [0,4) force the image pairs per unit (15 = window-pair
+// schedule), bits [4,8) select the exp2 evaluation + 1 (0 = the build's default PSW_ATTN_EXP).
+int window_attn_tc(const bf16* qkv, bf16* out, const float* qkv_bias, const void* bias_full, int B, int H, int W, int C,
+                   int heads, int window, int shift, int pano, float scale, long long* dbg, int mode, int variant,
+                   cudaStream_t st) {
+  PSW_REQUIRE(window == 7 && C / heads == 32, PSW_ERR_UNSUPPORTED,
+              "psw_window_attn_full_fwd: the tcgen05 kernel is instantiated for window 7 and head_dim 32 (every shipped "
+              "PanoSwin config); got window %d head_dim %d -- use psw_window_attn_fwd (generic route)", window, C / heads);
+  PSW_REQUIRE(bias_full != nullptr, PSW_ERR_BAD_ARG, "psw_window_attn_full_fwd: needs the bias table of psw_window_bias_full");
+  PSW_REQUIRE((int64_t)B * H * W < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_window_attn_full_fwd: too many tokens");
+  AttnParams p;
+  p.qkv = qkv; p.out = out; p.qkv_bias = qkv_bias;
+  p.bias_full = (const float4*)bias_full;
+  p.g = make_geom(H, W, window, shift, pano);
+  p.B = B; p.C = C; p.heads = heads; p.scale_l2 = scale * LOG2E;
+  p.dbg = kDiag ? dbg : nullptr;
+  p.mode = kDiag ? mode : 0;
+  p.n_windows = B * p.g.nWh * p.g.nWw;
+  const int forced = kDiag ? (variant & 15) : 0;
+  int expm = PSW_ATTN_EXP;
+  if (kDiag && ((variant >> 4) & 15)) expm = ((variant >> 4) & 15) - 1;
+  const size_t smem = attn_tc_smem_bytes();
+  const bool batch_inner = B >= 4 && forced != 15 && p.mode != 1;
+  if (!batch_inner) {
+    // window-pair schedule, one head per work item: sharing a window pair's token maps between the heads of a wider
+    // item saves little (measured: equal at stage 0), while single-head items balance the small launches of the late
+    // stages better (items are dealt out in contiguous ranges; -10% at stage 3)
+    p.hc = 1;
+    p.n_items = ((p.n_windows + 1) / 2) * heads;
+    return launch_attn(window_attn_pair_kernel<7, AT_EXP_F32>, p, smem, st, "window_attn_pair_kernel");
+  }
+  // image pairs per unit: as many as possible (the bias row and the token map are fetched once per unit) while the
+  // units still spread evenly over the resident CTAs (CTA c runs units c, c + grid, ...)
+  const int bp_total = (B + 1) / 2, ctas = num_sms() * AT_CTAS_PER_SM;
+  const int wh = p.g.nWh * p.g.nWw * heads;
+  double best = -1.0;
+  p.hc = 1;
+  for (int ch = 4; ch >= 1; ch >>= 1) {                 // measured: 8 is not better than 4 where both balance
+    const int64_t units = (int64_t)wh * ((bp_total + ch - 1) / ch);
+    const double steps_max = (double)((units + ctas - 1) / ctas) * ch;             // steps of the busiest CTA (upper bound)
+    const double eff = (double)wh * bp_total / ctas / steps_max;
+    if (forced ? ch == forced : (best < 0.9 && eff > best + 1e-9)) { best = eff; p.hc = ch; }
+  }
+  if (forced == 8) p.hc = 8;
+  p.nch = (bp_total + p.hc - 1) / p.hc;
+  p.n_items = wh * p.nch;                                                          // units: (window, chunk, head)
+  auto magic = [](int d) { return d == 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+  p.magic_heads = magic(heads);
+  p.magic_nch = magic(p.nch);
+  p.magic_nww = magic(p.g.nWw);
+  PSW_REQUIRE((uint64_t)(p.n_items + num_sms() * AT_CTAS_PER_SM) * (uint64_t)(heads > p.nch ? heads : p.nch) < (1ull << 32),
+              PSW_ERR_UNSUPPORTED, "psw_window_attn_full_fwd: too many work units");
+  switch (expm) {
+    case AT_EXP_BF16X2: return launch_attn(window_attn_bi_kernel<7, AT_EXP_BF16X2>, p, smem, st, "window_attn_bi_kernel");
+    case AT_EXP_F16X2:  return launch_attn(window_attn_bi_kernel<7, AT_EXP_F16X2>, p, smem, st, "window_attn_bi_kernel");
+    default:            return launch_attn(window_attn_bi_kernel<7, AT_EXP_F32>, p, smem, st, "window_attn_bi_kernel");
+  }
 }
 
 }  // namespace psw

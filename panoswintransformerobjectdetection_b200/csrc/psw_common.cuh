@@ -44,16 +44,7 @@ inline int launch_status(const char* what) {
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
+int num_sms();                 // SM count of the current device (psw_api.cu)
 
 // ------------------------------------------------------------------------------------------------
 // dtype helpers

@@ -725,8 +725,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 
 // Tile width: a multiple of 32 (epilogue chunks), <= 256 (TMEM double buffer); 192 keeps four pipeline stages
 // next to the epilogue staging, so it is preferred whenever it divides N.
-static int g_tc_mode = 0;   // diagnostics (psw_debug_linear_mode): bit0 no stores, bit1 no loads, bit2 no MMAs,
-                            // bits [8,12) stage-count override, bits [16,25) tile-width override
+// Diagnostics switch (psw_diag_linear_mode, include/panoswin_b200_debug.h): bit0 no stores, bit1 no loads, bit2 no MMAs,
+// bits [8,12) stage-count override, bits [16,25) tile-width override.  It exists -- as mutable state -- only in a
+// -DPSW_DIAGNOSTICS build; the product library compiles it to the constant 0, so kernel selection is stateless.
+#ifdef PSW_DIAGNOSTICS
+static int g_tc_mode = 0;
+#else
+static constexpr int g_tc_mode = 0;
+#endif
 
 static int pick_block_n(int N) {
   if ((g_tc_mode >> 16) & 0x1ff) return (g_tc_mode >> 16) & 0x1ff;
@@ -844,11 +850,13 @@ int linear_f32(const float* x, const float* w, const float* bias, const float* r
 
 using namespace psw;
 
-extern "C" PSW_API int psw_debug_linear_mode(int mode) {
+#ifdef PSW_DIAGNOSTICS
+extern "C" PSW_API int psw_diag_linear_mode(int mode) {
   const int old = g_tc_mode;
   g_tc_mode = mode;
   return old;
 }
+#endif
 
 // LNF 1: y = x . w^T + bias + residual (fp32, may alias residual) and ln_out = LayerNorm(y) * gamma + beta (bf16).
 // LNF 2 (residual == nullptr): y = LayerNorm(x . w^T + bias) * gamma + beta + pos (fp32); x may be a patch-conv view.
@@ -893,9 +901,9 @@ static int launch_tc_lnf(const void* x, const void* w, const float* bias, const 
     PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, EpiCfg<GW>::THREADS, smem, st>>>(mx, mw, mr, bias, (float*)y, M, N, K, block_n, stages, 0, cv, ln);
   } else {
-    auto kern = linear_tc_kernel<false, false, float, GW, 1, 2>;
-    PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, EpiCfg<GW>::THREADS, smem, st>>>(mx, mw, mr, bias, (float*)y, M, N, K, block_n, stages, 0, cv, ln);
+    // LNF 2 (no residual: LayerNorm(x . w^T + bias) + pos, the patch conv + patch_norm fusion) was measured slower than
+    // the two kernels it replaces and is not instantiated
+    PSW_REQUIRE(false, PSW_ERR_UNSUPPORTED, "psw_linear_ln_fwd: needs a residual");
   }
   return launch_status("linear_tc_kernel<LNF>");
 }
@@ -948,34 +956,13 @@ extern "C" PSW_API int psw_patch_conv_fwd(const void* x, const void* w, const fl
   return launch_tc<false, false, bf16>(x, w, bias, nullptr, out, M, cout, patch_h * patch_w * cin, (cudaStream_t)stream, &conv);
 }
 
-// Patch convolution + patch_norm LayerNorm + absolute position add in one kernel (the whole tail of the stem):
-// out fp32 [tokens, cout] = LN(conv(x) + bias) * gamma + beta + pos[token % pos_rows].
-extern "C" PSW_API int psw_patch_conv_ln_fwd(const void* x, const void* w, const float* bias, const float* ln_gamma,
-                                             const float* ln_beta, float ln_eps, const float* pos, int64_t pos_rows, void* out,
-                                             int B, int H, int W, int cin, int cout, int patch_h, int patch_w, void* stream) {
-  PSW_REQUIRE(x && w && out && ln_gamma && ln_beta, PSW_ERR_BAD_ARG, "psw_patch_conv_ln_fwd: null pointer");
-  PSW_REQUIRE(B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0 && patch_h > 0 && patch_w > 0, PSW_ERR_BAD_ARG,
-              "psw_patch_conv_ln_fwd: bad dims");
-  PSW_REQUIRE(H % patch_h == 0 && W % patch_w == 0, PSW_ERR_BAD_ARG,
-              "psw_patch_conv_ln_fwd: H=%d W=%d must be multiples of the patch %dx%d (pad the image first)", H, W, patch_h, patch_w);
-  PSW_REQUIRE((patch_w * cin) % TC_BK == 0 && cout % 32 == 0 && cout <= 256, PSW_ERR_UNSUPPORTED,
-              "psw_patch_conv_ln_fwd: needs patch_w * cin %% 64 == 0, cout %% 32 == 0, cout <= 256 (cin=%d patch_w=%d cout=%d)", cin,
-              patch_w, cout);
-  PSW_REQUIRE(pos == nullptr || (pos_rows > 0 && pos_rows < (1ll << 31)), PSW_ERR_BAD_ARG, "psw_patch_conv_ln_fwd: pos given but bad pos_rows");
-  PSW_REQUIRE(aligned16(x) && aligned16(w) && aligned16(out) && aligned16(bias) && aligned16(pos), PSW_ERR_BAD_ARG,
-              "psw_patch_conv_ln_fwd: pointers must be 16-byte aligned");
-  const int64_t M = (int64_t)B * (H / patch_h) * (W / patch_w);
-  PSW_REQUIRE(M < (1ll << 31) && (int64_t)B * H < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_patch_conv_ln_fwd: too many tokens");
-  const ConvArgs conv = {B * H, W, cin, patch_h, patch_w};
-  const LnFuse ln = {ln_gamma, ln_beta, nullptr, ln_eps, pos, pos ? (int)pos_rows : 1, nullptr, 1};
-  return launch_tc_lnf(x, w, bias, nullptr, out, ln, M, cout, patch_h * patch_w * cin, (cudaStream_t)stream, &conv);
-}
-
-extern "C" PSW_API int psw_debug_linear_cycles(long long* host_out16) {
-  PSW_REQUIRE(host_out16, PSW_ERR_BAD_ARG, "psw_debug_linear_cycles: null pointer");
+#ifdef PSW_DIAGNOSTICS
+extern "C" PSW_API int psw_diag_linear_cycles(long long* host_out16) {
+  PSW_REQUIRE(host_out16, PSW_ERR_BAD_ARG, "psw_diag_linear_cycles: null pointer");
   PSW_CUDA(cudaMemcpyFromSymbol(host_out16, g_tc_cycles, sizeof(long long) * 16));
   return PSW_OK;
 }
+#endif
 
 extern "C" PSW_API int psw_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* y,
                               int64_t M, int N, int K, int flags, int dtype, int out_dtype, void* stream) {

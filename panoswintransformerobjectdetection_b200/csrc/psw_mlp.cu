@@ -3,16 +3,14 @@
 // for C = 96, hidden = 384 (stage 0 of every embed_dim-96 model), where the 4C hidden activation is the largest tensor
 // of the block: it never leaves the SM.  Both weight matrices stay in shared memory for the kernel's lifetime.
 //
-// Per 128-token tile, the hidden dimension is processed in three chunks of 128 columns:
+// Per 128-token tile the hidden dimension is processed in FOUR chunks of 96 columns:
 //   fc1 chunk   : tcgen05.mma SS, A = xn tile (K = 96 as a 64-wide SWIZZLE_128B block + a 32-wide SWIZZLE_64B block),
-//                 B = 128 rows of W1, accumulator = one of two 128-column TMEM buffers H
-//   GELU        : 16 epilogue warps (four per TMEM lane quadrant, 32 columns each): tcgen05.ld -> + b1 -> GELU (packed
-//                 fp16, tanh fit) -> bf16 pairs -> tcgen05.st into the 64-column TMEM region P
-//   fc2 partial : tcgen05.mma TS, A = P from tensor memory (K = 128), B = two 64-wide K-blocks of W2, accumulating into
-//                 the 96-column TMEM accumulator D
-// then the final epilogue adds b2 and the residual and writes x (fp32) with coalesced 16-byte stores.
-// TMEM: H0 [0,128) H1 [128,256) P0 [256,320) D [320,416) P1 [416,480).  fc1 runs two chunks ahead of fc2 across tile
-// boundaries; the final epilogue of tile t runs after the first GELU chunk of tile t+1 (its D is complete by then).  warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-17 epilogue.
+//                 B = 96 rows of W1, accumulator = one of two TMEM buffers H
+//   GELU        : 12 warps (three per TMEM lane quadrant, 32 columns each): tcgen05.ld -> + b1 -> GELU (packed fp16,
+//                 tanh fit) -> bf16 pairs -> tcgen05.st into a TMEM region P
+//   fc2 partial : tcgen05.mma TS, A = P from tensor memory, B = K-blocks of W2, accumulating into D[tile & 1]
+// and four dedicated final-epilogue warps add b2 and the residual and write x (fp32) with coalesced 16-byte stores
+// while the GELU warps work on the next tile (details at the kernel).  warp 0 = TMA producer, warp 1 = MMA issuer.
 #include "psw_common.cuh"
 #include <cuda_fp16.h>
 #include <type_traits>
@@ -22,8 +20,6 @@ namespace psw {
 constexpr int ML_C = 96;
 constexpr int ML_HID = 384;
 constexpr int ML_BM = 128;
-constexpr int ML_EPI_WARPS = 16;                 // four per TMEM lane quadrant: 32 hidden columns each
-constexpr int ML_THREADS = 64 + 32 * ML_EPI_WARPS;
 constexpr uint32_t ML_W1A = 0;                               // W1 K-block 0: [384][128 B] SWIZZLE_128B
 constexpr uint32_t ML_W1B = ML_W1A + ML_HID * 128;           // W1 K-block 1: [384][64 B]  SWIZZLE_64B
 constexpr uint32_t ML_W2 = ML_W1B + ML_HID * 64;             // W2: 6 K-blocks [96][128 B] SWIZZLE_128B
@@ -31,15 +27,7 @@ constexpr uint32_t ML_X = ML_W2 + 6 * ML_C * 128;            // 2 stages x ([128
 constexpr uint32_t ML_XSTAGE = ML_BM * 128 + ML_BM * 64;
 constexpr uint32_t ML_STG = ML_X + 2 * ML_XSTAGE;            // 12 warps (final epilogue) x 2 KB staging
 constexpr uint32_t ML_TAIL = ML_STG + 12 * 2048;
-constexpr uint32_t ML_COL_H = 0, ML_COL_P0 = 256, ML_COL_D = 320, ML_COL_P1 = 416;   // P double-buffered
 
-struct alignas(16) MlTail {
-  uint64_t w_full, x_full[2], x_empty[2], h_full[2], h_free[2], p_full[2], p_free[2], d_full, d_free;
-  uint32_t tmem_base;
-  float b1[ML_HID];
-  float b2[ML_C];
-};
-constexpr size_t ML_SMEM = 1024 + ML_TAIL + sizeof(MlTail);
 
 __device__ __forceinline__ uint32_t mlp_gelu_pair(float x0, float x1) {
   uint32_t h, t;
@@ -70,239 +58,10 @@ __device__ __forceinline__ void ml_tmem_st_x16(uint32_t taddr, const uint32_t (&
       : "memory");
 }
 
-__global__ void __launch_bounds__(ML_THREADS, 1)
-mlp_fused_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_constant__ CUtensorMap map_xb,
-                 const __grid_constant__ CUtensorMap map_w1a, const __grid_constant__ CUtensorMap map_w1b,
-                 const __grid_constant__ CUtensorMap map_w2, const float* __restrict__ b1, const float* __restrict__ b2,
-                 float* __restrict__ x, int64_t M, int mode) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  MlTail* tail = reinterpret_cast<MlTail*>(smem + ML_TAIL);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles = (int)((M + ML_BM - 1) / ML_BM);
-
-  for (int i = threadIdx.x; i < ML_HID; i += blockDim.x) tail->b1[i] = b1 ? b1[i] : 0.f;
-  for (int i = threadIdx.x; i < ML_C; i += blockDim.x) tail->b2[i] = b2 ? b2[i] : 0.f;
-  if (threadIdx.x == 0) {
-    mbar_init(&tail->w_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tail->x_full[s], 1);
-      mbar_init(&tail->x_empty[s], 1);
-      mbar_init(&tail->h_full[s], 1);
-      mbar_init(&tail->h_free[s], ML_EPI_WARPS);
-      mbar_init(&tail->p_full[s], ML_EPI_WARPS);
-      mbar_init(&tail->p_free[s], 1);
-    }
-    mbar_init(&tail->d_full, 1);
-    mbar_init(&tail->d_free, 12);
-    mbar_fence_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tail->tmem_base)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tail->tmem_base;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // weights once: W1 as 2 x 192-row boxes per K-block, W2 as 6 K-blocks
-      mbar_expect_tx(&tail->w_full, ML_HID * 128 + ML_HID * 64 + 6 * ML_C * 128);
-      for (int j = 0; j < 2; ++j) {
-        tma_load_2d(smem + ML_W1A + j * 192 * 128, &map_w1a, &tail->w_full, 0, j * 192);
-        tma_load_2d(smem + ML_W1B + j * 192 * 64, &map_w1b, &tail->w_full, 64, j * 192);
-      }
-      for (int j = 0; j < 6; ++j) tma_load_2d(smem + ML_W2 + j * ML_C * 128, &map_w2, &tail->w_full, j * 64, 0);
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
-        const int s = it & 1;
-        mbar_wait(&tail->x_empty[s], ((it >> 1) & 1) ^ 1);
-        uint8_t* xs = smem + ML_X + s * ML_XSTAGE;
-        mbar_expect_tx(&tail->x_full[s], ML_XSTAGE);
-        tma_load_2d(xs, &map_xa, &tail->x_full[s], 0, t * ML_BM);
-        tma_load_2d(xs + ML_BM * 128, &map_xb, &tail->x_full[s], 64, t * ML_BM);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc1 = umma_idesc_bf16(128, 128, 0, 0);
-      const uint32_t idesc2 = umma_idesc_bf16(128, ML_C, 0, 0);
-      const uint32_t sb = smem_u32(smem);
-      mbar_wait(&tail->w_full, 0);
-      tc_fence_after();
-      const int my_tiles = (int)blockIdx.x < tiles ? (tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-      const uint32_t G_total = 3u * (uint32_t)my_tiles;
-      for (uint32_t G = 0; G <= G_total; ++G) {              // step G: fc1 of chunk G, then fc2 of chunk G - 1
-        if (G < G_total) {
-          const uint32_t ti = G / 3, h = G - 3 * ti;
-          const int s = ti & 1, hb = G & 1;
-          if (h == 0) {
-            mbar_wait(&tail->x_full[s], (ti >> 1) & 1);
-            tc_fence_after();
-          }
-          mbar_wait(&tail->h_free[hb], ((G >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint32_t xa = sb + ML_X + s * ML_XSTAGE, xb = xa + ML_BM * 128;
-          const uint32_t dH = tmem + ML_COL_H + (uint32_t)hb * 128;
-          const uint64_t da = umma_smem_desc(xa, 16, 1024, UMMA_SWIZZLE_128B);
-          const uint64_t dwa = umma_smem_desc(sb + ML_W1A + h * 128 * 128, 16, 1024, UMMA_SWIZZLE_128B);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(dH, da + 2 * k, dwa + 2 * k, idesc1, k != 0);
-          const uint64_t db = umma_smem_desc(xb, 16, 512, UMMA_SWIZZLE_64B);
-          const uint64_t dwb = umma_smem_desc(sb + ML_W1B + h * 128 * 64, 16, 512, UMMA_SWIZZLE_64B);
-#pragma unroll
-          for (int k = 0; k < 2; ++k) umma_ss(dH, db + 2 * k, dwb + 2 * k, idesc1, 1);
-          umma_commit(&tail->h_full[hb]);
-          if (h == 2) umma_commit(&tail->x_empty[s]);        // the x tile has been consumed by all three chunks
-        }
-        if (G >= 1) {
-          const uint32_t Gp = G - 1, tp = Gp / 3, hp = Gp - 3 * tp;
-          const int pb = Gp & 1;
-          if (hp == 0) {                                     // D of the previous tile must have been drained
-            mbar_wait(&tail->d_free, (tp & 1) ^ 1);
-            tc_fence_after();
-          }
-          mbar_wait(&tail->p_full[pb], (Gp >> 1) & 1);
-          tc_fence_after();
-          const uint32_t pcol = pb ? ML_COL_P1 : ML_COL_P0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint64_t dw = umma_smem_desc(sb + ML_W2 + (2 * hp + (uint32_t)(i >> 2)) * (ML_C * 128), 16, 1024, UMMA_SWIZZLE_128B) +
-                                (uint64_t)(2 * (i & 3));
-            umma_ts(tmem + ML_COL_D, tmem + pcol + (uint32_t)(i * 8), dw, idesc2, (hp | (uint32_t)i) != 0);
-          }
-          umma_commit(&tail->p_free[pb]);
-          if (hp == 2) umma_commit(&tail->d_full);
-        }
-      }
-    }
-  } else {
-    const int ew = warp - 2;
-    const int quad = warp & 3;
-    const int part = ew >> 2;                                // 0..3: hidden columns [32 part, 32 part + 32) of a chunk
-    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    uint8_t* stg = smem + ML_STG + (part * 4 + quad) * 2048;  // parts 0..2 only
-    const int sw = (lane >> 1) & 3;
-    const int t_row = lane >> 2, t_piece = lane & 3;
-    // final epilogue of tile t (the j-th tile of this CTA): x += D + b2 for my 32 columns
-    uint4 resid[8];                                          // residual rows of the PREVIOUS tile, four lanes per row
-    auto prefetch_resid = [&](int t) {                       // issued before the first GELU chunk of the next tile
-      if (part == 3) return;
-      const int row0 = t * ML_BM + quad * 32;
-      const float* gx = x + (int64_t)(row0 + t_row) * ML_C + part * 32 + t_piece * 4;
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          resid[4 * c + jj] = make_uint4(0, 0, 0, 0);
-          if (row0 + t_row + 8 * jj < M) resid[4 * c + jj] = ml_ldg_v4(gx + c * 16 + (int64_t)8 * jj * ML_C);
-        }
-    };
-    auto final_epilogue = [&](int t, uint32_t j) {
-      if (part == 3) return;                                 // 96 = 3 x 32 columns
-      mbar_wait(&tail->d_full, j & 1);
-      if (mode & 2) {                                        // diagnostics: no final epilogue traffic
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tail->d_free);
-        return;
-      }
-      tc_fence_after();
-      const int row0 = t * ML_BM + quad * 32;
-      float* gx = x + (int64_t)(row0 + t_row) * ML_C + part * 32 + t_piece * 4;
-      // read my 32 D columns first and hand the accumulator back at once: the MMA warp may then start fc2 of the
-      // next tile while this tile's rows are still being added to the residual and stored
-      uint32_t rd[2][16];
-      tmem_ld_x16(tmem + lane_base + ML_COL_D + (uint32_t)(part * 32), rd[0]);
-      tmem_ld_x16(tmem + lane_base + ML_COL_D + (uint32_t)(part * 32 + 16), rd[1]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tail->d_free);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int col = part * 32 + c * 16;
-        const uint32_t (&r)[16] = rd[c];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {                      // hand the residual rows to their owners through smem
-          const int rr = t_row + 8 * jj;
-          *reinterpret_cast<uint4*>(stg + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4)) = resid[4 * c + jj];
-        }
-        __syncwarp();
-        uint32_t o[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 p4 = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((q ^ sw) << 4));
-          const uint32_t pw[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            o[4 * q + i] = __float_as_uint(__uint_as_float(r[4 * q + i]) + tail->b2[col + 4 * q + i] + __uint_as_float(pw[i]));
-        }
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(stg + lane * 64 + ((q ^ sw) << 4)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int rr = t_row + 8 * jj;
-          const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((t_piece ^ ((rr >> 1) & 3)) << 4));
-          if (row0 + rr < M) *reinterpret_cast<uint4*>(gx + c * 16 + (int64_t)8 * jj * ML_C) = v;
-        }
-        __syncwarp();
-      }
-    };
-    uint32_t it = 0, G = 0;
-    int t_prev = -1;
-    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
-      if (t_prev >= 0) prefetch_resid(t_prev);               // lands while the first GELU chunk of this tile runs
-      for (int h = 0; h < 3; ++h, ++G) {
-        const int hb = G & 1;
-        mbar_wait(&tail->h_full[hb], (G >> 1) & 1);
-        tc_fence_after();
-        uint32_t r0[32];
-        tmem_ld_x32(tmem + lane_base + ML_COL_H + (uint32_t)hb * 128 + (uint32_t)part * 32, r0);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tail->h_free[hb]);
-        uint32_t pk[16];
-        const float* bb = tail->b1 + h * 128 + part * 32;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          pk[i] = mlp_gelu_pair(__uint_as_float(r0[2 * i]) + bb[2 * i], __uint_as_float(r0[2 * i + 1]) + bb[2 * i + 1]);
-        mbar_wait(&tail->p_free[hb], ((G >> 1) & 1) ^ 1);    // fc2 two chunks ago has consumed this P buffer
-        tc_fence_after();
-        ml_tmem_st_x16(tmem + lane_base + (hb ? ML_COL_P1 : ML_COL_P0) + (uint32_t)part * 16, pk);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tail->p_full[hb]);
-        if (h == 0 && t_prev >= 0) final_epilogue(t_prev, it - 1);   // the previous tile's D is complete by now
-      }
-      t_prev = t;
-    }
-    if (t_prev >= 0) {
-      prefetch_resid(t_prev);
-      final_epilogue(t_prev, it - 1);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-  }
-}
-
-
 // ---------------------------------------------------------------------------------------------------------------------
-// v2: the final epilogue has its own four warps.  In the kernel above the sixteen epilogue warps do GELU chunks AND the
-// final epilogue (+ b2 + residual -> x), one after the other: MMA/loads ~76 us + GELU ~90 us (MUFU-bound) + final epilogue
-// ~160 us (DRAM-bound) add up instead of overlapping.  Here the hidden dimension is cut into FOUR chunks of 96 columns, which
+// The final epilogue has its own four warps.  (A first version let sixteen epilogue warps do GELU chunks AND the final
+// epilogue one after the other: MMA/loads ~76 us + GELU ~90 us (MUFU-bound) + final epilogue ~160 us (DRAM-bound) added
+// up instead of overlapping: 328 us.)  The hidden dimension is cut into FOUR chunks of 96 columns, which
 // frees enough tensor memory for a second accumulator: H0 [0,96) H1 [96,192) P0 [192,240) P1 [256,304) D0 [320,416)
 // D1 [416,512).  fc2 of tile t accumulates into D[t & 1]; warps 14-17 (one per TMEM lane quadrant) drain it during tile
 // t + 1: the accumulator row of a lane goes through a 2 KB staging tile into a four-lanes-per-row layout, where b2 and the
@@ -311,7 +70,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_consta
 // warps 2-13 (three per quadrant, 32 columns each) keep the GELU chunks going.  The MMA-issuing thread runs a fully
 // unrolled per-tile schedule with prebuilt descriptors: with run-time chunk indices its instruction stream was the
 // critical path (195 -> 139 us for the MMA / synchronisation skeleton alone).
-// Measured (M = 1 Mi rows): 270 us vs 328 us for the kernel above; 197 us without the final epilogue, 231 us without the
+// Measured (M = 1 Mi rows): 270 us; 197 us without the final epilogue, 231 us without the
 // GELU arithmetic, 144 us with neither: the final-epilogue warps are bound by bytes in flight x memory latency.
 // ---------------------------------------------------------------------------------------------------------------------
 // The kernel is close to issue-bound (GELU arithmetic), so a warp that waits must not spin at full rate: back off between
@@ -593,16 +352,21 @@ mlp_fused_v2_kernel(const __grid_constant__ CUtensorMap map_xa, const __grid_con
 
 using namespace psw;
 
-static int g_mlp_mode = 0;   // diagnostics (psw_debug_mlp_mode): bit1 no final epilogue, bit2 first kernel version, bit3 no GELU arithmetic
-extern "C" PSW_API int psw_debug_mlp_mode(int mode) {
+// Diagnostics switch (psw_diag_mlp_mode, -DPSW_DIAGNOSTICS builds only): bit1 no final epilogue, bit3 no GELU arithmetic.
+#ifdef PSW_DIAGNOSTICS
+static int g_mlp_mode = 0;
+extern "C" PSW_API int psw_diag_mlp_mode(int mode) {
   const int old = g_mlp_mode;
   g_mlp_mode = mode;
   return old;
 }
+#else
+static constexpr int g_mlp_mode = 0;
+#endif
 
 extern "C" PSW_API int psw_mlp_fused_fwd(const void* xn, const void* w1, const float* b1, const void* w2, const float* b2,
                                          void* x, int64_t M, int C, int hidden, void* stream) {
-  PSW_REQUIRE(xn && w1 && w2 && x, PSW_ERR_BAD_ARG, "psw_mlp_fused_fwd: null pointer");
+  PSW_REQUIRE(xn && w1 && b1 && w2 && b2 && x, PSW_ERR_BAD_ARG, "psw_mlp_fused_fwd: null pointer");
   PSW_REQUIRE(C == ML_C && hidden == ML_HID, PSW_ERR_UNSUPPORTED,
               "psw_mlp_fused_fwd: instantiated for C = 96, hidden = 384 (got C=%d hidden=%d)", C, hidden);
   PSW_REQUIRE(M > 0 && M < (1ll << 31), PSW_ERR_BAD_ARG, "psw_mlp_fused_fwd: M=%lld", (long long)M);
@@ -621,13 +385,8 @@ extern "C" PSW_API int psw_mlp_fused_fwd(const void* xn, const void* w1, const f
   if (rc) return rc;
   const int tiles = (int)((M + ML_BM - 1) / ML_BM);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  if (!(g_mlp_mode & 4)) {                                   // bit 2 (diagnostics): the first version of the kernel
-    PSW_CUDA(cudaFuncSetAttribute(mlp_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M2_SMEM));
-    mlp_fused_v2_kernel<<<grid, M2_THREADS, M2_SMEM, (cudaStream_t)stream>>>(mxa, mxb, mw1a, mw1b, mw2, b1, b2, (float*)x, M,
-                                                                            g_mlp_mode);
-    return launch_status("mlp_fused_v2_kernel");
-  }
-  PSW_CUDA(cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ML_SMEM));
-  mlp_fused_kernel<<<grid, ML_THREADS, ML_SMEM, (cudaStream_t)stream>>>(mxa, mxb, mw1a, mw1b, mw2, b1, b2, (float*)x, M, g_mlp_mode);
-  return launch_status("mlp_fused_kernel");
+  PSW_CUDA(cudaFuncSetAttribute(mlp_fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M2_SMEM));
+  mlp_fused_v2_kernel<<<grid, M2_THREADS, M2_SMEM, (cudaStream_t)stream>>>(mxa, mxb, mw1a, mw1b, mw2, b1, b2, (float*)x, M,
+                                                                          g_mlp_mode);
+  return launch_status("mlp_fused_v2_kernel");
 }

@@ -195,32 +195,15 @@ def window_grid(H, W, window, pano_mode):
     return nwh.value, nww.value
 
 
-def window_hav_table(uv, window, shift):
-    """fp16 great-circle distance table [nW, window^2, 56] for one image geometry (pano mode, bf16 path).
-    uv [H, W, 2] fp32 (make_uv_hw2).  Depends on (H, W, window, shift) only: build once, reuse every forward."""
-    dev = _chk(uv)
-    H, W, _ = uv.shape
-    nwh, nww = window_grid(H, W, window, True)
-    table = torch.empty((nwh * nww, window * window, 56), dtype=torch.float16, device=uv.device)
-    with torch.cuda.device(dev):
-        _call("psw_window_hav_table", _ptr(_f32(uv, "uv")), _ptr(table), H, W, window, shift, _stream(dev))
-    return table
-
-
-def window_bias_tables(alpha, beta, window):
-    """Per-head packing of the alpha/beta tables for the bf16 attention kernel: fp16 [heads, 508, 2]."""
-    dev = _chk(alpha, beta)
-    heads = alpha.shape[1]
-    out = torch.empty((heads, 508, 2), dtype=torch.float16, device=alpha.device)
-    with torch.cuda.device(dev):
-        _call("psw_window_bias_tables", _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta")), _ptr(out), heads, window,
-              _stream(dev))
-    return out
+def window_attention_full_supported(window, head_dim) -> bool:
+    """True when the bf16 tcgen05 attention kernel is instantiated for this window / head_dim (window 7, head_dim 32)."""
+    return bool(_lib.load().psw_window_attn_full_supported(int(window), int(head_dim)))
 
 
 def window_bias_full(alpha, beta, uv, mask, H, W, window, shift, pano_mode):
     """Every additive term of the logits of one block at one resolution (great-circle + relative-position bias, planar
-    shift mask) for all windows of one image and all heads: fp32 [windows, heads, 13, 64, 4] for window_attention_full."""
+    shift mask; times log2 e) for all windows of one image and all heads: fp32 [windows, heads, 13, 64, 4] for
+    window_attention_full."""
     dev = _chk(alpha, beta, uv, mask)
     heads = alpha.shape[1]
     nbytes = _lib.load().psw_window_bias_full_bytes(H, W, heads, window, 1 if pano_mode else 0)
@@ -231,59 +214,35 @@ def window_bias_full(alpha, beta, uv, mask, H, W, window, shift, pano_mode):
     return out
 
 
-def window_attention_full(qkv, bias_full, qkv_bias, heads, window, shift, pano_mode, scale, out=None, dims=None):
+def window_attention_full(qkv, bias_full, qkv_bias, heads, window, shift, pano_mode, scale, out=None):
     """The bf16 tcgen05 attention kernel with the precomputed bias table of window_bias_full() (production path).
-    qkv is [B, H, W, 3C], or -- with dims=(B, H, W) -- a [B*H*W + 1, 3C] tensor whose last row holds the bf16 qkv bias
-    (the qkv GEMM of an input with one extra all-zero row), which lets the kernel gather q/k/v with TMA."""
+    qkv [B, H, W, 3C] bf16 -> [B, H, W, C] bf16."""
     dev = _chk(qkv, bias_full, qkv_bias, out)
-    if dims is None:
-        B, H, W, C3 = qkv.shape
-        rows = B * H * W
-    else:
-        B, H, W = dims
-        rows, C3 = qkv.shape
-        if rows not in (B * H * W, B * H * W + 1):
-            raise PanoSwinB200Error("window_attention_full: qkv rows must be B*H*W or B*H*W + 1")
+    B, H, W, C3 = qkv.shape
     C = C3 // 3
     if qkv.dtype != torch.bfloat16:
         raise PanoSwinB200Error("window_attention_full is the bf16 path")
     if out is None:
         out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
     with torch.cuda.device(dev):
-        _call("psw_window_attn_full_fwd", _ptr(qkv), _ptr(out), _ptr(bias_full), _ptr(_f32(qkv_bias, "qkv_bias")), rows, B, H, W,
+        _call("psw_window_attn_full_fwd", _ptr(qkv), _ptr(out), _ptr(bias_full), _ptr(_f32(qkv_bias, "qkv_bias")), B, H, W,
               C, heads, window, shift, 1 if pano_mode else 0, float(scale), _stream(dev))
     return out
 
 
-def window_attention(qkv, alpha, beta, qkv_bias, uv, mask, heads, window, shift, pano_mode, scale, out=None,
-                     impl=None, hav_table=None, bias_tables=None):
-    """Fused shift + partition + W-MSA core + reverse + un-shift.  qkv [B, H, W, 3C] -> [B, H, W, C].
-    fp32 tensors: CUDA-core parity kernel (needs `uv` in pano mode).  bf16 tensors: tcgen05 kernel (needs
-    `hav_table` from window_hav_table() in pano mode; built on the fly from `uv` when omitted).
-    `impl='simt'`: the CUDA-core kernel on bf16 tensors (cross-check)."""
-    dev = _chk(qkv, alpha, beta, qkv_bias, uv, mask, out, hav_table, bias_tables)
+def window_attention(qkv, alpha, beta, qkv_bias, uv, mask, heads, window, shift, pano_mode, scale, out=None):
+    """Fused shift + partition + W-MSA core + reverse + un-shift on the generic CUDA-core kernel (any window size and
+    head_dim).  qkv [B, H, W, 3C] -> [B, H, W, C], fp32 (parity path) or bf16 (the route for shapes the tcgen05 kernel
+    of window_attention_full is not instantiated for); `uv` is required in pano mode."""
+    dev = _chk(qkv, alpha, beta, qkv_bias, uv, mask, out)
     B, H, W, C3 = qkv.shape
     C = C3 // 3
     if out is None:
         out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
-    if qkv.dtype == torch.bfloat16 and impl is None:
-        if pano_mode and hav_table is None and uv is not None:
-            hav_table = window_hav_table(uv, window, shift)
-        if bias_tables is None:
-            bias_tables = window_bias_tables(alpha, beta, window)
-    head = [_ptr(qkv), _ptr(out), _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta"))]
-    mid = [_ptr(_f32(qkv_bias, "qkv_bias")), _ptr(_f32(uv, "uv"))]
-    tail = [_ptr(_f32(mask, "mask")), B, H, W, C, heads, window, shift, 1 if pano_mode else 0, float(scale)]
     with torch.cuda.device(dev):
-        if impl is None:
-            _call("psw_window_attn_fwd", *head, _ptr(bias_tables), *mid, _ptr(hav_table), *tail,
-                  _dt(qkv), _stream(dev))
-        elif impl == "simt":
-            if qkv.dtype != torch.bfloat16:
-                raise PanoSwinB200Error("impl='simt' is the bf16 cross-check kernel")
-            _call("psw_window_attn_fwd_simt_bf16", *head, *mid, *tail, _stream(dev))
-        else:
-            raise PanoSwinB200Error(f"unknown impl {impl!r}")
+        _call("psw_window_attn_fwd", _ptr(qkv), _ptr(out), _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta")),
+              _ptr(_f32(qkv_bias, "qkv_bias")), _ptr(_f32(uv, "uv")), _ptr(_f32(mask, "mask")), B, H, W, C, heads, window,
+              shift, 1 if pano_mode else 0, float(scale), _dt(qkv), _stream(dev))
     return out
 
 
@@ -355,23 +314,6 @@ def patch_conv(x_nhwc, w_ohwi, bias, patch):
     out = torch.empty((B, H // ph, W // pw, cout), dtype=torch.bfloat16, device=x_nhwc.device)
     with torch.cuda.device(dev):
         _call("psw_patch_conv_fwd", _ptr(x_nhwc), _ptr(w_ohwi), _ptr(_f32(bias, "bias")), _ptr(out), B, H, W, cin, cout, ph, pw,
-              _stream(dev))
-    return out
-
-
-def patch_conv_layernorm(x_nhwc, w_ohwi, bias, patch, ln_gamma, ln_beta, ln_eps, pos=None):
-    """patch_conv + LayerNorm + position add in one kernel: fp32 tokens [B, H/ph * W/pw, cout] (the stem's tail)."""
-    dev = _chk(x_nhwc, w_ohwi, bias, ln_gamma, ln_beta, pos)
-    B, H, W, cin = x_nhwc.shape
-    ph, pw = patch
-    cout = w_ohwi.shape[0]
-    if x_nhwc.dtype != torch.bfloat16 or w_ohwi.dtype != torch.bfloat16 or tuple(w_ohwi.shape) != (cout, ph, pw, cin):
-        raise PanoSwinB200Error("patch_conv_layernorm wants bf16 NHWC x and bf16 w [cout, ph, pw, cin]")
-    out = torch.empty((B, (H // ph) * (W // pw), cout), dtype=torch.float32, device=x_nhwc.device)
-    pos_rows = 0 if pos is None else pos.numel() // cout
-    with torch.cuda.device(dev):
-        _call("psw_patch_conv_ln_fwd", _ptr(x_nhwc), _ptr(w_ohwi), _ptr(_f32(bias, "bias")), _ptr(_f32(ln_gamma, "ln_gamma")),
-              _ptr(_f32(ln_beta, "ln_beta")), float(ln_eps), _ptr(_f32(pos, "pos")), pos_rows, _ptr(out), B, H, W, cin, cout, ph, pw,
               _stream(dev))
     return out
 

@@ -45,10 +45,23 @@ class GraphedForward:
     launches of a forward without any Python / ctypes work (small chunks are launch-bound otherwise).
     The forward is cut into one graph per output map (all in one memory pool, replayed in capture order), so a
     caller can start reading output k while the stages after it still run (`replay(on_output)`).
-    `static_in` is the graphs' input buffer, `static_out` the tuple of output maps."""
+    `static_in` is the graphs' input buffer, `static_out` the tuple of output maps.
+
+    A graph bakes in raw pointers to the model's cached bf16 weight copies, folded stem weights and bias tables, and
+    the compute dtype / pano mode of capture time.  The capture therefore records `model.cache_signature()` and keeps
+    strong references to every cached tensor it uses; `replay()` compares the signature first and RE-CAPTURES when a
+    parameter changed (load_state_dict, optimizer step), or the compute dtype / pano mode was switched — a stale
+    replay would silently produce old results or read recycled memory."""
 
     def __init__(self, model, shape, device):
+        self.model = model
+        self.device = device
         self.static_in = torch.zeros(shape, device=device)
+        self.recaptures = 0
+        self._capture()
+
+    def _capture(self):
+        model, device = self.model, self.device
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side), torch.no_grad():      # warm-up: builds every cached constant / bf16 weight copy
@@ -78,10 +91,16 @@ class GraphedForward:
                 self.graphs[-1].capture_end()
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
+        self.signature = model.cache_signature()
+        # the tensors whose addresses the graphs hold: converted weights and this resolution's constants
+        self._keep = (dict(model._weight_cache), dict(model._cur_res))
 
     def replay(self, on_output=None):
         """Re-run the forward on the current stream; `on_output(k, map)` is called right after the graph that
         produces output k has been launched."""
+        if self.model.cache_signature() != self.signature:
+            self.recaptures += 1
+            self._capture()
         for k, g in enumerate(self.graphs):
             g.replay()
             if on_output is not None:

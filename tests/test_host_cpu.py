@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
     assert len(names) >= 11 and "psw_window_attn_fwd" in names and "psw_linear_fwd" in names
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/panoswin_b200.h but not exported"
-    assert lib.psw_abi_version() == 1
+    assert lib.psw_abi_version() == _lib.ABI_VERSION
     # the ctypes table binds exactly the header's functions (besides the error-string getter)
     assert sorted(list(_lib.SIGNATURES) + ["psw_last_error_string"]) == names
 
@@ -47,22 +47,23 @@ def test_argument_errors_do_not_need_a_gpu(lib):
     assert lib.psw_layernorm_fwd(None, None, None, None, None, 4, 96, 0, 1e-5, 0, 0, None) == -1
     assert b"null" in lib.psw_last_error_string()
     hp, wp = C.c_int(), C.c_int()
-    assert lib.psw_debug_source_map(4, 8, 7, 7, 1, None, 0, C.byref(hp), C.byref(wp)) == -1   # shift >= window
+    assert lib.psw_window_source_map(4, 8, 7, 7, 1, None, 0, C.byref(hp), C.byref(wp)) == -1   # shift >= window
     # every entry point validates before it touches the device: null pointers, unsupported shapes
     assert lib.psw_layernorm2_fwd(None, None, None, None, None, None, None, None, 4, 96, 0, 1e-5, 1e-5, 1, None) == -1
     assert b"psw_layernorm2_fwd" in lib.psw_last_error_string()
     assert lib.psw_mlp_fused_fwd(None, None, None, None, None, None, 128, 96, 384, None) == -1
     assert b"psw_mlp_fused_fwd" in lib.psw_last_error_string()
     fake = C.c_void_p(1 << 20)                                   # never dereferenced: the shape check comes first
-    assert lib.psw_mlp_fused_fwd(fake, fake, None, fake, None, fake, 128, 192, 768, None) == -2
+    assert lib.psw_mlp_fused_fwd(fake, fake, None, fake, None, fake, 128, 96, 384, None) == -1   # b1 / b2 are required
+    assert lib.psw_mlp_fused_fwd(fake, fake, fake, fake, fake, fake, 128, 192, 768, None) == -2
     assert b"C = 96" in lib.psw_last_error_string()
 
 
 def _source_map(lib, H, W, ws, s, pano):
     hp, wp = C.c_int(), C.c_int()
-    assert lib.psw_debug_source_map(H, W, ws, s, pano, None, 0, C.byref(hp), C.byref(wp)) == 0
+    assert lib.psw_window_source_map(H, W, ws, s, pano, None, 0, C.byref(hp), C.byref(wp)) == 0
     m = np.zeros((hp.value, wp.value), dtype=np.int32)
-    assert lib.psw_debug_source_map(H, W, ws, s, pano, m.ctypes.data, m.size, C.byref(hp), C.byref(wp)) == 0
+    assert lib.psw_window_source_map(H, W, ws, s, pano, m.ctypes.data, m.size, C.byref(hp), C.byref(wp)) == 0
     return m
 
 
@@ -138,8 +139,29 @@ def test_registry_and_constructor_contract():
         P.backbone.PanoSwinTransformerBlock(dim=32, num_heads=1, window_size=7, shift_size=7)
     with pytest.raises(AssertionError):                       # reference :284
         P.backbone.WindowAttention(dim=30, window_size=7, num_heads=4)
-    with pytest.raises(NotImplementedError):                  # odd depth -> PitchAttentionModule (broken upstream)
-        P.SimplePanoSwinTransformer(depths=[2, 2, 7, 2])
+    # the reference's DEFAULT constructor (depths=[2,2,7,2], :785) builds: the odd stage ends in a PitchAttentionModule
+    d = P.SimplePanoSwinTransformer()
+    assert isinstance(d.layers[2].blocks[6], P.backbone.PitchAttentionModule) and len(d.layers[2].blocks) == 7
+    assert d.pano_mode is True and d.ape is False
+
+
+def test_odd_depth_state_dict_and_mode_switch():
+    """Odd stage depths append a PitchAttentionModule with the reference's parameter names (strict load of the
+    state_dict the real reference accepted, tests/golden/planar_odd.npz) and follow set_pano_mode like any block."""
+    meta, _ = load_golden("planar_odd")
+    cfg = meta["cfg"]
+    m = P.SimplePanoSwinTransformer(embed_dim=cfg["embed_dim"], depths=list(cfg["depths"]), num_heads=list(cfg["num_heads"]),
+                                    out_indices=tuple(cfg["out_indices"]), ape=cfg["ape"], pano_mode=cfg["pano_mode"])
+    res = m.load_state_dict(O.make_state_dict(cfg, meta["param_seed"]), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    pam = m.layers[0].blocks[2]
+    assert isinstance(pam, P.backbone.PitchAttentionModule) and pam.pano_mode is False
+    assert sorted(k for k, _ in pam.named_parameters()) == sorted(
+        ["proj.weight", "proj.bias", "sphere_position_alpha_table_Te", "sphere_position_beta_table_Te", "mlp.fc1.weight",
+         "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias",
+         "q_linear.weight", "q_linear.bias", "k_linear.weight", "k_linear.bias", "v_linear.weight", "v_linear.bias"])
+    m.set_pano_mode(True)
+    assert pam.pano_mode is True
 
 
 def test_set_pano_mode_propagates():

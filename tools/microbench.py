@@ -3,6 +3,8 @@ through enough distinct buffers).  usage: python tools/microbench.py {attn|linea
 import os
 import sys
 
+os.environ["PSW_DIAGNOSTICS"] = "1"       # every call goes to the -DPSW_DIAGNOSTICS build (libpanoswin_b200_diag.so)
+
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -27,28 +29,45 @@ def time_op(fn, n_bufs, iters):
     return e0.elapsed_time(e1) / iters * 1e3      # us
 
 
+STAGES = [(128, 256, 96, 3), (64, 128, 192, 6), (32, 64, 384, 12), (16, 32, 768, 24)]
+
+
+def _attn_setup(H, W, C, heads, shift=3):
+    nb = max(2, int(400e6 // (B * H * W * 4 * C * 2)) + 1)
+    qkv = [torch.randn(B, H, W, 3 * C, device=DEV).bfloat16() for _ in range(nb)]
+    out = [torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
+    alpha = torch.randn(169, heads, device=DEV) * 0.1
+    beta = torch.randn(169, heads, device=DEV) * 0.1
+    qb = torch.randn(3 * C, device=DEV) * 0.1
+    bf = ops.window_bias_full(alpha, beta, make_uv_hw2(H, W).to(DEV), None, H, W, 7, shift, True)
+    return nb, qkv, out, qb, bf
+
+
+def _attn_diag(lib, qkv, out, bf, qb, H, W, C, heads, shift, ph=None, mode=0, variant=0):
+    from panoswintransformerobjectdetection_b200 import _lib
+    rc = lib.psw_diag_window_attn_full(qkv.data_ptr(), out.data_ptr(), bf.data_ptr(), qb.data_ptr(), B, H, W, C, heads, 7, shift, 1,
+                                       32 ** -0.5, None if ph is None else ph.data_ptr(), mode, variant,
+                                       torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "psw_diag_window_attn_full")
+
+
 def attn(iters):
-    for (H, W, C, heads) in [(128, 256, 96, 3), (64, 128, 192, 6), (32, 64, 384, 12), (16, 32, 768, 24)]:
-        nb = max(2, int(400e6 // (B * H * W * 4 * C * 2)) + 1)
-        qkv = [torch.randn(B, H, W, 3 * C, device=DEV).bfloat16() for _ in range(nb)]
-        out = [torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
-        alpha = torch.randn(169, heads, device=DEV) * 0.1
-        beta = torch.randn(169, heads, device=DEV) * 0.1
-        qb = torch.randn(3 * C, device=DEV) * 0.1
-        uv = make_uv_hw2(H, W).to(DEV)
+    """The production attention kernel per stage, and the exp2 variants (diagnostics build: variant bits [4,8))."""
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    for (H, W, C, heads) in STAGES:
         for shift in (0, 3):
-            hav = ops.window_hav_table(uv, 7, shift)
-            bt = ops.window_bias_tables(alpha, beta, 7)
-            bf = ops.window_bias_full(alpha, beta, uv, None, H, W, 7, shift, True)
-            us = time_op(lambda i: ops.window_attention(qkv[i], alpha, beta, qb, uv, None, heads, 7, shift, True, 32 ** -0.5,
-                                                        out=out[i], hav_table=hav, bias_tables=bt), nb, iters)
-            us2 = time_op(lambda i: ops.window_attention_full(qkv[i], bf, qb, heads, 7, shift, True, 32 ** -0.5, out=out[i]), nb, iters)
-            rows = [torch.cat([q.reshape(-1, 3 * C), qb.bfloat16()[None]], 0).contiguous() for q in qkv]
-            us3 = time_op(lambda i: ops.window_attention_full(rows[i], bf, qb, heads, 7, shift, True, 32 ** -0.5, out=out[i],
-                                                              dims=(B, H, W)), nb, iters)
+            nb, qkv, out, qb, bf = _attn_setup(H, W, C, heads, shift)
             byt = B * H * W * C * 8
-            print(f"attn B{B} {H}x{W} C{C} h{heads} s{shift}: tables {us:8.1f} us  {byt / us / 1e3:7.0f} GB/s   "
-                  f"full-bias {us2:8.1f} us  {byt / us2 / 1e3:7.0f} GB/s   +tma-gather {us3:8.1f} us  {byt / us3 / 1e3:7.0f} GB/s", flush=True)
+            res = []
+            us = min(time_op(lambda i: ops.window_attention_full(qkv[i], bf, qb, heads, 7, shift, True, 32 ** -0.5, out=out[i]), nb, iters)
+                     for _ in range(2))
+            res.append(f"default {us:7.1f} us {byt / us / 1e3:6.0f} GB/s")
+            for name, var in (("ex2-f32", 1 << 4), ("ex2-bf16x2", 2 << 4), ("ex2-f16x2", 3 << 4)):
+                us = min(time_op(lambda i: _attn_diag(lib, qkv[i], out[i], bf, qb, H, W, C, heads, shift, variant=var), nb, iters)
+                         for _ in range(2))
+                res.append(f"{name} {us:7.1f} us {byt / us / 1e3:6.0f} GB/s")
+            print(f"attn B{B} {H}x{W} C{C} h{heads} s{shift}: " + "   ".join(res), flush=True)
 
 
 def linear(iters):
@@ -96,56 +115,33 @@ if __name__ == "__main__":
 
 
 def attn_phases():
-    """Per-phase cycle breakdown of one CTA of the tcgen05 attention kernel (psw_window_attn_fwd_profile)."""
+    """Per-phase cycle breakdown of one CTA of the tcgen05 attention kernel (psw_diag_window_attn_full)."""
     from panoswintransformerobjectdetection_b200 import _lib
     lib = _lib.load()
-    for (H, W, C, heads) in [(128, 256, 96, 3), (32, 64, 384, 12)]:
-        qkv = torch.randn(B, H, W, 3 * C, device=DEV).bfloat16()
-        out = torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16)
-        alpha = torch.randn(169, heads, device=DEV) * 0.1
-        beta = torch.randn(169, heads, device=DEV) * 0.1
-        qb = torch.randn(3 * C, device=DEV) * 0.1
-        uv = make_uv_hw2(H, W).to(DEV)
-        hav = ops.window_hav_table(uv, 7, 3)
-        bt = ops.window_bias_tables(alpha, beta, 7)
-        bf = ops.window_bias_full(alpha, beta, uv, None, H, W, 7, 3, True)
-        for full in (None, bf):
-            ph = torch.zeros(6, dtype=torch.int64, device=DEV)
-            for _ in range(2):
-                rc = lib.psw_window_attn_fwd_profile(qkv.data_ptr(), out.data_ptr(), alpha.data_ptr(), beta.data_ptr(), bt.data_ptr(), qb.data_ptr(),
-                                                     hav.data_ptr(), None if full is None else full.data_ptr(), B, H, W, C, heads, 7, 3,
-                                                     32 ** -0.5, ph.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
-                _lib.check(rc, "profile")
-            torch.cuda.synchronize()
-            v = ph.tolist()
-            n = max(v[5], 1)
-            names = ["wait-loads", "S-mma", "softmax", "PV-mma", "store"]
-            print(f"attn phases {H}x{W} C{C} {'tables' if full is None else 'full-bias'}: steps {v[5]}  " +
-                  "  ".join(f"{nm} {v[i] / n:.0f}" for i, nm in enumerate(names)) + f"  total/step {sum(v[:5]) / n:.0f} cyc", flush=True)
+    for (H, W, C, heads) in STAGES:
+        nb, qkv, out, qb, bf = _attn_setup(H, W, C, heads)
+        ph = torch.zeros(6, dtype=torch.int64, device=DEV)
+        for _ in range(2):
+            _attn_diag(lib, qkv[0], out[0], bf, qb, H, W, C, heads, 3, ph=ph)
+        torch.cuda.synchronize()
+        v = ph.tolist()
+        n = max(v[5], 1)
+        names = ["wait-loads", "S-mma+loads", "softmax", "PV-mma", "store"]
+        print(f"attn phases {H}x{W} C{C}: steps {v[5]}  " + "  ".join(f"{nm} {v[i] / n:.0f}" for i, nm in enumerate(names)) +
+              f"  total/step {sum(v[:5]) / n:.0f} cyc", flush=True)
 
 
 def attn_skeleton(iters=20):
-    """The attention kernel's memory skeleton (gathers + stores only) vs the full kernel."""
+    """The attention kernel's memory skeleton (gathers + stores only) vs the full kernel and its ablations."""
     from panoswintransformerobjectdetection_b200 import _lib
     lib = _lib.load()
-    for (H, W, C, heads) in [(128, 256, 96, 3), (64, 128, 192, 6), (32, 64, 384, 12)]:
-        nb = max(2, int(400e6 // (B * H * W * 4 * C * 2)) + 1)
-        qkv = [torch.randn(B, H, W, 3 * C, device=DEV).bfloat16() for _ in range(nb)]
-        out = [torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
-        alpha = torch.randn(169, heads, device=DEV) * 0.1
-        beta = torch.randn(169, heads, device=DEV) * 0.1
-        qb = torch.randn(3 * C, device=DEV) * 0.1
-        hav = ops.window_hav_table(make_uv_hw2(H, W).to(DEV), 7, 3)
-        bt = ops.window_bias_tables(alpha, beta, 7)
-        bf = ops.window_bias_full(alpha, beta, make_uv_hw2(H, W).to(DEV), None, H, W, 7, 3, True)
-        for mode in (1, 0, 2, 3, 4):
-            def run(i):
-                rc = lib.psw_window_attn_fwd_profile(qkv[i].data_ptr(), out[i].data_ptr(), alpha.data_ptr(), beta.data_ptr(),
-                                                     bt.data_ptr(), qb.data_ptr(), hav.data_ptr(), bf.data_ptr() if mode >= 2 else None, B, H, W, C,
-                                                     heads, 7, 3, 32 ** -0.5, None, {0: 0, 1: 1, 2: 2, 3: 0, 4: 3}[mode], torch.cuda.current_stream().cuda_stream)
-                _lib.check(rc, "profile")
-            us = time_op(run, nb, iters)
-            print(f"attn {['tables  ', 'skeleton', 'fullbias-nobiasload', 'fullbias', 'fullbias-noqkvload'][mode]} {H}x{W} C{C}: {us:8.1f} us  {B * H * W * C * 8 / us / 1e3:7.0f} GB/s", flush=True)
+    for (H, W, C, heads) in STAGES:
+        nb, qkv, out, qb, bf = _attn_setup(H, W, C, heads)
+        res = []
+        for name, mode in (("full", 0), ("skeleton(pair schedule)", 1), ("no-bias-loads", 2), ("no-qkv-loads", 3)):
+            us = min(time_op(lambda i: _attn_diag(lib, qkv[i], out[i], bf, qb, H, W, C, heads, 3, mode=mode), nb, iters) for _ in range(2))
+            res.append(f"{name} {us:.1f} us {B * H * W * C * 8 / us / 1e3:.0f} GB/s")
+        print(f"attn {H}x{W} C{C}: " + "   ".join(res), flush=True)
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "phases":
@@ -155,7 +151,7 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "skeleton":
 
 
 def linear_modes(iters=20):
-    """GEMM diagnostics: which of loads / MMAs / stores bounds each shape (psw_debug_linear_mode), the stage-count and
+    """GEMM diagnostics: which of loads / MMAs / stores bounds each shape (psw_diag_linear_mode), the stage-count and
     tile-width sensitivity, and the cuBLAS time of the same product (library reference, no epilogue fusion)."""
     from panoswintransformerobjectdetection_b200 import _lib
     lib = _lib.load()
@@ -181,14 +177,14 @@ def linear_modes(iters=20):
         for name, mode in variants:
             if ((mode >> 16) & 0x1ff) and N % ((mode >> 16) & 0x1ff):
                 continue
-            lib.psw_debug_linear_mode(mode)
+            lib.psw_diag_linear_mode(mode)
             try:
                 us = time_op(lambda i: ops.linear(x[i], w, b, residual=y[i] if res else None, gelu=bool(gelu), out=y[i], out_dtype=od),
                              nb, iters)
                 line.append(f"{name} {us:.0f}")
             except Exception as e:  # noqa: BLE001
                 line.append(f"{name} ERR")
-            lib.psw_debug_linear_mode(0)
+            lib.psw_diag_linear_mode(0)
         yb = [torch.empty(M, N, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
         us = time_op(lambda i: torch.matmul(x[i], w.t(), out=yb[i]), nb, iters)
         line.append(f"cublas(no epi, bf16 out) {us:.0f}")
@@ -200,7 +196,7 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "linmodes":
 
 
 def linear_cycles():
-    """Per-role SM-cycle breakdown of CTA 0 of the tcgen05 GEMM (psw_debug_linear_mode bit 4)."""
+    """Per-role SM-cycle breakdown of CTA 0 of the tcgen05 GEMM (psw_diag_linear_mode bit 4)."""
     import ctypes
     from panoswintransformerobjectdetection_b200 import _lib
     lib = _lib.load()
@@ -217,12 +213,12 @@ def linear_cycles():
         w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
         b = torch.randn(N, device=DEV)
         for extra in (1 << 26, 1 << 27):
-            lib.psw_debug_linear_mode(16 | extra)
+            lib.psw_diag_linear_mode(16 | extra)
             for _ in range(2):
                 ops.linear(x, w, b, residual=y if res else None, gelu=bool(gelu), out=y, out_dtype=od)
             buf = (ctypes.c_longlong * 16)()
-            _lib.check(lib.psw_debug_linear_cycles(ctypes.cast(buf, ctypes.c_void_p)), "cycles")
-            lib.psw_debug_linear_mode(0)
+            _lib.check(lib.psw_diag_linear_cycles(ctypes.cast(buf, ctypes.c_void_p)), "cycles")
+            lib.psw_diag_linear_mode(0)
             v = list(buf)
             n = max(v[8], 1)
             print(f"linear M{M} N{N} K{K} gelu{gelu} res{res} {odt} {'pair' if extra >> 27 else '1cta'}: tiles {v[8]}  per tile (epilogue warp 0 sees every 2nd tile): " +
@@ -259,14 +255,14 @@ def linear_sweep(iters=20):
                 bn = (mode >> 16) & 0x1ff
                 if bn and (N % bn or bn > 256):
                     continue
-                lib.psw_debug_linear_mode(mode)
+                lib.psw_diag_linear_mode(mode)
                 try:
                     us = time_op(lambda i: ops.linear(x[i], w, b, residual=y[i] if res else None, gelu=bool(gelu), out=y[i], out_dtype=od),
                                  nb, iters)
                     best[name] = min(best.get(name, 1e9), us)
                 except Exception:  # noqa: BLE001
                     best[name] = float("nan")
-                lib.psw_debug_linear_mode(0)
+                lib.psw_diag_linear_mode(0)
         print(f"linear M{M} N{N} K{K} gelu{gelu} res{res} {odt} [us]: " + "  ".join(f"{k} {v:.1f}" for k, v in best.items()), flush=True)
 
 
@@ -275,29 +271,16 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "linsweep":
 
 
 def attn_hc(iters=20):
-    """Image-pairs-per-unit sweep of the batch-innermost attention kernel (profile entry, mode bits [8,12); 15 = the
-    window-pair kernel with the full bias table)."""
+    """Image-pairs-per-unit sweep of the batch-innermost attention kernel (variant bits [0,4); 15 = the window-pair
+    schedule)."""
     from panoswintransformerobjectdetection_b200 import _lib
     lib = _lib.load()
-    for (H, W, C, heads) in [(128, 256, 96, 3), (64, 128, 192, 6), (32, 64, 384, 12), (16, 32, 768, 24)]:
-        nb = max(2, int(400e6 // (B * H * W * 4 * C * 2)) + 1)
-        qkv = [torch.randn(B, H, W, 3 * C, device=DEV).bfloat16() for _ in range(nb)]
-        out = [torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
-        alpha = torch.randn(169, heads, device=DEV) * 0.1
-        beta = torch.randn(169, heads, device=DEV) * 0.1
-        qb = torch.randn(3 * C, device=DEV) * 0.1
-        hav = ops.window_hav_table(make_uv_hw2(H, W).to(DEV), 7, 3)
-        bt = ops.window_bias_tables(alpha, beta, 7)
-        bf = ops.window_bias_full(alpha, beta, make_uv_hw2(H, W).to(DEV), None, H, W, 7, 3, True)
+    for (H, W, C, heads) in STAGES:
+        nb, qkv, out, qb, bf = _attn_setup(H, W, C, heads)
         res = []
-        for hc, mode in ((0, 0), (0, 4), (1, 0), (2, 0), (4, 0), (8, 0), (15, 0)):     # mode 4: padding cells from the fp32 bias (old path)
-            def run(i):
-                rc = lib.psw_window_attn_fwd_profile(qkv[i].data_ptr(), out[i].data_ptr(), alpha.data_ptr(), beta.data_ptr(),
-                                                     bt.data_ptr(), qb.data_ptr(), hav.data_ptr(), bf.data_ptr(), B, H, W, C, heads, 7, 3, 32 ** -0.5, None,
-                                                     (hc << 8) | mode, torch.cuda.current_stream().cuda_stream)
-                _lib.check(rc, "profile")
-            us = min(time_op(run, nb, iters) for _ in range(3))
-            res.append(f"hc{hc if hc else '-auto'}{'-ldgpad' if mode == 4 else ''} {us:.1f}")
+        for hc in (0, 1, 2, 4, 8, 15):
+            us = min(time_op(lambda i: _attn_diag(lib, qkv[i], out[i], bf, qb, H, W, C, heads, 3, variant=hc), nb, iters) for _ in range(3))
+            res.append(f"hc{hc if hc else '-auto'} {us:.1f}")
         print(f"attn {H}x{W} C{C} h{heads}: " + "  ".join(res), flush=True)
 
 
@@ -362,10 +345,10 @@ def mlp(iters=20):
     print(f"MLP M{M}: fc1 {us1:.1f} us + fc2 {us2:.1f} us = {us1 + us2:.1f}   fused {us3:.1f} us  {byt / us3 / 1e3:.0f} GB/s", flush=True)
     from panoswintransformerobjectdetection_b200 import _lib
     lib = _lib.load()
-    for mode, name in ((2, "no-final-epilogue"), (8, "no-gelu-math"), (10, "no-gelu-math no-final-epilogue"), (4, "v1 kernel"), (6, "v1 no-final-epilogue")):
-        lib.psw_debug_mlp_mode(mode)
+    for mode, name in ((2, "no-final-epilogue"), (8, "no-gelu-math"), (10, "no-gelu-math no-final-epilogue")):
+        lib.psw_diag_mlp_mode(mode)
         us = time_op(lambda i: ops.mlp_fused(xn[i], w1, b1, w2, b2, x[i]), nb, iters)
-        lib.psw_debug_mlp_mode(0)
+        lib.psw_diag_mlp_mode(0)
         print(f"   fused {name}: {us:.1f} us", flush=True)
 
 

@@ -1,4 +1,6 @@
-import sys, torch
+import sys, os
+os.environ["PSW_DIAGNOSTICS"] = "1"
+import torch
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from panoswintransformerobjectdetection_b200 import ops, _lib
 lib = _lib.load()
@@ -7,9 +9,9 @@ dev = 'cuda:0'
 def check(M, N, K, gelu, res, od, force):
     x = torch.randn(M, K, device=dev).bfloat16(); w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16(); b = torch.randn(N, device=dev)
     r = torch.randn(M, N, device=dev).to(od) if res else None
-    lib.psw_debug_linear_mode((1 << 27) if force else (1 << 26))
+    lib.psw_diag_linear_mode((1 << 27) if force else (1 << 26))
     y = ops.linear(x, w, b, residual=r, gelu=gelu, out_dtype=od)
-    lib.psw_debug_linear_mode(0)
+    lib.psw_diag_linear_mode(0)
     torch.cuda.synchronize()
     ref = x.float() @ w.float().t() + b
     if gelu: ref = torch.nn.functional.gelu(ref)
