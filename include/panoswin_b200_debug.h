@@ -20,8 +20,8 @@ extern "C" {
 /* psw_window_attn_full_fwd plus: per-phase SM-cycle totals of CTA 0 in phase_cycles[6] (device, int64; NULL allowed):
  * {wait-for-loads, S MMA, softmax, P.V MMA, store, steps}; mode 1 = memory skeleton only (same gathers and stores,
  * no MMA / softmax; output = q rows), 2 = no bias loads, 3 = no q/k/v loads (results are then garbage);
- * variant bits [0,4): force the image pairs per unit of the batch-innermost schedule (15 = window-pair schedule),
- * bits [4,8): exp2 evaluation + 1 (1 = fp32 ex2, 2 = bf16x2 ex2, 3 = f16x2 ex2 with fp16 probabilities). */
+ * variant bits [0,4): force the image pairs per unit of the batch-innermost schedule (15 = window-pair schedule).
+ *  */
 PSW_API int psw_diag_window_attn_full(const void* qkv, void* out, const void* bias_full, const float* qkv_bias,
                                       int B, int H, int W, int C, int heads, int window, int shift, int pano_mode,
                                       float scale, long long* phase_cycles, int mode, int variant, void* stream);

@@ -6,12 +6,12 @@
 // A "unit" is one (window, head): 49 tokens x head_dim 32.  The tensor-core tile has 128 rows = two units:
 //   S[128x128] = [Q_u0;Q_u1] . [K_u0;K_u1]^T      tcgen05.mma M=128 N=128 K=32; only the two diagonal 64x64
 //                                                 blocks are used (the tensor pipe is far from the bound)
-//   O[128x64]  = P[128x64 keys] . [V_u0 | V_u1]   tcgen05.mma M=128 N=64 K=64, P read from TMEM (16-bit),
+//   O[128x64]  = P[128x64 keys] . [V_u0 | V_u1]   tcgen05.mma M=128 N=64 K=64, P read from TMEM (bf16),
 //                                                 V consumed MN-major straight from its [key][dim] rows;
 //                                                 rows of unit u use output columns [32u, 32u+32)
 // Thread r owns tile row r (TMEM lane r): tcgen05.ld of its 49 logits, t = S * (scale * log2 e) + bias (every
 // additive term -- great-circle bias, relative-position bias, planar shift mask -- comes precomputed and already
-// multiplied by log2 e from psw_window_bias_full), row maximum, exp2, un-normalised 16-bit P back to TMEM, finally
+// multiplied by log2 e from psw_window_bias_full), row maximum, exp2, un-normalised bf16 P back to TMEM, finally
 // the O row * 1/sum stored with 128-bit stores at the token's UN-shifted position.  q/k/v rows are gathered with
 // cp.async (16 B) straight from the un-shifted [B,H,W,3C] qkv tensor into the 64B-swizzled UMMA layout: pano shift
 // with longitude wrap-around, the odd-W zero column, window padding (padding tokens = qkv bias) and partition are
@@ -41,22 +41,12 @@ constexpr int AT_THREADS = 128;
 constexpr int AT_PART_BYTES = 128 * 64;            // 128 rows x 64 B (32 bf16), SWIZZLE_64B
 constexpr int AT_BUF_BYTES = 3 * AT_PART_BYTES;    // q, k, v
 constexpr int AT_TMEM_COLS = 128;
-constexpr int AT_P_COL = 0;                        // P (16-bit pairs): TMEM columns [0, 32)
+constexpr int AT_P_COL = 0;                        // P (bf16 pairs): TMEM columns [0, 32)
 constexpr int AT_O_COL = 32;                       // O (fp32): TMEM columns [32, 96)
 constexpr int AT_SUM_COL = 96;                     // row sums of P (fp32, batch-innermost kernel): TMEM columns [96, 112)
 constexpr int AT_CTAS_PER_SM = 4;                  // 128 registers per thread (no spills), 4 x 128 TMEM columns
 constexpr int AT_FULL_CHUNKS = 13;                 // float4 chunks per bias row: 49 logits padded to 52
 constexpr float LOG2E = 1.4426950408889634f;
-
-// how exp2 of the shifted logits is evaluated and what the probabilities are stored as (A operand of the P.V MMA)
-enum : int {
-  AT_EXP_F32 = 0,      // ex2.approx.ftz.f32 per element, pairs packed to bf16x2
-  AT_EXP_BF16X2 = 1,   // (t - max) packed to bf16x2, ex2.approx.ftz.bf16x2: one MUFU op per PAIR, result is P
-  AT_EXP_F16X2 = 2     // (t - max) packed to f16x2, ex2.approx.f16x2; P is fp16 (kind::f16 MMA with A = f16, B = bf16)
-};
-#ifndef PSW_ATTN_EXP
-#define PSW_ATTN_EXP AT_EXP_F32
-#endif
 
 __device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
@@ -82,37 +72,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// two exp2 per MUFU op: pack (lo, hi) to a 16-bit pair, evaluate, the result IS the packed probability pair
-__device__ __forceinline__ uint32_t exp2_pair_bf16(float lo, float hi) {
-  uint32_t x, y;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(hi), "f"(lo));
-  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t exp2_pair_f16(float lo, float hi) {
-  uint32_t x, y;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(hi), "f"(lo));
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
-// kind::f16 instruction descriptor with independent A / B element formats (0 = f16, 1 = bf16), fp32 accumulate
-__host__ __device__ inline uint32_t umma_idesc_16(int M, int N, int a_fmt, int b_fmt, int a_mn_major, int b_mn_major) {
-  uint32_t d = 0;
-  d |= 1u << 4;
-  d |= (uint32_t)(a_fmt & 7) << 7;
-  d |= (uint32_t)(b_fmt & 7) << 10;
-  d |= (uint32_t)(a_mn_major & 1) << 15;
-  d |= (uint32_t)(b_mn_major & 1) << 16;
-  d |= (uint32_t)(N >> 3) << 17;
-  d |= (uint32_t)(M >> 4) << 24;
-  return d;
-}
-
 // bias + softmax numerator of one row: sr = the 49 raw logits of TMEM, bias = the row's additive terms (x log2 e),
-// scale_l2 = scale * log2 e.  Writes the un-normalised probabilities as 16-bit pairs (key columns 49..63 zero) and, for
+// scale_l2 = scale * log2 e.  Writes the un-normalised probabilities as bf16 pairs (key columns 49..63 zero) and, for
 // the fp32 schedule that needs it, returns their fp32 sum.  Rows that do not exist (tile rows 49..63 of a unit, the
 // second unit of an odd tail) are NOT zeroed: a row of P only feeds the same row of O, which is never stored.
-template <int EXPM, int N>
+template <int N>
 __device__ __forceinline__ float softmax_row(const uint32_t (&sr)[N], const float* bias, float scale_l2, uint32_t (&pk)[32]) {
   float t[N];
 #pragma unroll
@@ -125,18 +89,12 @@ __device__ __forceinline__ float softmax_row(const uint32_t (&sr)[N], const floa
   for (int k = 0; k < 32; ++k) {
     uint32_t w = 0u;
     if (2 * k < N) {
-      const float x0 = t[2 * k] - mx;
-      const float x1 = (2 * k + 1 < N) ? t[2 * k + 1] - mx : -INFINITY;
-      if constexpr (EXPM == AT_EXP_F32) {
-        const float p0 = fast_exp2(x0);
-        const float p1 = (2 * k + 1 < N) ? fast_exp2(x1) : 0.f;
-        sum += p0 + p1;
-        w = pack_bf16x2(p0, p1);
-      } else if constexpr (EXPM == AT_EXP_BF16X2) {
-        w = exp2_pair_bf16(x0, x1);
-      } else {
-        w = exp2_pair_f16(x0, x1);
-      }
+      // (packed ex2.approx.bf16x2 / f16x2 were tried: sm_100a issues one MUFU.EX2 per element either way, so they
+      // save nothing, and fp16 probabilities against bf16 values are not a legal kind::f16 operand pair)
+      const float p0 = fast_exp2(t[2 * k] - mx);
+      const float p1 = (2 * k + 1 < N) ? fast_exp2(t[2 * k + 1] - mx) : 0.f;
+      sum += p0 + p1;
+      w = pack_bf16x2(p0, p1);
     }
     pk[k] = w;
   }
@@ -169,12 +127,11 @@ struct Step {
   int n;                  // running step count of this CTA (parity selects the buffers)
 };
 
-template <int WS, int EXPM>
+template <int WS>
 __global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
 window_attn_pair_kernel(const AttnParams p) {
   constexpr int N = WS * WS;                     // tokens per window (<= 64)
   static_assert(N == 49, "TMEM row load below is written for 49 logits");
-  constexpr int P_FMT = EXPM == AT_EXP_F16X2 ? 0 : 1;
 
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B by OFFSETTING the __shared__ array (keeps the shared address space: LDS/STS, not generic LD/ST)
@@ -397,7 +354,7 @@ window_attn_pair_kernel(const AttnParams p) {
         sr[48] = t1;
       }
       uint32_t pk[32];
-      sum = softmax_row<AT_EXP_F32, N>(sr, bfull, p.scale_l2, pk);   // fp32 sums: this schedule has no sum MMA
+      sum = softmax_row<N>(sr, bfull, p.scale_l2, pk);   // fp32 sums: this schedule has no sum MMA
       tmem_st_x32(tmem_base + lane_base + AT_P_COL, pk);
       tmem_st_wait();
     }
@@ -457,7 +414,6 @@ window_attn_pair_kernel(const AttnParams p) {
   }
   if (prof)
     for (int k = 0; k < 6; ++k) p.dbg[k] = ph[k];
-  (void)P_FMT;
 
   cp_async_wait<0>();
   tc_fence_before();
@@ -492,21 +448,47 @@ struct BiIt {
 
 __device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic) { return magic ? __umulhi(x, magic) : x; }
 
-template <int WS, int EXPM>
+// Shared-memory map of the batch-innermost kernel (offsets from the 1024-byte aligned base): two stages of
+// [q | k | v] x [128 rows (img*64 + token) x 64 B] SWIZZLE_64B, then the per-unit data.
+constexpr int BI_MISC = 2 * AT_BUF_BYTES;          // token maps, row offsets, padding rows, barriers, TMEM slot
+constexpr int BI_SLOTS = 4;                        // per-unit slots: the units of steps n .. n+3 are alive at once
+constexpr int BI_S_COL = 0;                        // S (fp32, 64 columns shared by both images) then P (bf16 pairs, 32 columns)
+constexpr int BI_O_COL = 64;                       // O (fp32): image h in columns [64 + 32h, 96 + 32h)
+
+// D[tmem] (+)= A[smem] * B[smem] with the output lanes whose mask bit is set left untouched (disable-output-lane)
+__device__ __forceinline__ void umma_ss_masked(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3) : "memory");
+}
+
+// The two images of a tile share the 64 key columns of S: S = [Q_img0; Q_img1] . K_img^T is issued once per image with
+// N = 64 and the OTHER image's 64 output lanes disabled (tcgen05.mma disable-output-lane), so both land in TMEM columns
+// [0, 64).  S then needs 64 columns instead of 128, O gets its own 64, and the S MMA of step n+1 can be issued as soon
+// as the P.V MMA of step n has consumed P -- BEFORE O(n) is drained and stored.  Per step and CTA:
+//   (a) wait S(n)
+//   (b) softmax(n): tcgen05.ld S, + bias, max, exp2, row sum (registers), bf16 P -> TMEM;          barrier
+//   (c) one thread: P.V MMA(n)        (e) wait P.V(n)
+//   (f) q / k / v of step n+1 (requested a whole step ago) have landed; proxy fence;               barrier;  S MMA(n+1)
+//   (g) q / k / v rows of step n+2 -> the stage S(n) and P.V(n) have released; unit data of step n+3
+//   (h) O(n) * 1/sum -> global, while S(n+1) runs on the tensor core
+// so the S MMA round trip is hidden behind the gather issue and the store.  There is exactly ONE proxy fence per step
+// and no cp.async request is younger than a whole step when it executes: fence.proxy.async waits for copies in flight
+// (measured: with a fresh group behind it, the fence costs the full memory latency).
+template <int WS>
 __global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
 window_attn_bi_kernel(const AttnParams p) {
   constexpr int N = WS * WS;
   static_assert(N == 49, "TMEM row load below is written for 49 logits");
-  constexpr int P_FMT = EXPM == AT_EXP_F16X2 ? 0 : 1;      // element format of P: 0 = f16, 1 = bf16
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* bufs = smem;                                                  // [2 stages][3][128 x 64 B]
-  int* src = reinterpret_cast<int*>(bufs + 2 * AT_BUF_BYTES);            // [2 unit slots][64]: token index in the image or -1
-  int* soff = src + 2 * 64;                                              // [2 unit slots][64]: token index * 3C (element offset of the qkv row)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(soff + 2 * 64);           // [2]: S ready, O ready
+  int* src = reinterpret_cast<int*>(smem + BI_MISC);                     // [BI_SLOTS][64]: token index in the image or -1
+  int* soff = src + BI_SLOTS * 64;                                       // [BI_SLOTS][64]: token index * 3C (element offset of the qkv row)
+  uint4* padrow = reinterpret_cast<uint4*>(soff + BI_SLOTS * 64);        // [BI_SLOTS][3][4]: bf16 qkv bias of the unit's head
+  uint64_t* bars = reinterpret_cast<uint64_t*>(padrow + BI_SLOTS * 12);  // [2]: S ready, O ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  uint8_t* ones = bufs + 2 * AT_BUF_BYTES + 2048;                        // 1 KB of bf16 1.0: B operand of the row-sum MMA
-  uint4* padrow = reinterpret_cast<uint4*>(bufs + 2 * AT_BUF_BYTES + 3072); // [2 unit slots][3][4]: bf16 qkv bias of the unit's head
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -516,9 +498,8 @@ window_attn_bi_kernel(const AttnParams p) {
   const int BP = (p.B + 1) / 2;                            // steps per item
   const int G = gridDim.x;
 
-  for (int i = tid; i < 2 * AT_BUF_BYTES / 16; i += AT_THREADS)
-    reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0, 0, 0, 0);          // padding rows must stay finite
-  if (tid < 64) reinterpret_cast<uint4*>(ones)[tid] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  for (int i = tid; i < BI_MISC / 16; i += AT_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);          // zero K-slots of Q, padding rows: must stay finite
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -544,7 +525,7 @@ window_attn_bi_kernel(const AttnParams p) {
   const int CH = p.hc;                                     // image pairs per unit
   const int NCH = p.nch;                                   // chunks per (window position, head)
 
-  const int unit = tid >> 6;                               // warp-uniform: which image of the pair
+  const int img = tid >> 6;                                // warp-uniform: which image of the pair my row belongs to
   const int ti = tid & 63;
   const int ic = ti < N ? ti : 0;
   const int ri = ic / WS, ci = ic - ri * WS;
@@ -565,23 +546,25 @@ window_attn_bi_kernel(const AttnParams p) {
     ++it.ic;
     if (it.u < n_units) decode(it);
   };
-  // per-unit data -> shared-memory slot (ic & 1): token map of the window position (threads 0..63) and the head's
+  // per-unit data -> shared-memory slot (ic % BI_SLOTS): token map of the window position (threads 0..63) and the head's
   // slice of the bf16 qkv bias for padding cells (threads 64..75)
   auto prep_item = [&](const BiIt& it) {
+    const int slot = it.ic & (BI_SLOTS - 1);
     if (tid < 64) {
       int t = -1;
       if (tid < N) {
         const int wr = (int)fast_div((uint32_t)it.wi, p.magic_nww), wc = it.wi - wr * g.nWw;
         t = source_token(g, wr * WS + ri, wc * WS + ci);
       }
-      src[(it.ic & 1) * 64 + tid] = t;
-      soff[(it.ic & 1) * 64 + tid] = t * C3;
+      src[slot * 64 + tid] = t;
+      soff[slot * 64 + tid] = t * C3;
     } else if (tid < 76) {                                 // [q|k|v][4 x 16 B]
       const int j = tid - 64;
-      padrow[(it.ic & 1) * 12 + j] = bias_chunk((j >> 2) * C + it.e * 32 + (j & 3) * 8);
+      padrow[slot * 12 + j] = bias_chunk((j >> 2) * C + it.e * 32 + (j & 3) * 8);
     }
   };
-  // loader role of this thread: 16-byte chunk lc of tokens lt0 and lt0 + 32 of both images
+  // loader role of this thread: 16-byte chunk lc of tokens lt0 and lt0 + 32 of both images; row = img*64 + token of
+  // 64-byte rows (SWIZZLE_64B: chunk ^ ((row >> 1) & 3)), the same offset in the q, k and v parts
   const bool ld_ok1 = lt0 + 32 < N;                        // token lt0 (< 32) always exists; lt0 + 32 only below 49
   uint32_t ld_dst[4];
 #pragma unroll
@@ -590,13 +573,14 @@ window_attn_bi_kernel(const AttnParams p) {
     ld_dst[k] = (uint32_t)(row * 64 + ((lc ^ ((row >> 1) & 3)) << 4));
   }
   const int64_t img_stride = HW * C3;                      // elements per image of the qkv tensor
-  auto issue_loads = [&](const BiIt& it, int stage) {
-    uint8_t* base = bufs + stage * AT_BUF_BYTES;
-    const int* so = soff + (it.ic & 1) * 64;
+  auto issue_loads = [&](const BiIt& it, int stage) {       // all q / k / v rows of a step into `stage`
+    const int slot = it.ic & (BI_SLOTS - 1);
+    const int* so = soff + slot * 64;
     const int o0 = so[lt0];
     const int o1 = ld_ok1 ? so[lt0 + 32] : 0;
     const bf16* g0 = p.qkv + (int64_t)(2 * it.bp) * img_stride + it.e * 32 + lc * 8;
     const bool img1 = 2 * it.bp + 1 < p.B;
+    uint8_t* base = smem + stage * AT_BUF_BYTES;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if ((k & 1) && !ld_ok1) continue;
@@ -609,7 +593,7 @@ window_attn_bi_kernel(const AttnParams p) {
         cp_async16(dst + AT_PART_BYTES, grow + C);
         cp_async16(dst + 2 * AT_PART_BYTES, grow + 2 * C);
       } else {                                             // padding cell: q/k/v = bias (staged per unit by prep_item)
-        const uint4* pr = padrow + (it.ic & 1) * 12 + lc;
+        const uint4* pr = padrow + slot * 12 + lc;
         *reinterpret_cast<uint4*>(dst) = pr[0];
         *reinterpret_cast<uint4*>(dst + AT_PART_BYTES) = pr[4];
         *reinterpret_cast<uint4*>(dst + 2 * AT_PART_BYTES) = pr[8];
@@ -631,22 +615,42 @@ window_attn_bi_kernel(const AttnParams p) {
 #pragma unroll
   for (int k = 0; k < 4 * AT_FULL_CHUNKS; ++k) bias[k] = 0.f;
 
-  // software pipeline over steps: cur (computed now), nxt (its q/k/v are in flight), nn (its unit data is prepared)
-  BiIt cur, nxt, nn;
+  const bool no_loads = kDiag && p.mode == 3;
+  auto issue_s_mma = [&](int stage) {                      // one thread: S(img) = [Q_img0; Q_img1] . K_img^T, other image's lanes masked
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+    const uint32_t sq = smem_u32(smem + stage * AT_BUF_BYTES);
+    const uint64_t da = umma_smem_desc(sq, 16, 512, UMMA_SWIZZLE_64B);
+    const uint64_t db0 = umma_smem_desc(sq + AT_PART_BYTES, 16, 512, UMMA_SWIZZLE_64B);
+    const uint64_t db1 = umma_smem_desc(sq + AT_PART_BYTES + 64 * 64, 16, 512, UMMA_SWIZZLE_64B);
+    umma_ss_masked(tmem_base + BI_S_COL, da, db0, idesc, 0, 0u, 0u, ~0u, ~0u);          // image 0: lanes 0..63
+    umma_ss_masked(tmem_base + BI_S_COL, da + 2, db0 + 2, idesc, 1, 0u, 0u, ~0u, ~0u);  // head_dim 16..31: +32 B in the swizzle row
+    umma_ss_masked(tmem_base + BI_S_COL, da, db1, idesc, 0, ~0u, ~0u, 0u, 0u);          // image 1: lanes 64..127
+    umma_ss_masked(tmem_base + BI_S_COL, da + 2, db1 + 2, idesc, 1, ~0u, ~0u, 0u, 0u);
+    umma_commit(&bars[0]);
+  };
+
+  // software pipeline over steps: cur = n (computed now), nxt = n+1, nn = n+2, n3 = n+3
+  BiIt cur, nxt, nn, n3;
   cur.u = blockIdx.x; cur.ic = 0; cur.e = 0; cur.wi = 0; cur.bp = 0; cur.bp_end = 0;
   if (cur.u < n_units) decode(cur);
-  nxt = cur;
-  advance(nxt);
-  nn = nxt;
-  advance(nn);
+  nxt = cur; advance(nxt);
+  nn = nxt; advance(nn);
+  n3 = nn; advance(n3);
   if (cur.u < n_units) {
     prep_item(cur);
     if (nxt.u < n_units && nxt.ic != cur.ic) prep_item(nxt);
+    if (nn.u < n_units && nn.ic != nxt.ic) prep_item(nn);
     __syncthreads();
-    issue_loads(cur, 0);
+    if (!no_loads) issue_loads(cur, 0);
+    if (nxt.u < n_units && !no_loads) issue_loads(nxt, 1);
+    cp_async_commit();
     load_bias(cur);
+    cp_async_wait<0>();
+    fence_async_shared();
+    __syncthreads();
+    if (tid == 0) issue_s_mma(0);
   }
-  cp_async_commit();
 
   uint32_t par = 0;
   long long ph[6] = {0, 0, 0, 0, 0, 0};
@@ -655,33 +659,18 @@ window_attn_bi_kernel(const AttnParams p) {
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     if (prof) c0 = clock64();
     const bool has_next = nxt.u < n_units;
-    const int my_b = 2 * cur.bp + unit;
-    // ---- 1. this step's q/k/v (requested one step ago) have landed
-    cp_async_wait<0>();
-    fence_async_shared();
-    __syncthreads();
-    const int ts = src[(cur.ic & 1) * 64 + ic];            // my token (read now: the slot may be re-used for `nn` below)
-    if (prof) c1 = clock64();
-    // ---- 2. S = Q . K^T (both images at once, block diagonal)
-    const uint32_t sq = smem_u32(bufs + (par & 1) * AT_BUF_BYTES);
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
-      const uint64_t dq = umma_smem_desc(sq, 16, 512, UMMA_SWIZZLE_64B);
-      const uint64_t dk = umma_smem_desc(sq + AT_PART_BYTES, 16, 512, UMMA_SWIZZLE_64B);
-      umma_ss(tmem_base, dq, dk, idesc, 0);
-      umma_ss(tmem_base, dq + 2, dk + 2, idesc, 1);
-      umma_commit(&bars[0]);
-    }
-    if (has_next && !(kDiag && p.mode == 3)) issue_loads(nxt, (par & 1) ^ 1);   // whole next step into the other stage
-    cp_async_commit();
+    const int stage = (int)(par & 1);
+    const int my_b = 2 * cur.bp + img;
+    const int ts = src[(cur.ic & (BI_SLOTS - 1)) * 64 + ic];   // my token
+    // ---- (a) S(n) is ready
     mbar_wait(&bars[0], par);
     tc_fence_after();
-    if (prof) c2 = clock64();
-    // ---- 3. bias + softmax on my row
+    if (prof) c1 = clock64();
+    // ---- (b) bias + softmax on my row
+    float sum;
     {
       uint32_t sr[N];
-      const uint32_t s_addr = tmem_base + lane_base + (uint32_t)(unit * 64);
+      const uint32_t s_addr = tmem_base + lane_base + BI_S_COL;
       {
         uint32_t t32[32], t16[16], t1;
         tmem_ld_x32(s_addr, t32);
@@ -694,44 +683,48 @@ window_attn_bi_kernel(const AttnParams p) {
         for (int k = 0; k < 16; ++k) sr[32 + k] = t16[k];
         sr[48] = t1;
       }
-      uint32_t pk[32];                                     // the row sum comes from the tensor core (P . ones)
-      (void)softmax_row<EXPM, N>(sr, bias, p.scale_l2, pk);
-      tmem_st_x32(tmem_base + lane_base + AT_P_COL, pk);
+      uint32_t pk[32];
+      sum = softmax_row<N>(sr, bias, p.scale_l2, pk);
+      tmem_st_x32(tmem_base + lane_base + BI_S_COL, pk);
       tmem_st_wait();
     }
     if (has_next && nxt.ic != cur.ic) load_bias(nxt);      // new (window, head): the bias registers are free again
     tc_fence_before();
     __syncthreads();
-    if (prof) c3 = clock64();
-    // ---- 4. O = P . [V_img0 | V_img1]
+    if (prof) c2 = clock64();
+    // ---- (c) O = P . [V_img0 | V_img1]
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t idesc = umma_idesc_16(128, 64, P_FMT, 1, 0, 1);
-      const uint32_t idesc1 = umma_idesc_16(128, 16, P_FMT, 1, 0, 1);    // row sums: P . ones[keys][16]
-      const uint32_t sv = sq + 2 * AT_PART_BYTES;
-      const uint64_t d1 = umma_smem_desc(smem_u32(ones), 4096, 512, UMMA_SWIZZLE_64B);
+      const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);       // B (V) is MN-major: [key][dim] rows
+      const uint32_t sv = smem_u32(smem + stage * AT_BUF_BYTES + 2 * AT_PART_BYTES);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint64_t dv = umma_smem_desc(sv + k * 1024, 4096, 512, UMMA_SWIZZLE_64B);
-        umma_ts(tmem_base + AT_O_COL, tmem_base + AT_P_COL + k * 8, dv, idesc, k > 0);
-        umma_ts(tmem_base + AT_SUM_COL, tmem_base + AT_P_COL + k * 8, d1, idesc1, k > 0);
+      for (int k = 0; k < 4; ++k) {                                // 16 keys per MMA = two 8-key groups of 512 B
+        const uint64_t dvd = umma_smem_desc(sv + k * 1024, 4096, 512, UMMA_SWIZZLE_64B);
+        umma_ts(tmem_base + BI_O_COL, tmem_base + BI_S_COL + k * 8, dvd, idesc, k > 0);
       }
       umma_commit(&bars[1]);
     }
-    // while the MMA runs: unit data of the step after next when it starts a new unit (its loader runs after the
-    // next barriers)
-    if (nn.u < n_units && nn.ic != nxt.ic) prep_item(nn);
+    // ---- (e) P.V(n) done: P and this stage's V are free
     mbar_wait(&bars[1], par);
     tc_fence_after();
+    if (prof) c3 = clock64();
+    // ---- (f) the ONE proxy fence of the step: q / k / v of step n+1 (requested a whole step ago) have landed
+    cp_async_wait<0>();
+    fence_async_shared();
+    __syncthreads();
+    if (tid == 0 && has_next) issue_s_mma(stage ^ 1);
+    // ---- (g) q / k / v rows of step n+2 into the stage that S(n) and P.V(n) have released; unit data of step n+3
+    if (nn.u < n_units && !no_loads) issue_loads(nn, stage);
+    cp_async_commit();
+    if (n3.u < n_units && n3.ic != nn.ic) prep_item(n3);
     if (prof) c4 = clock64();
-    // ---- 5. normalise and store my output row at the token's un-shifted position
+    // ---- (h) normalise and store my output row at the token's un-shifted position
     {
-      uint32_t orow[32], osum;
-      tmem_ld_x32(tmem_base + lane_base + AT_O_COL + (uint32_t)(unit * 32), orow);
-      tmem_ld_x1(tmem_base + lane_base + AT_SUM_COL, osum);
+      uint32_t orow[32];
+      tmem_ld_x32(tmem_base + lane_base + BI_O_COL + (uint32_t)(img * 32), orow);
       tmem_ld_wait();
       if (ti < N && my_b < p.B && ts >= 0) {
-        const float inv = 1.0f / __uint_as_float(osum);
+        const float inv = 1.0f / sum;
         uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)my_b * HW + ts) * C + cur.e * 32);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -744,7 +737,7 @@ window_attn_bi_kernel(const AttnParams p) {
         }
       }
     }
-    tc_fence_before();
+    tc_fence_before();       // the next barrier orders these TMEM reads before the next P.V MMA overwrites O
     if (prof) {
       const long long c5 = clock64();
       ph[0] += c1 - c0; ph[1] += c2 - c1; ph[2] += c3 - c2; ph[3] += c4 - c3; ph[4] += c5 - c4; ph[5] += 1;
@@ -752,7 +745,8 @@ window_attn_bi_kernel(const AttnParams p) {
     par ^= 1;
     cur = nxt;
     nxt = nn;
-    advance(nn);
+    nn = n3;
+    advance(n3);
   }
   if (prof)
     for (int k = 0; k < 6; ++k) p.dbg[k] = ph[k];
@@ -769,7 +763,7 @@ window_attn_bi_kernel(const AttnParams p) {
 static size_t attn_tc_smem_bytes() {
   size_t b = 1024;                                   // alignment slack
   b += 2 * AT_BUF_BYTES;
-  b += 3072 + 512;                                   // token maps + row offsets / barriers / TMEM slot (2 KB), ones tile (1 KB), padding rows
+  b += 3072 + 512;                                   // token maps + row offsets, padding rows, barriers, TMEM slot
   // keep the CTA count per SM at AT_CTAS_PER_SM (register budget 65536 / (3 * 128) = 170 per thread)
   const size_t floor_bytes = (size_t)(233472 / (AT_CTAS_PER_SM + 1)) - 1024 + 16;
   return b < floor_bytes ? floor_bytes : b;
@@ -839,7 +833,7 @@ static int launch_attn(K kern, const AttnParams& p, size_t smem, cudaStream_t st
 }
 
 // `variant` (diagnostics build only; 0 in production): bits [0,4) force the image pairs per unit (15 = window-pair
-// schedule), bits [4,8) select the exp2 evaluation + 1 (0 = the build's default PSW_ATTN_EXP).
+// schedule).
 int window_attn_tc(const bf16* qkv, bf16* out, const float* qkv_bias, const void* bias_full, int B, int H, int W, int C,
                    int heads, int window, int shift, int pano, float scale, long long* dbg, int mode, int variant,
                    cudaStream_t st) {
@@ -857,8 +851,6 @@ int window_attn_tc(const bf16* qkv, bf16* out, const float* qkv_bias, const void
   p.mode = kDiag ? mode : 0;
   p.n_windows = B * p.g.nWh * p.g.nWw;
   const int forced = kDiag ? (variant & 15) : 0;
-  int expm = PSW_ATTN_EXP;
-  if (kDiag && ((variant >> 4) & 15)) expm = ((variant >> 4) & 15) - 1;
   const size_t smem = attn_tc_smem_bytes();
   const bool batch_inner = B >= 4 && forced != 15 && p.mode != 1;
   if (!batch_inner) {
@@ -867,7 +859,7 @@ int window_attn_tc(const bf16* qkv, bf16* out, const float* qkv_bias, const void
     // stages better (items are dealt out in contiguous ranges; -10% at stage 3)
     p.hc = 1;
     p.n_items = ((p.n_windows + 1) / 2) * heads;
-    return launch_attn(window_attn_pair_kernel<7, AT_EXP_F32>, p, smem, st, "window_attn_pair_kernel");
+    return launch_attn(window_attn_pair_kernel<7>, p, smem, st, "window_attn_pair_kernel");
   }
   // image pairs per unit: as many as possible (the bias row and the token map are fetched once per unit) while the
   // units still spread evenly over the resident CTAs (CTA c runs units c, c + grid, ...)
@@ -890,11 +882,7 @@ int window_attn_tc(const bf16* qkv, bf16* out, const float* qkv_bias, const void
   p.magic_nww = magic(p.g.nWw);
   PSW_REQUIRE((uint64_t)(p.n_items + num_sms() * AT_CTAS_PER_SM) * (uint64_t)(heads > p.nch ? heads : p.nch) < (1ull << 32),
               PSW_ERR_UNSUPPORTED, "psw_window_attn_full_fwd: too many work units");
-  switch (expm) {
-    case AT_EXP_BF16X2: return launch_attn(window_attn_bi_kernel<7, AT_EXP_BF16X2>, p, smem, st, "window_attn_bi_kernel");
-    case AT_EXP_F16X2:  return launch_attn(window_attn_bi_kernel<7, AT_EXP_F16X2>, p, smem, st, "window_attn_bi_kernel");
-    default:            return launch_attn(window_attn_bi_kernel<7, AT_EXP_F32>, p, smem, st, "window_attn_bi_kernel");
-  }
+  return launch_attn(window_attn_bi_kernel<7>, p, smem, st, "window_attn_bi_kernel");
 }
 
 }  // namespace psw

@@ -52,7 +52,7 @@ def _attn_diag(lib, qkv, out, bf, qb, H, W, C, heads, shift, ph=None, mode=0, va
 
 
 def attn(iters):
-    """The production attention kernel per stage, and the exp2 variants (diagnostics build: variant bits [4,8))."""
+    """The production attention kernel per stage."""
     from panoswintransformerobjectdetection_b200 import _lib
     lib = _lib.load()
     for (H, W, C, heads) in STAGES:
@@ -63,10 +63,6 @@ def attn(iters):
             us = min(time_op(lambda i: ops.window_attention_full(qkv[i], bf, qb, heads, 7, shift, True, 32 ** -0.5, out=out[i]), nb, iters)
                      for _ in range(2))
             res.append(f"default {us:7.1f} us {byt / us / 1e3:6.0f} GB/s")
-            for name, var in (("ex2-f32", 1 << 4), ("ex2-bf16x2", 2 << 4), ("ex2-f16x2", 3 << 4)):
-                us = min(time_op(lambda i: _attn_diag(lib, qkv[i], out[i], bf, qb, H, W, C, heads, shift, variant=var), nb, iters)
-                         for _ in range(2))
-                res.append(f"{name} {us:7.1f} us {byt / us / 1e3:6.0f} GB/s")
             print(f"attn B{B} {H}x{W} C{C} h{heads} s{shift}: " + "   ".join(res), flush=True)
 
 
@@ -126,7 +122,7 @@ def attn_phases():
         torch.cuda.synchronize()
         v = ph.tolist()
         n = max(v[5], 1)
-        names = ["wait-loads", "S-mma+loads", "softmax", "PV-mma", "store"]
+        names = ["wait-S", "softmax", "PV-mma", "fence+barrier+S-issue+loads", "store"]
         print(f"attn phases {H}x{W} C{C}: steps {v[5]}  " + "  ".join(f"{nm} {v[i] / n:.0f}" for i, nm in enumerate(names)) +
               f"  total/step {sum(v[:5]) / n:.0f} cyc", flush=True)
 
