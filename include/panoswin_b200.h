@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PSW_ABI_VERSION 2   /* bumped with every change of a prototype below */
+#define PSW_ABI_VERSION 3   /* bumped with every change of a prototype below */
 
 #if defined(__GNUC__)
 #define PSW_API __attribute__((visibility("default")))
@@ -218,6 +218,65 @@ PSW_API int psw_patch_conv_fwd(const void* x, const void* w, const float* bias, 
 
 /* dtype conversion helper for activations entering / leaving the bf16 path: n elements. */
 PSW_API int psw_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);
+
+
+/* ================================================================================================================
+ * Backward entry points (training: the reference obtains all of these from torch autograd).
+ * Same conventions as above.  Gradients that are REDUCTIONS over the batch (dgamma, dbeta, dw, db, dalpha, dbeta
+ * tables, dqkv_bias) are zeroed by the call (cudaMemsetAsync on `stream`) and then accumulated with fp32 atomics: the
+ * summation order, hence the last bits, varies from run to run.
+ * ================================================================================================================ */
+
+/*
+ * Gradient of psw_layernorm_fwd (without the position add, whose gradient is the row sum of dy):
+ * x [rows, C] (x_dtype), dy [rows, C] (dy_dtype) -> dx [rows, C] (x_dtype), dgamma / dbeta [C] fp32 (both or neither).
+ * stats_ws: scratch of 2 * rows floats (mean, rstd per row).  Reference: nn.LayerNorm at :504, :534, :768-772, :975-976.
+ */
+PSW_API int psw_layernorm_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgamma, float* dbeta,
+                              float* stats_ws, int64_t rows, int C, float eps, int x_dtype, int dy_dtype, void* stream);
+
+/*
+ * Gradient of psw_patch_merge_ln_fwd: x [B, H, W, C] (x_dtype), dy [B, ceil(H/2)*ceil(W/2), 4C] (dy_dtype) ->
+ * dx [B, H, W, C] (x_dtype: the 2x2 gather's scatter is folded into the store), dgamma / dbeta [4C] fp32.
+ * stats_ws: 2 * B * ceil(H/2) * ceil(W/2) floats.  Reference: PatchMerging.forward :563-574.
+ */
+PSW_API int psw_patch_merge_ln_bwd(const void* x, const void* dy, const float* gamma, void* dx, float* dgamma,
+                                   float* dbeta, float* stats_ws, int B, int H, int W, int C, float eps, int x_dtype,
+                                   int dy_dtype, void* stream);
+
+/*
+ * Gradients of y = x . w^T + bias (psw_linear_fwd without epilogue flags): x [M, K], w [N, K], dy [M, N] (all `dtype`)
+ * -> dx [M, K] (dx_dtype; NULL to skip), dw [N, K] fp32 (NULL to skip), db [N] fp32 (NULL to skip).
+ * PSW_F32: CUDA-core FMAs.  PSW_BF16: dx on the tcgen05 GEMM against the transposed weight, which is written into
+ * `workspace` (psw_linear_bwd_workspace_bytes(); without it, or for K % 16 != 0 / N % 8 != 0, the CUDA-core kernel
+ * serves); dw accumulates in fp32 from the bf16 operands, split over the rows of the batch.
+ * Reference: nn.Linear at :287, :309, :55-61, :575.
+ */
+PSW_API int64_t psw_linear_bwd_workspace_bytes(int64_t M, int N, int K, int dtype);
+PSW_API int psw_linear_bwd(const void* x, const void* w, const void* dy, void* dx, float* dw, float* db,
+                           int64_t M, int N, int K, int dtype, int dx_dtype, void* workspace, int64_t workspace_bytes,
+                           void* stream);
+
+/* Exact (erf) GELU of the training path, which keeps the pre-activation h: y = gelu(h); dh = dy * gelu'(h).
+ * n elements (n % 4 == 0), all tensors `dtype`.  Reference: Mlp.act (:51, :57). */
+PSW_API int psw_gelu_fwd(const void* h, void* y, int64_t n, int dtype, void* stream);
+PSW_API int psw_gelu_bwd(const void* h, const void* dy, void* dh, int64_t n, int dtype, void* stream);
+
+/* dst [cols, rows] = src [rows, cols]^T (helper of the bf16 backward path). */
+PSW_API int psw_transpose(const void* src, void* dst, int64_t rows, int64_t cols, int dtype, void* stream);
+
+/*
+ * Gradient of the fused window attention (psw_window_attn_fwd and psw_window_attn_full_fwd: same function of qkv,
+ * alpha, beta): qkv [B, H, W, 3C], dout [B, H, W, C] (both `dtype`) -> dqkv [B, H, W, 3C] (`dtype`, every element
+ * written), dalpha / dbeta [(2*window-1)^2, heads] fp32, dqkv_bias [3C] fp32 = the gradient that reaches the qkv bias
+ * through the PADDING cells (zero tokens whose q / k / v are the bias, reference :486-491; the bias gradient of the
+ * real tokens is psw_linear_bwd's db).  The probabilities are recomputed from qkv; uv / mask carry no gradient.
+ * qkv_bias and dqkv_bias are both NULL or both given; dalpha is untouched in planar mode.  Any window / head_dim.
+ */
+PSW_API int psw_window_attn_bwd(const void* qkv, const void* dout, const float* alpha, const float* beta,
+                                const float* qkv_bias, const float* uv, const float* mask, void* dqkv, float* dalpha,
+                                float* dbeta, float* dqkv_bias, int B, int H, int W, int C, int heads, int window,
+                                int shift, int pano_mode, float scale, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

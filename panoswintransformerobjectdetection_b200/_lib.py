@@ -12,7 +12,7 @@ PSW_EPI_GELU = 1
 
 _vp, _fp, _i, _i64, _f = C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float
 
-ABI_VERSION = 2            # must equal PSW_ABI_VERSION of include/panoswin_b200.h (bumped with every prototype change)
+ABI_VERSION = 3            # must equal PSW_ABI_VERSION of include/panoswin_b200.h (bumped with every prototype change)
 
 # name -> argtypes, exactly the prototypes of include/panoswin_b200.h
 SIGNATURES = {
@@ -37,6 +37,14 @@ SIGNATURES = {
     "psw_stem_conv3x3_c32_relu_fwd": [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _vp],
     "psw_patch_conv_fwd": [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "psw_cast": [_vp, _vp, _i64, _i, _i, _vp],
+    "psw_layernorm_bwd": [_vp, _vp, _fp, _vp, _fp, _fp, _fp, _i64, _i, _f, _i, _i, _vp],
+    "psw_patch_merge_ln_bwd": [_vp, _vp, _fp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _i, _i, _vp],
+    "psw_linear_bwd_workspace_bytes": [_i64, _i, _i, _i],
+    "psw_linear_bwd": [_vp, _vp, _vp, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _vp, _i64, _vp],
+    "psw_gelu_fwd": [_vp, _vp, _i64, _i, _vp],
+    "psw_gelu_bwd": [_vp, _vp, _vp, _i64, _i, _vp],
+    "psw_transpose": [_vp, _vp, _i64, _i64, _i, _vp],
+    "psw_window_attn_bwd": [_vp, _vp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _vp],
 }
 # include/panoswin_b200_debug.h: present only in the -DPSW_DIAGNOSTICS build (load(diagnostics=True))
 DIAG_SIGNATURES = {
@@ -88,7 +96,7 @@ def load(build_if_missing: bool = True, diagnostics: bool = None) -> C.CDLL:
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)            # AttributeError here = header / library mismatch
         fn.argtypes = argtypes
-        fn.restype = C.c_int64 if name == "psw_window_bias_full_bytes" else C.c_int
+        fn.restype = C.c_int64 if name in ("psw_window_bias_full_bytes", "psw_linear_bwd_workspace_bytes") else C.c_int
     lib.psw_last_error_string.argtypes = []
     lib.psw_last_error_string.restype = C.c_char_p
     _libs[diagnostics] = lib

@@ -11,7 +11,8 @@ copies, the uv channels or the [nW,49,49,heads] bias tensor of the reference.
 
 Compute modes (`set_compute_dtype`): "bf16" (default; bf16 activations + tcgen05 GEMM/attention, fp32
 residual stream, fp32 softmax / LayerNorm statistics) and "fp32" (CUDA-core kernels, <=1e-5 of the reference).
-Forward only: training kernels (backward) are the next scope row.
+In train mode with gradients enabled the forward runs through torch.autograd Functions whose backward is a set of
+hand-written kernels behind the same C ABI (autograd.py, csrc/psw_train.cu, csrc/psw_attn_bwd.cu).
 """
 from __future__ import annotations
 
@@ -24,6 +25,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import autograd as AG
 from . import ops
 from .registry import BACKBONES
 
@@ -546,6 +548,8 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             warnings.warn("PanoSwin is configured in Pano mode, expecting channel3 == 2 * channel2, but get {} and {}, "
                           "probably cause an error".format(x_bchw.shape[3], x_bchw.shape[2]))
         self._check_forward(x_bchw)
+        if self.training and torch.is_grad_enabled():
+            return self._forward_train(x_bchw.float())      # autograd path: libpanoswin_b200 forward + backward kernels
         with torch.no_grad():
             return self._forward_tokens(x_bchw.float())
 
@@ -562,12 +566,94 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
     def _check_forward(self, x_bchw):
         if not x_bchw.is_cuda:
             raise ops.PanoSwinB200Error("SimplePanoSwinTransformer (B200) needs a CUDA input; there is no CPU fallback")
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("libpanoswin_b200 is forward-only so far (backward kernels: SURVEY.md §8 f-3); "
-                                      "call under torch.no_grad() / in eval mode")
         if self.pano_mode and not self.ape:
             raise AttributeError("pano_mode=True requires ape=True: the reference builds abs_encoder only when ape is set "
                                  "(simple_panoswin_transformer.py:841-842) and always calls it in pano mode (:934)")
+
+    # ---- training forward (autograd) -----------------------------------------------------------
+    def _forward_train(self, img: torch.Tensor) -> Tuple[torch.Tensor, ...]:
+        """forward() in train mode with gradients (reference :940-979 under autograd; callers
+        mmdet/apis/train.py:91-99, mmdet/utils/optimizer.py:22-33).  Every op of the block path runs on a
+        libpanoswin_b200 kernel forward AND backward (autograd.py); the stem (convolutions + train-mode BatchNorm with
+        batch statistics) and the 5-input abs_encoder go through torch.  compute dtype fp32: CUDA-core kernels,
+        gradients within 1e-4 of torch autograd; bf16: bf16 activations, fp32 residual stream and parameters, tcgen05
+        forward / input-gradient GEMMs.  DropPath (:533-534) and `use_checkpoint` (:705-706) are honoured."""
+        cd = self._compute_dtype
+        dev = img.device
+        ws = self.window_size
+        pe = self.patch_embed
+        ph, pw = pe.patch_size
+        _, _, H0, W0 = img.shape
+        if W0 % pw != 0:
+            img = F.pad(img, (0, pw - W0 % pw))
+        if H0 % ph != 0:
+            img = F.pad(img, (0, 0, 0, ph - H0 % ph))
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            tok = pe.proj(img)                                    # conv-BN-ReLU x2 + patch conv (torch / cuDNN, fp32)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        B, E, Hs, Ws = tok.shape
+        self._enter_resolution(Hs, Ws, dev)
+        x = tok.permute(0, 2, 3, 1).reshape(B, Hs * Ws, E)
+        if pe.norm is not None:
+            x = AG.LayerNormFn.apply(x, pe.norm.weight, pe.norm.bias, pe.norm.eps, torch.float32)
+        if self.pano_mode and self.ape:
+            def build():
+                uv = make_uv_hw2(Hs, Ws)
+                u, v = uv[..., 0], uv[..., 1]
+                return torch.stack([torch.sin(u) * torch.sin(v), torch.cos(u) * torch.sin(v), torch.cos(v), u, v], -1).reshape(-1, 5)
+            xyzuv = self._const(("xyzuv", Hs, Ws), build, dev)
+            x = x + self.abs_encoder(xyzuv)[None]
+        x = self.pos_drop(x)
+
+        def wc(p):                                                # weight in the compute dtype (no gradient of its own)
+            return p.detach() if cd == torch.float32 else self._w(p, cd)
+
+        H, W = Hs, Ws
+        outs = []
+        for i, layer in enumerate(self.layers):
+            C = self.num_features[i]
+            uv = self._const(("uv", H, W), lambda: make_uv_hw2(H, W), dev) if self.pano_mode else None
+            for blk in layer.blocks:
+                if isinstance(blk, PitchAttentionModule):
+                    raise NotImplementedError("PitchAttentionModule (odd stage depth) has no training path; use even depths")
+                shift = blk.shift_size
+                mask = None
+                if not self.pano_mode and shift > 0:
+                    mask = self._const(("mask", H, W, ws, shift), lambda: planar_attention_mask(H, W, ws, shift), dev)
+
+                def block_fn(x, blk=blk, shift=shift, mask=mask, uv=uv, H=H, W=W, C=C):
+                    a = blk.attn
+                    xn = AG.LayerNormFn.apply(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, cd)
+                    qkv = AG.LinearFn.apply(xn, a.qkv.weight, a.qkv.bias, wc(a.qkv.weight), cd)
+                    att = AG.WindowAttentionFn.apply(qkv.view(B, H, W, 3 * C), a.sphere_position_alpha_table_Te,
+                                                     a.sphere_position_beta_table_Te, a.qkv.bias, uv, mask, a.num_heads, ws,
+                                                     shift, self.pano_mode, a.scale)
+                    y = AG.LinearFn.apply(att.view(B, H * W, C), a.proj.weight, a.proj.bias, wc(a.proj.weight), torch.float32)
+                    x = x + blk.drop_path(a.proj_drop(y))
+                    xn2 = AG.LayerNormFn.apply(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, cd)
+                    h = AG.LinearFn.apply(xn2, blk.mlp.fc1.weight, blk.mlp.fc1.bias, wc(blk.mlp.fc1.weight), cd)
+                    h = blk.mlp.drop(AG.GeluFn.apply(h))
+                    y2 = AG.LinearFn.apply(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias, wc(blk.mlp.fc2.weight), torch.float32)
+                    return x + blk.drop_path(blk.mlp.drop(y2))
+
+                if layer.use_checkpoint:                          # reference :705-706
+                    from torch.utils.checkpoint import checkpoint
+                    x = checkpoint(block_fn, x, use_reentrant=False)
+                else:
+                    x = block_fn(x)
+            if i in self.out_indices:
+                n = getattr(self, f"norm{i}")
+                o = AG.LayerNormFn.apply(x, n.weight, n.bias, n.eps, torch.float32)
+                outs.append(o.view(B, H, W, C).permute(0, 3, 1, 2).contiguous())
+            if layer.downsample is not None:
+                d = layer.downsample
+                xm = AG.PatchMergeLayerNormFn.apply(x, d.norm.weight, d.norm.bias, H, W, d.norm.eps, cd)
+                x = AG.LinearFn.apply(xm, d.reduction.weight, None, wc(d.reduction.weight), torch.float32)
+                H, W = (H + 1) // 2, (W + 1) // 2
+        return tuple(outs)
 
     def _pitch_block(self, blk, x, xn, B, H, W, C, cd, rd):
         """PitchAttentionModule.forward (:1143-1209) in planar mode: un-shifted windows attend to themselves with

@@ -324,3 +324,105 @@ def cast(x, dtype):
     with torch.cuda.device(dev):
         _call("psw_cast", _ptr(x), _ptr(out), x.numel(), _dt(x), _dt(out), _stream(dev))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backward ops (training path; include/panoswin_b200.h "Backward entry points")
+# ---------------------------------------------------------------------------------------------------------------------
+def layernorm_bwd(x, dy, gamma, eps=1e-5, need_params=True):
+    """Gradients of layernorm(): returns (dx [like x], dgamma, dbeta) — the last two None when not needed."""
+    dev = _chk(x, dy, gamma)
+    C = x.shape[-1]
+    rows = x.numel() // C
+    dx = torch.empty_like(x)
+    dg = torch.empty(C, dtype=torch.float32, device=x.device) if need_params else None
+    db = torch.empty(C, dtype=torch.float32, device=x.device) if need_params else None
+    stats = torch.empty(2 * rows, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(dev):
+        _call("psw_layernorm_bwd", _ptr(x), _ptr(dy), _ptr(_f32(gamma, "gamma")), _ptr(dx), _ptr(dg), _ptr(db), _ptr(stats), rows, C,
+              float(eps), _dt(x), _dt(dy), _stream(dev))
+    return dx, dg, db
+
+
+def patch_merge_layernorm_bwd(x, dy, gamma, H, W, eps=1e-5, need_params=True):
+    """Gradients of patch_merge_layernorm(): x [B, H*W, C], dy [B, H2*W2, 4C] -> (dx [like x], dgamma [4C], dbeta [4C])."""
+    dev = _chk(x, dy, gamma)
+    B, S, C = x.shape
+    if S != H * W:
+        raise PanoSwinB200Error("input feature has wrong size")
+    rows = B * ((H + 1) // 2) * ((W + 1) // 2)
+    dx = torch.empty_like(x)
+    dg = torch.empty(4 * C, dtype=torch.float32, device=x.device) if need_params else None
+    db = torch.empty(4 * C, dtype=torch.float32, device=x.device) if need_params else None
+    stats = torch.empty(2 * rows, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(dev):
+        _call("psw_patch_merge_ln_bwd", _ptr(x), _ptr(dy), _ptr(_f32(gamma, "gamma")), _ptr(dx), _ptr(dg), _ptr(db), _ptr(stats),
+              B, H, W, C, float(eps), _dt(x), _dt(dy), _stream(dev))
+    return dx, dg, db
+
+
+def linear_bwd(x, w, dy, need_dx=True, need_dw=True, need_db=True, dx_dtype=None):
+    """Gradients of linear() without epilogue: x [..., K], w [N, K], dy [..., N] (one dtype) ->
+    (dx [..., K] in dx_dtype, dw [N, K] fp32, db [N] fp32); entries not needed are None."""
+    dev = _chk(x, w, dy)
+    K = w.shape[1]
+    N = w.shape[0]
+    M = dy.numel() // N
+    if x is not None and x.dtype != w.dtype or dy.dtype != w.dtype:
+        raise PanoSwinB200Error("linear_bwd: x, w and dy must share a dtype")
+    dx_dtype = dx_dtype or w.dtype
+    dx = torch.empty(dy.shape[:-1] + (K,), dtype=dx_dtype, device=dy.device) if need_dx else None
+    dw = torch.empty((N, K), dtype=torch.float32, device=dy.device) if need_dw else None
+    db = torch.empty(N, dtype=torch.float32, device=dy.device) if need_db else None
+    nbytes = _lib.load().psw_linear_bwd_workspace_bytes(M, N, K, _dt(w)) if need_dx else 0
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dy.device) if nbytes else None
+    with torch.cuda.device(dev):
+        _call("psw_linear_bwd", _ptr(x), _ptr(w), _ptr(dy), _ptr(dx), _ptr(dw), _ptr(db), M, N, K, _dt(w),
+              PSW_F32 if dx_dtype == torch.float32 else PSW_BF16, _ptr(ws), nbytes, _stream(dev))
+    return dx, dw, db
+
+
+def gelu(h):
+    """Exact (erf) GELU, elementwise, keeping h for gelu_bwd (training path)."""
+    dev = _chk(h)
+    y = torch.empty_like(h)
+    with torch.cuda.device(dev):
+        _call("psw_gelu_fwd", _ptr(h), _ptr(y), h.numel(), _dt(h), _stream(dev))
+    return y
+
+
+def gelu_bwd(h, dy):
+    dev = _chk(h, dy)
+    dh = torch.empty_like(h)
+    with torch.cuda.device(dev):
+        _call("psw_gelu_bwd", _ptr(h), _ptr(dy), _ptr(dh), h.numel(), _dt(h), _stream(dev))
+    return dh
+
+
+def transpose(x):
+    """[R, C] -> [C, R] (contiguous)."""
+    dev = _chk(x)
+    R, Cc = x.shape
+    out = torch.empty((Cc, R), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(dev):
+        _call("psw_transpose", _ptr(x), _ptr(out), R, Cc, _dt(x), _stream(dev))
+    return out
+
+
+def window_attention_bwd(qkv, dout, alpha, beta, qkv_bias, uv, mask, heads, window, shift, pano_mode, scale):
+    """Gradients of window_attention() / window_attention_full(): returns (dqkv [like qkv], dalpha, dbeta [fp32, like
+    alpha], dqkv_bias [3C] fp32 or None: the gradient reaching the qkv bias through the padding cells)."""
+    dev = _chk(qkv, dout, alpha, beta, qkv_bias, uv, mask)
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    if dout.dtype != qkv.dtype:
+        raise PanoSwinB200Error("window_attention_bwd: qkv and dout must share a dtype")
+    dqkv = torch.empty_like(qkv)
+    dalpha = torch.zeros_like(alpha)
+    dbeta = torch.empty_like(beta)
+    dqb = torch.empty(C3, dtype=torch.float32, device=qkv.device) if qkv_bias is not None else None
+    with torch.cuda.device(dev):
+        _call("psw_window_attn_bwd", _ptr(qkv), _ptr(dout), _ptr(_f32(alpha, "alpha")), _ptr(_f32(beta, "beta")),
+              _ptr(_f32(qkv_bias, "qkv_bias")), _ptr(_f32(uv, "uv")), _ptr(_f32(mask, "mask")), _ptr(dqkv), _ptr(dalpha), _ptr(dbeta),
+              _ptr(dqb), B, H, W, C, heads, window, shift, 1 if pano_mode else 0, float(scale), _dt(qkv), _stream(dev))
+    return dqkv, dalpha, dbeta, dqb

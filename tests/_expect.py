@@ -51,7 +51,7 @@ def attention_core(qkv, alpha, beta, qkv_bias, uv, H, W, heads, ws, shift, pano,
         logits = (logits.view(n // nW, nW, heads, N, N) + mask[None, :, None]).view(n, heads, N, N)
     o = (torch.softmax(logits, -1) @ v).transpose(1, 2).reshape(n, N, C)
     o_map = O._unwindows(o, ws, B, Hp, Wp).reshape(B, Hp * Wp, C)
-    out = torch.zeros(B, S + 1, C)
+    out = torch.zeros(B, S + 1, C, dtype=o_map.dtype)
     out[:, torch.where(flat < 0, S, flat)] = o_map
     return out[:, :S].view(B, H, W, C)
 
