@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PSW_ABI_VERSION 3   /* bumped with every change of a prototype below */
+#define PSW_ABI_VERSION 4   /* bumped with every change of a prototype below */
 
 #if defined(__GNUC__)
 #define PSW_API __attribute__((visibility("default")))
@@ -215,6 +215,16 @@ PSW_API int psw_stem_conv3x3_c32_relu_fwd(const void* x, const void* w_taps, con
  */
 PSW_API int psw_patch_conv_fwd(const void* x, const void* w, const float* bias, void* out, int B, int H, int W,
                                int cin, int cout, int patch_h, int patch_w, void* stream);
+
+/*
+ * fp32 parity path of the stem: direct convolution (square kernel, stride, zero padding) on CUDA-core FMAs with the
+ * eval-mode BatchNorm affine (y * bn_scale[c] + bn_shift[c], both or neither) and ReLU in the epilogue — so that the
+ * "<= 1e-5 of the reference" path contains no library kernel (PatchEmbed.proj, reference :742-750).
+ * in [B, cin, H, W] fp32 NCHW, w [cout, cin, k, k], bias [cout] or NULL -> out fp32, NCHW or (out_nhwc = 1) NHWC tokens.
+ */
+PSW_API int psw_conv2d_f32_fwd(const float* in, const float* w, const float* bias, const float* bn_scale,
+                               const float* bn_shift, float* out, int B, int cin, int H, int W, int cout,
+                               int kernel, int stride, int padding, int relu, int out_nhwc, void* stream);
 
 /* dtype conversion helper for activations entering / leaving the bf16 path: n elements. */
 PSW_API int psw_cast(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, void* stream);

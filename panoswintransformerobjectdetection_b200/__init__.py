@@ -10,6 +10,7 @@ The CUDA library (libpanoswin_b200.so, C ABI in include/panoswin_b200.h) is buil
 from . import _build, _lib, ops  # noqa: F401
 from .backbone import (SimplePanoSwinTransformer, make_relative_position_index, make_uv_hw2,  # noqa: F401
                        planar_attention_mask)
+from .detector import FPN, PanoSwinMaskRCNN  # noqa: F401
 from .registry import BACKBONES, build_backbone  # noqa: F401
 
 __version__ = "0.1.0"

@@ -454,17 +454,17 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             x = F.pad(x, (0, 0, 0, ph - H % ph))
         conv1, bn1, _, conv2, bn2, _, conv3 = pe.proj
         if self._compute_dtype == torch.float32:
-            prev = torch.backends.cudnn.allow_tf32
-            torch.backends.cudnn.allow_tf32 = False
-            try:
-                y = F.relu(F.batch_norm(F.conv2d(x, conv1.weight, conv1.bias, padding=1), bn1.running_mean,
-                                        bn1.running_var, bn1.weight, bn1.bias, False, 0.0, bn1.eps))
-                y = F.relu(F.batch_norm(F.conv2d(y, conv2.weight, conv2.bias, padding=1), bn2.running_mean,
-                                        bn2.running_var, bn2.weight, bn2.bias, False, 0.0, bn2.eps))
-                y = F.conv2d(y, conv3.weight, conv3.bias, stride=pe.patch_size)
-            finally:
-                torch.backends.cudnn.allow_tf32 = prev
-            return y.permute(0, 2, 3, 1).contiguous()
+            # parity path: direct fp32 convolutions on CUDA cores, BatchNorm (running statistics) + ReLU in the epilogue
+            def bn_affine(bn):
+                s = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
+                return s, (bn.bias - bn.running_mean * s).detach().float().contiguous()
+            s1, t1 = bn_affine(bn1)
+            s2, t2 = bn_affine(bn2)
+            y = ops.conv2d_f32(x.contiguous(), self._f(conv1.weight), self._f(conv1.bias), s1, t1, 1, 1, relu=True)
+            y = ops.conv2d_f32(y, self._f(conv2.weight), self._f(conv2.bias), s2, t2, 1, 1, relu=True)
+            if ph != pw:
+                raise NotImplementedError("square patches only")
+            return ops.conv2d_f32(y, self._f(conv3.weight), self._f(conv3.bias), None, None, ph, 0, out_nhwc=True)
         # bf16: fold the eval-mode BatchNorm into the convolution, channels-last
         def folded(conv, bn):
             s = bn.weight / torch.sqrt(bn.running_var + bn.eps)

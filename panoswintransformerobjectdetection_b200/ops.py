@@ -318,6 +318,23 @@ def patch_conv(x_nhwc, w_ohwi, bias, patch):
     return out
 
 
+def conv2d_f32(x, w, bias=None, bn_scale=None, bn_shift=None, stride=1, padding=0, relu=False, out_nhwc=False):
+    """fp32 direct convolution (+ BatchNorm affine + ReLU) on CUDA cores: the stem of the fp32 parity path (reference
+    PatchEmbed.proj :742-750).  x [B, cin, H, W] NCHW, w [cout, cin, k, k] -> NCHW, or NHWC tokens with out_nhwc."""
+    dev = _chk(x, w, bias, bn_scale, bn_shift)
+    B, cin, H, W = x.shape
+    cout, _, k, k2 = w.shape
+    if x.dtype != torch.float32 or w.dtype != torch.float32 or k != k2 or w.shape[1] != cin:
+        raise PanoSwinB200Error("conv2d_f32 wants fp32 NCHW x and a square fp32 kernel [cout, cin, k, k]")
+    Ho, Wo = (H + 2 * padding - k) // stride + 1, (W + 2 * padding - k) // stride + 1
+    out = torch.empty((B, Ho, Wo, cout) if out_nhwc else (B, cout, Ho, Wo), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(dev):
+        _call("psw_conv2d_f32_fwd", _ptr(x), _ptr(w), _ptr(_f32(bias, "bias")), _ptr(_f32(bn_scale, "bn_scale")),
+              _ptr(_f32(bn_shift, "bn_shift")), _ptr(out), B, cin, H, W, cout, k, stride, padding, 1 if relu else 0,
+              1 if out_nhwc else 0, _stream(dev))
+    return out
+
+
 def cast(x, dtype):
     dev = _chk(x)
     out = torch.empty(x.shape, dtype=dtype, device=x.device)

@@ -434,3 +434,24 @@ def test_layernorm2_dual(ops, rows, C, with_pos):
     assert y.dtype == torch.float32 and y2.dtype == torch.bfloat16
     assert rel_l2(y, want) <= 2e-6
     assert rel_l2(y2.float(), want2) <= 4e-3
+
+
+@pytest.mark.parametrize("B,cin,H,W,cout,k,s,p", [(2, 3, 20, 36, 32, 3, 1, 1), (1, 32, 17, 33, 64, 3, 1, 1), (2, 64, 16, 24, 96, 4, 4, 0),
+                                                  (1, 42, 9, 11, 84, 3, 1, 1), (1, 5, 8, 8, 7, 2, 2, 0)])
+@pytest.mark.parametrize("nhwc", [False, True])
+def test_conv2d_f32_parity_path(ops, B, cin, H, W, cout, k, s, p, nhwc):
+    """The fp32 stem convolution (CUDA-core direct conv + BatchNorm affine + ReLU) against torch fp64."""
+    g = _g(B + cin + H + W + cout)
+    x = torch.randn(B, cin, H, W, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    sc, sh = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1
+    want = F.relu(F.conv2d(x.double(), w.double(), b.double(), stride=s, padding=p) * sc.double()[None, :, None, None] +
+                  sh.double()[None, :, None, None])
+    got = ops.conv2d_f32(x.to(DEV), w.to(DEV), b.to(DEV), sc.to(DEV), sh.to(DEV), s, p, relu=True, out_nhwc=nhwc)
+    torch.cuda.synchronize()
+    if nhwc:
+        got = got.permute(0, 3, 1, 2)
+    assert got.shape == want.shape and rel_l2(got, want) <= 2e-6
+    plain = ops.conv2d_f32(x.to(DEV), w.to(DEV), None, None, None, s, p)
+    assert rel_l2(plain, F.conv2d(x.double(), w.double(), None, stride=s, padding=p)) <= 2e-6
