@@ -259,7 +259,8 @@ PSW_API int psw_patch_merge_ln_bwd(const void* x, const void* dy, const float* g
  * -> dx [M, K] (dx_dtype; NULL to skip), dw [N, K] fp32 (NULL to skip), db [N] fp32 (NULL to skip).
  * PSW_F32: CUDA-core FMAs.  PSW_BF16: dx on the tcgen05 GEMM against the transposed weight, which is written into
  * `workspace` (psw_linear_bwd_workspace_bytes(); without it, or for K % 16 != 0 / N % 8 != 0, the CUDA-core kernel
- * serves); dw accumulates in fp32 from the bf16 operands, split over the rows of the batch.
+ * serves); dw on tcgen05 as well, with both operands MN-major straight from the row-major activations (no transposed
+ * copies), fp32 accumulation, the rows of the batch split over the grid (N % 8 == 0 and K % 8 == 0, else CUDA cores).
  * Reference: nn.Linear at :287, :309, :55-61, :575.
  */
 PSW_API int64_t psw_linear_bwd_workspace_bytes(int64_t M, int N, int K, int dtype);

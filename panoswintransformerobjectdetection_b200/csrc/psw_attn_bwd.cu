@@ -24,12 +24,14 @@ window_attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, co
   const int N = ws * ws;
   const int hd = C / heads;
   const int SP = N + 1;
+  const int hp = hd + 1;                                  // row pitch of q / k / v / dO: lanes that walk over tokens at a
+                                                          // fixed dim hit different banks (pitch hd = 32 is a 32-way conflict)
   const int tw = 2 * ws - 1, TAB = tw * tw;
-  float* sq = sm;                                         // [N][hd]  q * scale
-  float* sk = sq + N * hd;                                // [N][hd]
-  float* sv = sk + N * hd;                                // [N][hd]
-  float* sdo = sv + N * hd;                               // [N][hd]  dO (zero on padding cells: their rows are cropped)
-  float* sP = sdo + N * hd;                               // [N][N+1] logits -> P -> dS
+  float* sq = sm;                                         // [N][hp]  q * scale
+  float* sk = sq + N * hp;                                // [N][hp]
+  float* sv = sk + N * hp;                                // [N][hp]
+  float* sdo = sv + N * hp;                               // [N][hp]  dO (zero on padding cells: their rows are cropped)
+  float* sP = sdo + N * hp;                               // [N][N+1] logits -> P -> dS
   float* su = sP + N * SP;                                // [N]
   float* sw = su + N;                                     // [N]
   float* sdelta = sw + N;                                 // [N] rowsum(dO o O)
@@ -73,7 +75,7 @@ window_attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, co
     } else {
       val = s >= 0 ? to_f32(dout[((int64_t)b * HW + s) * C + e * hd + d]) : 0.f;
     }
-    sm[idx] = val;                                          // sq, sk, sv, sdo are contiguous
+    sm[(part * N + t) * hp + d] = val;                      // sq, sk, sv, sdo are contiguous
   }
   __syncthreads();
 
@@ -81,7 +83,7 @@ window_attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, co
   for (int p = tid; p < N * N; p += blockDim.x) {
     const int i = p / N, j = p - i * N;
     float dot = 0.f;
-    for (int d = 0; d < hd; ++d) dot = fmaf(sq[i * hd + d], sk[j * hd + d], dot);
+    for (int d = 0; d < hd; ++d) dot = fmaf(sq[i * hp + d], sk[j * hp + d], dot);
     const int ri = i / ws, ci = i - ri * ws, rj = j / ws, cj = j - rj * ws;
     const int idx = (ri - rj + ws - 1) * tw + (ci - cj + ws - 1);
     float bia = beta[idx * heads + e];
@@ -118,9 +120,9 @@ window_attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, co
   for (int idx = tid; idx < N * hd; idx += blockDim.x) {
     const int t = idx / hd, d = idx - t * hd;
     float dv = 0.f, o = 0.f;
-    for (int i = 0; i < N; ++i) dv = fmaf(sP[i * SP + t], sdo[i * hd + d], dv);
-    for (int j = 0; j < N; ++j) o = fmaf(sP[t * SP + j], sv[j * hd + d], o);
-    atomicAdd(&sdelta[t], o * sdo[t * hd + d]);
+    for (int i = 0; i < N; ++i) dv = fmaf(sP[i * SP + t], sdo[i * hp + d], dv);
+    for (int j = 0; j < N; ++j) o = fmaf(sP[t * SP + j], sv[j * hp + d], o);
+    atomicAdd(&sdelta[t], o * sdo[t * hp + d]);
     const int s = ssrc[t];
     const int ch = 2 * C + e * hd + d;
     if (s >= 0) dqkv[((int64_t)b * HW + s) * (3 * C) + ch] = from_f32<T>(dv);
@@ -132,7 +134,7 @@ window_attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, co
   for (int p = tid; p < N * N; p += blockDim.x) {
     const int i = p / N, j = p - i * N;
     float dp = 0.f;
-    for (int d = 0; d < hd; ++d) dp = fmaf(sdo[i * hd + d], sv[j * hd + d], dp);
+    for (int d = 0; d < hd; ++d) dp = fmaf(sdo[i * hp + d], sv[j * hp + d], dp);
     const float ds = sP[i * SP + j] * (dp - sdelta[i]);
     sP[i * SP + j] = ds;
     const int ri = i / ws, ci = i - ri * ws, rj = j / ws, cj = j - rj * ws;
@@ -151,8 +153,8 @@ window_attn_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ dout, co
   for (int idx = tid; idx < N * hd; idx += blockDim.x) {
     const int t = idx / hd, d = idx - t * hd;
     float dq = 0.f, dk = 0.f;
-    for (int j = 0; j < N; ++j) dq = fmaf(sP[t * SP + j], sk[j * hd + d], dq);
-    for (int i = 0; i < N; ++i) dk = fmaf(sP[i * SP + t], sq[i * hd + d], dk);
+    for (int j = 0; j < N; ++j) dq = fmaf(sP[t * SP + j], sk[j * hp + d], dq);
+    for (int i = 0; i < N; ++i) dk = fmaf(sP[i * SP + t], sq[i * hp + d], dk);
     dq *= scale;
     const int s = ssrc[t];
     const int ch = e * hd + d;
@@ -178,7 +180,7 @@ static int window_attn_bwd(const T* qkv, const T* dout, const float* alpha, cons
                            cudaStream_t st) {
   WinGeom g = make_geom(H, W, window, shift, pano);
   const int N = window * window, hd = C / heads, TAB = (2 * window - 1) * (2 * window - 1);
-  const size_t smem = ((size_t)4 * N * hd + (size_t)N * (N + 1) + 4 * (size_t)N + 2 * (size_t)TAB) * sizeof(float);
+  const size_t smem = ((size_t)4 * N * (hd + 1) + (size_t)N * (N + 1) + 4 * (size_t)N + 2 * (size_t)TAB) * sizeof(float);
   PSW_REQUIRE(smem <= 220 * 1024, PSW_ERR_UNSUPPORTED, "psw_window_attn_bwd: window %d x head_dim %d needs %zu B smem", window, hd, smem);
   const int64_t blocks = (int64_t)B * g.nWh * g.nWw * heads;
   PSW_REQUIRE(blocks < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_window_attn_bwd: too many windows");

@@ -19,10 +19,11 @@ window_attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, const fl
   const int N = ws * ws;
   const int hd = C / heads;
   const int SP = N + 1;                                   // padded row pitch of the logits
-  float* sq = sm;                                         // [N][hd]  (already * scale)
-  float* sk = sq + N * hd;                                // [N][hd]
-  float* sv = sk + N * hd;                                // [N][hd]
-  float* sS = sv + N * hd;                                // [N][N+1]
+  const int hp = hd + 1;                                  // padded row pitch of q / k / v (bank-conflict-free token walks)
+  float* sq = sm;                                         // [N][hp]  (already * scale)
+  float* sk = sq + N * hp;                                // [N][hp]
+  float* sv = sk + N * hp;                                // [N][hp]
+  float* sS = sv + N * hp;                                // [N][N+1]
   float* su = sS + N * SP;                                // [N]
   float* sw = su + N;                                     // [N] (v coordinate)
   int* ssrc = reinterpret_cast<int*>(sw + N);             // [N]
@@ -57,7 +58,7 @@ window_attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, const fl
     if (s >= 0) val = to_f32(qkv[((int64_t)b * HW + s) * (3 * C) + ch]);
     else        val = qkv_bias ? qkv_bias[ch] : 0.f;       // zero (padding) token: qkv = bias
     if (part == 0) val *= scale;
-    sm[idx] = val;                                          // sq, sk, sv are contiguous
+    sm[(part * N + t) * hp + d] = val;                      // sq, sk, sv are contiguous
   }
   __syncthreads();
 
@@ -65,7 +66,7 @@ window_attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, const fl
   for (int p = tid; p < N * N; p += blockDim.x) {
     int i = p / N, j = p - i * N;
     float dot = 0.f;
-    for (int d = 0; d < hd; ++d) dot = fmaf(sq[i * hd + d], sk[j * hd + d], dot);
+    for (int d = 0; d < hd; ++d) dot = fmaf(sq[i * hp + d], sk[j * hp + d], dot);
     int ri = i / ws, ci = i - ri * ws, rj = j / ws, cj = j - rj * ws;
     int idx = (ri - rj + ws - 1) * tw + (ci - cj + ws - 1);
     float bia = beta[idx * heads + e];
@@ -104,7 +105,7 @@ window_attn_simt_kernel(const T* __restrict__ qkv, T* __restrict__ out, const fl
     int s = ssrc[t];
     if (s < 0) continue;                                   // padded cells are cropped (:516)
     float acc = 0.f;
-    for (int j = 0; j < N; ++j) acc = fmaf(sS[t * SP + j], sv[j * hd + d], acc);
+    for (int j = 0; j < N; ++j) acc = fmaf(sS[t * SP + j], sv[j * hp + d], acc);
     out[((int64_t)b * HW + s) * C + e * hd + d] = from_f32<T>(acc);
   }
 }
@@ -115,7 +116,7 @@ int window_attn_simt(const T* qkv, T* out, const float* alpha, const float* beta
                      int pano, float scale, cudaStream_t st) {
   WinGeom g = make_geom(H, W, window, shift, pano);
   int N = window * window, hd = C / heads;
-  size_t smem = ((size_t)3 * N * hd + (size_t)N * (N + 1) + 3 * (size_t)N) * sizeof(float);
+  size_t smem = ((size_t)3 * N * (hd + 1) + (size_t)N * (N + 1) + 3 * (size_t)N) * sizeof(float);
   PSW_REQUIRE(smem <= 220 * 1024, PSW_ERR_UNSUPPORTED, "window attention (simt): window %d x head_dim %d needs %zu B smem",
               window, hd, smem);
   int64_t blocks = (int64_t)B * g.nWh * g.nWw * heads;

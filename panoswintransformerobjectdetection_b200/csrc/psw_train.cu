@@ -335,6 +335,8 @@ static int linear_bwd_simt(const T* x, const T* w, const T* dy, TDX* dx, float* 
   return 0;
 }
 
+int wgrad_tc(const bf16* dy, const bf16* x, float* dw, int64_t M, int N, int K, cudaStream_t st);   // psw_wgrad_tc.cu
+
 }  // namespace psw
 
 using namespace psw;
@@ -432,6 +434,14 @@ extern "C" PSW_API int psw_linear_bwd(const void* x, const void* w, const void* 
     if (rc) return rc;
     dx_simt = nullptr;
   }
+  if (dw && N % 8 == 0 && K % 8 == 0 && aligned16(dy) && aligned16(x) && M >= 64) {
+    // dW = dy^T . x on tcgen05 with MN-major operands straight from the row-major activations (psw_wgrad_tc.cu)
+    PSW_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, st));
+    int rc = wgrad_tc((const bf16*)dy, (const bf16*)x, dw, M, N, K, st);
+    if (rc) return rc;
+    dw = nullptr;
+  }
+  if (!dx_simt && !dw && !db) return 0;
   if (dx_dtype == PSW_F32)
     return linear_bwd_simt<bf16, float>((const bf16*)x, (const bf16*)w, (const bf16*)dy, (float*)dx_simt, dw, db, M, N, K, st);
   return linear_bwd_simt<bf16, bf16>((const bf16*)x, (const bf16*)w, (const bf16*)dy, (bf16*)dx_simt, dw, db, M, N, K, st);
