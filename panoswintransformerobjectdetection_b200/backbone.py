@@ -588,12 +588,18 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
             img = F.pad(img, (0, pw - W0 % pw))
         if H0 % ph != 0:
             img = F.pad(img, (0, 0, 0, ph - H0 % ph))
-        prev = torch.backends.cudnn.allow_tf32
-        torch.backends.cudnn.allow_tf32 = False
-        try:
-            tok = pe.proj(img)                                    # conv-BN-ReLU x2 + patch conv (torch / cuDNN, fp32)
-        finally:
-            torch.backends.cudnn.allow_tf32 = prev
+        if cd == torch.bfloat16:
+            # throughput mode: the stem's convolutions forward and backward in bf16 channels-last (cuDNN under autocast,
+            # BatchNorm statistics in fp32) -- what the reference does under apex O1 (mmdet/apis/train.py:82-88)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                tok = pe.proj(img.contiguous(memory_format=torch.channels_last)).float()
+        else:
+            prev = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False
+            try:
+                tok = pe.proj(img)                                # conv-BN-ReLU x2 + patch conv (torch / cuDNN, fp32)
+            finally:
+                torch.backends.cudnn.allow_tf32 = prev
         B, E, Hs, Ws = tok.shape
         self._enter_resolution(Hs, Ws, dev)
         x = tok.permute(0, 2, 3, 1).reshape(B, Hs * Ws, E)
