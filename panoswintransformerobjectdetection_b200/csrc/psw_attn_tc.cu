@@ -43,7 +43,6 @@ constexpr int AT_BUF_BYTES = 3 * AT_PART_BYTES;    // q, k, v
 constexpr int AT_TMEM_COLS = 128;
 constexpr int AT_P_COL = 0;                        // P (bf16 pairs): TMEM columns [0, 32)
 constexpr int AT_O_COL = 32;                       // O (fp32): TMEM columns [32, 96)
-constexpr int AT_SUM_COL = 96;                     // row sums of P (fp32, batch-innermost kernel): TMEM columns [96, 112)
 constexpr int AT_CTAS_PER_SM = 4;                  // 128 registers per thread (no spills), 4 x 128 TMEM columns
 constexpr int AT_FULL_CHUNKS = 13;                 // float4 chunks per bias row: 49 logits padded to 52
 constexpr float LOG2E = 1.4426950408889634f;
@@ -108,14 +107,15 @@ struct AttnParams {
   const float* qkv_bias;
   WinGeom g;
   int B, C, heads;
-  int hc;                 // pair kernel: heads per work item; batch-innermost kernel: image pairs per unit
+  int hc;                 // pair kernel: heads per work item
   int n_windows;          // B * windows per image
-  int n_items;            // work items / units
-  int nch;                // batch-innermost kernel: chunks per (window position, head)
-  uint32_t magic_heads, magic_nch, magic_nww;   // multiply-high reciprocals of heads / nch / windows per row (0 = divisor 1)
+  int n_items;            // pair kernel: work items
+  int nslots;             // batch-innermost kernel: ranges per head (grid = nslots * heads)
+  int steps_per_head;     // batch-innermost kernel: windows per image * image pairs
   float scale_l2;         // scale * log2(e)
   long long* dbg;         // diagnostics build: per-phase cycle totals of CTA 0 (nullptr otherwise)
   int mode;               // diagnostics build: 0 normal, 1 memory skeleton, 2 no bias loads, 3 no q/k/v loads
+  int variant;            // diagnostics build: bit 5 = per-CTA {SM, start, end} -> dbg[8 + 3 * CTA], phase cycles -> dbg[8 + 3 * 1024 + 8 * CTA]
 };
 
 // One pipeline step of the window-pair kernel = one head of one window pair.
@@ -426,32 +426,42 @@ window_attn_pair_kernel(const AttnParams p) {
 
 // ---------------------------------------------------------------------------------------------------
 // Batch-innermost schedule (production path for batches of 4 images or more).
-// The 128-row tile holds the SAME window position and head of TWO images; a work item is (window position, head)
-// and its steps walk over the image pairs.  Everything that depends on the geometry or the head only -- the token
-// map of the window and the thread's 49-entry bias row -- is fetched once per item and kept (shared memory /
-// registers) for all of its steps, so a step is nothing but the q/k/v gather, the two MMAs, the softmax and the
-// store.  An item is cut into units of p.hc image pairs (chosen by the host for balance); units are numbered
-// (window, chunk, head) with the head fastest and CTA c runs units c, c + grid, c + 2 grid, ...: at any moment the
-// resident CTAs work on ALL heads of the same windows and images, so the head slices sharing a 128-byte line of the
-// qkv rows meet in L2 (a contiguous range per CTA separates them by ~40 us and doubles the DRAM reads -- measured).
+// The 128-row tile holds the SAME window position and head of TWO images.  A CTA owns ONE head for its whole life and a
+// contiguous range of the (window position, image pair) list of that head, image pair fastest: everything that
+// depends on the geometry or the head only -- the token map of the window, the thread's 49-entry bias row, the
+// padding cells' q / k / v -- is set up once per window position and reused for all image pairs, so a step is nothing
+// but the q/k/v gather, the two MMAs, the softmax and the store.  CTA c has head c % heads and range slot c / heads:
+// the CTAs of one slot walk through the same windows and images at the same pace, one head each, so the head slices
+// that share a 128-byte line of the qkv rows meet in L2.
+//
+// The two images of a tile share the 64 key columns of S: S = [Q_img0; Q_img1] . K_img^T is issued once per image with
+// N = 64 and the OTHER image's 64 output lanes disabled (tcgen05.mma disable-output-lane), so both land in TMEM columns
+// [0, 64), O gets its own 64 columns, and the S MMA of step n+1 is issued as soon as the P.V MMA of step n has
+// consumed P -- before O(n) is drained and stored.  q / k / v travel with cp.async whose completion is tracked by an
+// mbarrier per stage (cp.async.mbarrier.arrive.noinc): no thread ever waits for its own copies and there is no proxy
+// fence on the step's critical path -- only the MMA-issuing thread waits for the stage, right before the S MMA that
+// reads it.  Per step and CTA:
+//   (a) wait S(n)
+//   (b) softmax(n): tcgen05.ld S, + bias, max, exp2, row sum (registers), bf16 P -> TMEM;          barrier
+//   (c) one thread: P.V MMA(n)        (d) wait P.V(n): P and the stage's q / k / v are free
+//   (e) one thread: wait for the q / k / v of step n+1 (requested a whole step ago), S MMA(n+1)
+//   (f) q / k / v rows of step n+2 -> the stage just released; token map of the window of step n+3
+//   (g) O(n) * 1/sum -> global, while S(n+1) runs on the tensor core
+// Padding cells (zero tokens whose q / k / v equal the qkv bias) are the same cells for every step of a window and
+// keep their place in a stage buffer, so they are written (generic stores + one proxy fence, before that step's
+// copies are requested) only by the first two steps of a window, one per stage.
 // ---------------------------------------------------------------------------------------------------
-// Unit iterator of the batch-innermost schedule.  All threads of a CTA hold the same state; advancing costs a handful
-// of instructions (the unit index is decoded with multiply-high "magic" divisions only when a unit ends).
 struct BiIt {
-  int u;                  // unit index: (window position * chunks + chunk) * heads + head
-  int e;                  // head
   int wi;                 // window position inside an image
   int bp;                 // image pair: images 2*bp, 2*bp + 1
-  int bp_end;             // end of the unit's image-pair range
-  int ic;                 // running unit count of this CTA (parity selects the per-unit shared-memory slot)
+  int ic;                 // running window count of this CTA (selects the per-window shared-memory slot)
+  int k;                  // running step count of this CTA (parity selects the stage)
 };
 
-__device__ __forceinline__ uint32_t fast_div(uint32_t x, uint32_t magic) { return magic ? __umulhi(x, magic) : x; }
-
 // Shared-memory map of the batch-innermost kernel (offsets from the 1024-byte aligned base): two stages of
-// [q | k | v] x [128 rows (img*64 + token) x 64 B] SWIZZLE_64B, then the per-unit data.
+// [q | k | v] x [128 rows (img*64 + token) x 64 B] SWIZZLE_64B, then the per-window data.
 constexpr int BI_MISC = 2 * AT_BUF_BYTES;          // token maps, row offsets, padding rows, barriers, TMEM slot
-constexpr int BI_SLOTS = 4;                        // per-unit slots: the units of steps n .. n+3 are alive at once
+constexpr int BI_SLOTS = 4;                        // per-window slots: the windows of steps n .. n+3 are alive at once
 constexpr int BI_S_COL = 0;                        // S (fp32, 64 columns shared by both images) then P (bf16 pairs, 32 columns)
 constexpr int BI_O_COL = 64;                       // O (fp32): image h in columns [64 + 32h, 96 + 32h)
 
@@ -464,19 +474,6 @@ __device__ __forceinline__ void umma_ss_masked(uint32_t tmem_d, uint64_t desc_a,
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3) : "memory");
 }
 
-// The two images of a tile share the 64 key columns of S: S = [Q_img0; Q_img1] . K_img^T is issued once per image with
-// N = 64 and the OTHER image's 64 output lanes disabled (tcgen05.mma disable-output-lane), so both land in TMEM columns
-// [0, 64).  S then needs 64 columns instead of 128, O gets its own 64, and the S MMA of step n+1 can be issued as soon
-// as the P.V MMA of step n has consumed P -- BEFORE O(n) is drained and stored.  Per step and CTA:
-//   (a) wait S(n)
-//   (b) softmax(n): tcgen05.ld S, + bias, max, exp2, row sum (registers), bf16 P -> TMEM;          barrier
-//   (c) one thread: P.V MMA(n)        (e) wait P.V(n)
-//   (f) q / k / v of step n+1 (requested a whole step ago) have landed; proxy fence;               barrier;  S MMA(n+1)
-//   (g) q / k / v rows of step n+2 -> the stage S(n) and P.V(n) have released; unit data of step n+3
-//   (h) O(n) * 1/sum -> global, while S(n+1) runs on the tensor core
-// so the S MMA round trip is hidden behind the gather issue and the store.  There is exactly ONE proxy fence per step
-// and no cp.async request is younger than a whole step when it executes: fence.proxy.async waits for copies in flight
-// (measured: with a fresh group behind it, the fence costs the full memory latency).
 template <int WS>
 __global__ void __launch_bounds__(AT_THREADS, AT_CTAS_PER_SM)
 window_attn_bi_kernel(const AttnParams p) {
@@ -486,44 +483,50 @@ window_attn_bi_kernel(const AttnParams p) {
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   int* src = reinterpret_cast<int*>(smem + BI_MISC);                     // [BI_SLOTS][64]: token index in the image or -1
   int* soff = src + BI_SLOTS * 64;                                       // [BI_SLOTS][64]: token index * 3C (element offset of the qkv row)
-  uint4* padrow = reinterpret_cast<uint4*>(soff + BI_SLOTS * 64);        // [BI_SLOTS][3][4]: bf16 qkv bias of the unit's head
-  uint64_t* bars = reinterpret_cast<uint64_t*>(padrow + BI_SLOTS * 12);  // [2]: S ready, O ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint4* padrow = reinterpret_cast<uint4*>(soff + BI_SLOTS * 64);        // [3][4]: bf16 qkv bias of this CTA's head
+  uint64_t* bars = reinterpret_cast<uint64_t*>(padrow + 12);             // S ready, O ready, stage 0 full, stage 1 full
+  uint64_t* full = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int C = p.C, heads = p.heads, C3 = 3 * p.C;
   const WinGeom g = p.g;
   const int64_t HW = (int64_t)g.H * g.W;
-  const int BP = (p.B + 1) / 2;                            // steps per item
-  const int G = gridDim.x;
+  const int BP = (p.B + 1) / 2;                            // steps per window position
 
   for (int i = tid; i < BI_MISC / 16; i += AT_THREADS)
-    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);          // zero K-slots of Q, padding rows: must stay finite
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);          // rows 49..63 of a unit: must stay finite
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&full[0], AT_THREADS);
+    mbar_init(&full[1], AT_THREADS);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<AT_TMEM_COLS>(tmem_slot);
+
+  // this CTA's head and its range [l0, l1) of the head's (window position, image pair) list
+  const int e = blockIdx.x % heads;
+  const int range_slot = blockIdx.x / heads;
+  const int l0 = (int)((int64_t)p.steps_per_head * range_slot / p.nslots);
+  const int nsteps = (int)((int64_t)p.steps_per_head * (range_slot + 1) / p.nslots) - l0;
+  if (tid >= 64 && tid < 76) {                             // padding cells: [q|k|v][4 x 16 B] of the head's bf16 bias
+    const int j = tid - 64;
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (p.qkv_bias) {
+      const float* bsrc = p.qkv_bias + (j >> 2) * C + e * 32 + (j & 3) * 8;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(bsrc));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bsrc) + 1);
+      r = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+    padrow[j] = r;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  auto bias_chunk = [&](int ch) {
-    uint4 r = make_uint4(0, 0, 0, 0);
-    if (p.qkv_bias) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(p.qkv_bias + ch));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.qkv_bias + ch) + 1);
-      r = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
-    }
-    return r;
-  };
-
-  const int n_units = p.n_items;                           // (window positions) x chunks x heads
-  const int CH = p.hc;                                     // image pairs per unit
-  const int NCH = p.nch;                                   // chunks per (window position, head)
 
   const int img = tid >> 6;                                // warp-uniform: which image of the pair my row belongs to
   const int ti = tid & 63;
@@ -532,35 +535,21 @@ window_attn_bi_kernel(const AttnParams p) {
   const int lc = tid & 3;
   const int lt0 = tid >> 2;
 
-  auto decode = [&](BiIt& it) {                            // unit index -> head, window position, image-pair range
-    const uint32_t wc = fast_div((uint32_t)it.u, p.magic_heads);
-    it.e = it.u - (int)wc * heads;
-    const uint32_t w = fast_div(wc, p.magic_nch);
-    it.wi = (int)w;
-    it.bp = ((int)wc - (int)w * NCH) * CH;
-    it.bp_end = it.bp + CH < BP ? it.bp + CH : BP;
-  };
   auto advance = [&](BiIt& it) {
-    if (++it.bp < it.bp_end) return;
-    it.u += G;
-    ++it.ic;
-    if (it.u < n_units) decode(it);
+    ++it.k;
+    if (++it.bp == BP) { it.bp = 0; ++it.wi; ++it.ic; }
   };
-  // per-unit data -> shared-memory slot (ic % BI_SLOTS): token map of the window position (threads 0..63) and the head's
-  // slice of the bf16 qkv bias for padding cells (threads 64..75)
+  // token map of a window position -> shared-memory slot (ic % BI_SLOTS), threads 0..63
   auto prep_item = [&](const BiIt& it) {
-    const int slot = it.ic & (BI_SLOTS - 1);
     if (tid < 64) {
       int t = -1;
       if (tid < N) {
-        const int wr = (int)fast_div((uint32_t)it.wi, p.magic_nww), wc = it.wi - wr * g.nWw;
+        const int wr = it.wi / g.nWw, wc = it.wi - wr * g.nWw;
         t = source_token(g, wr * WS + ri, wc * WS + ci);
       }
+      const int slot = it.ic & (BI_SLOTS - 1);
       src[slot * 64 + tid] = t;
       soff[slot * 64 + tid] = t * C3;
-    } else if (tid < 76) {                                 // [q|k|v][4 x 16 B]
-      const int j = tid - 64;
-      padrow[slot * 12 + j] = bias_chunk((j >> 2) * C + it.e * 32 + (j & 3) * 8);
     }
   };
   // loader role of this thread: 16-byte chunk lc of tokens lt0 and lt0 + 32 of both images; row = img*64 + token of
@@ -573,38 +562,50 @@ window_attn_bi_kernel(const AttnParams p) {
     ld_dst[k] = (uint32_t)(row * 64 + ((lc ^ ((row >> 1) & 3)) << 4));
   }
   const int64_t img_stride = HW * C3;                      // elements per image of the qkv tensor
-  auto issue_loads = [&](const BiIt& it, int stage) {       // all q / k / v rows of a step into `stage`
-    const int slot = it.ic & (BI_SLOTS - 1);
-    const int* so = soff + slot * 64;
+  const bool no_loads = kDiag && p.mode == 3;
+  auto issue_loads = [&](const BiIt& it) {                  // all q / k / v rows of a step into stage (k & 1)
+    const int stage = it.k & 1;
+    const int* so = soff + (it.ic & (BI_SLOTS - 1)) * 64;
     const int o0 = so[lt0];
     const int o1 = ld_ok1 ? so[lt0 + 32] : 0;
-    const bf16* g0 = p.qkv + (int64_t)(2 * it.bp) * img_stride + it.e * 32 + lc * 8;
+    const bf16* g0 = p.qkv + (int64_t)(2 * it.bp) * img_stride + e * 32 + lc * 8;
     const bool img1 = 2 * it.bp + 1 < p.B;
     uint8_t* base = smem + stage * AT_BUF_BYTES;
+    if (it.bp < 2 || it.k < 2) {                           // first visit of this window to this stage: its padding cells
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if ((k & 1) && !ld_ok1) continue;
-      if ((k >> 1) && !img1) continue;
-      const int o = (k & 1) ? o1 : o0;
-      uint8_t* dst = base + ld_dst[k];
-      if (o >= 0) {
-        const bf16* grow = g0 + ((k >> 1) ? img_stride : 0) + o;
-        cp_async16(dst, grow);
-        cp_async16(dst + AT_PART_BYTES, grow + C);
-        cp_async16(dst + 2 * AT_PART_BYTES, grow + 2 * C);
-      } else {                                             // padding cell: q/k/v = bias (staged per unit by prep_item)
-        const uint4* pr = padrow + slot * 12 + lc;
-        *reinterpret_cast<uint4*>(dst) = pr[0];
-        *reinterpret_cast<uint4*>(dst + AT_PART_BYTES) = pr[4];
-        *reinterpret_cast<uint4*>(dst + 2 * AT_PART_BYTES) = pr[8];
+      for (int k = 0; k < 4; ++k) {
+        if ((k & 1) && !ld_ok1) continue;
+        if (((k & 1) ? o1 : o0) < 0) {
+          uint8_t* dst = base + ld_dst[k];
+          *reinterpret_cast<uint4*>(dst) = padrow[lc];
+          *reinterpret_cast<uint4*>(dst + AT_PART_BYTES) = padrow[4 + lc];
+          *reinterpret_cast<uint4*>(dst + 2 * AT_PART_BYTES) = padrow[8 + lc];
+        }
+      }
+      fence_async_shared();                                // before this step's copies are requested: nothing young in flight
+    }
+    if (!no_loads) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if ((k & 1) && !ld_ok1) continue;
+        if ((k >> 1) && !img1) continue;
+        const int o = (k & 1) ? o1 : o0;
+        if (o >= 0) {
+          uint8_t* dst = base + ld_dst[k];
+          const bf16* grow = g0 + ((k >> 1) ? img_stride : 0) + o;
+          cp_async16(dst, grow);
+          cp_async16(dst + AT_PART_BYTES, grow + C);
+          cp_async16(dst + 2 * AT_PART_BYTES, grow + 2 * C);
+        }
       }
     }
+    cp_async_mbar_arrive_noinc(&full[stage]);              // arrives when this thread's copies have landed
   };
-  // my row of the unit's precomputed bias: [window][head][chunk][row] float4
+  // my row of the window's precomputed bias: [window][head][chunk][row] float4
   float bias[4 * AT_FULL_CHUNKS];
   auto load_bias = [&](const BiIt& it) {
     if (ti < N && !(kDiag && p.mode == 2)) {
-      const float4* brow = p.bias_full + ((size_t)it.wi * heads + it.e) * (AT_FULL_CHUNKS * 64) + ti;
+      const float4* brow = p.bias_full + ((size_t)it.wi * heads + e) * (AT_FULL_CHUNKS * 64) + ti;
 #pragma unroll
       for (int k = 0; k < AT_FULL_CHUNKS; ++k) {
         const float4 b4 = __ldg(brow + k * 64);
@@ -615,8 +616,10 @@ window_attn_bi_kernel(const AttnParams p) {
 #pragma unroll
   for (int k = 0; k < 4 * AT_FULL_CHUNKS; ++k) bias[k] = 0.f;
 
-  const bool no_loads = kDiag && p.mode == 3;
-  auto issue_s_mma = [&](int stage) {                      // one thread: S(img) = [Q_img0; Q_img1] . K_img^T, other image's lanes masked
+  // one thread: wait for the stage, then S(img) = [Q_img0; Q_img1] . K_img^T with the other image's lanes masked
+  auto issue_s_mma = [&](int k) {
+    const int stage = k & 1;
+    mbar_wait(&full[stage], (uint32_t)(k >> 1) & 1u);
     tc_fence_after();
     const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
     const uint32_t sq = smem_u32(smem + stage * AT_BUF_BYTES);
@@ -630,36 +633,32 @@ window_attn_bi_kernel(const AttnParams p) {
     umma_commit(&bars[0]);
   };
 
+  long long t_start = 0;
+  if (kDiag && (p.variant & 32) && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
   // software pipeline over steps: cur = n (computed now), nxt = n+1, nn = n+2, n3 = n+3
   BiIt cur, nxt, nn, n3;
-  cur.u = blockIdx.x; cur.ic = 0; cur.e = 0; cur.wi = 0; cur.bp = 0; cur.bp_end = 0;
-  if (cur.u < n_units) decode(cur);
+  cur.wi = l0 / BP; cur.bp = l0 - cur.wi * BP; cur.ic = 0; cur.k = 0;
   nxt = cur; advance(nxt);
   nn = nxt; advance(nn);
   n3 = nn; advance(n3);
-  if (cur.u < n_units) {
+  if (nsteps > 0) {
     prep_item(cur);
-    if (nxt.u < n_units && nxt.ic != cur.ic) prep_item(nxt);
-    if (nn.u < n_units && nn.ic != nxt.ic) prep_item(nn);
+    if (nxt.k < nsteps && nxt.ic != cur.ic) prep_item(nxt);
+    if (nn.k < nsteps && nn.ic != nxt.ic) prep_item(nn);
     __syncthreads();
-    if (!no_loads) issue_loads(cur, 0);
-    if (nxt.u < n_units && !no_loads) issue_loads(nxt, 1);
-    cp_async_commit();
+    issue_loads(cur);
+    if (nxt.k < nsteps) issue_loads(nxt);
     load_bias(cur);
-    cp_async_wait<0>();
-    fence_async_shared();
-    __syncthreads();
     if (tid == 0) issue_s_mma(0);
   }
 
   uint32_t par = 0;
   long long ph[6] = {0, 0, 0, 0, 0, 0};
-  const bool prof = kDiag && p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
-  while (cur.u < n_units) {
+  const bool prof = kDiag && p.dbg != nullptr && (blockIdx.x == 0 || (p.variant & 32)) && tid == 0;
+  while (cur.k < nsteps) {
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     if (prof) c0 = clock64();
-    const bool has_next = nxt.u < n_units;
-    const int stage = (int)(par & 1);
+    const bool has_next = nxt.k < nsteps;
     const int my_b = 2 * cur.bp + img;
     const int ts = src[(cur.ic & (BI_SLOTS - 1)) * 64 + ic];   // my token
     // ---- (a) S(n) is ready
@@ -688,7 +687,7 @@ window_attn_bi_kernel(const AttnParams p) {
       tmem_st_x32(tmem_base + lane_base + BI_S_COL, pk);
       tmem_st_wait();
     }
-    if (has_next && nxt.ic != cur.ic) load_bias(nxt);      // new (window, head): the bias registers are free again
+    if (has_next && nxt.ic != cur.ic) load_bias(nxt);      // new window: the bias registers are free again
     tc_fence_before();
     __syncthreads();
     if (prof) c2 = clock64();
@@ -696,7 +695,7 @@ window_attn_bi_kernel(const AttnParams p) {
     if (tid == 0) {
       tc_fence_after();
       const uint32_t idesc = umma_idesc_bf16(128, 64, 0, 1);       // B (V) is MN-major: [key][dim] rows
-      const uint32_t sv = smem_u32(smem + stage * AT_BUF_BYTES + 2 * AT_PART_BYTES);
+      const uint32_t sv = smem_u32(smem + (cur.k & 1) * AT_BUF_BYTES + 2 * AT_PART_BYTES);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {                                // 16 keys per MMA = two 8-key groups of 512 B
         const uint64_t dvd = umma_smem_desc(sv + k * 1024, 4096, 512, UMMA_SWIZZLE_64B);
@@ -704,28 +703,24 @@ window_attn_bi_kernel(const AttnParams p) {
       }
       umma_commit(&bars[1]);
     }
-    // ---- (e) P.V(n) done: P and this stage's V are free
+    // ---- (d) P.V(n) done: P and this stage's q / k / v are free
     mbar_wait(&bars[1], par);
     tc_fence_after();
     if (prof) c3 = clock64();
-    // ---- (f) the ONE proxy fence of the step: q / k / v of step n+1 (requested a whole step ago) have landed
-    cp_async_wait<0>();
-    fence_async_shared();
-    __syncthreads();
-    if (tid == 0 && has_next) issue_s_mma(stage ^ 1);
-    // ---- (g) q / k / v rows of step n+2 into the stage that S(n) and P.V(n) have released; unit data of step n+3
-    if (nn.u < n_units && !no_loads) issue_loads(nn, stage);
-    cp_async_commit();
-    if (n3.u < n_units && n3.ic != nn.ic) prep_item(n3);
+    // ---- (e) S(n+1) as soon as its q / k / v (requested a whole step ago) have landed
+    if (tid == 0 && has_next) issue_s_mma(nxt.k);
+    // ---- (f) q / k / v rows of step n+2 into the stage just released; token map of the window of step n+3
+    if (nn.k < nsteps) issue_loads(nn);
+    if (n3.k < nsteps && n3.ic != nn.ic) prep_item(n3);
     if (prof) c4 = clock64();
-    // ---- (h) normalise and store my output row at the token's un-shifted position
+    // ---- (g) normalise and store my output row at the token's un-shifted position
     {
       uint32_t orow[32];
       tmem_ld_x32(tmem_base + lane_base + BI_O_COL + (uint32_t)(img * 32), orow);
       tmem_ld_wait();
       if (ti < N && my_b < p.B && ts >= 0) {
         const float inv = 1.0f / sum;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)my_b * HW + ts) * C + cur.e * 32);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)my_b * HW + ts) * C + e * 32);
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 v;
@@ -748,10 +743,19 @@ window_attn_bi_kernel(const AttnParams p) {
     nn = n3;
     advance(n3);
   }
-  if (prof)
+  if (prof && blockIdx.x == 0)
     for (int k = 0; k < 6; ++k) p.dbg[k] = ph[k];
+  if (kDiag && (p.variant & 32) && tid == 0 && p.dbg != nullptr) {
+    for (int k = 0; k < 6; ++k) p.dbg[8 + 3 * 1024 + 8 * blockIdx.x + k] = ph[k];
+    long long t_end;
+    uint32_t smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.dbg[8 + 3 * blockIdx.x] = smid;
+    p.dbg[9 + 3 * blockIdx.x] = t_start;
+    p.dbg[10 + 3 * blockIdx.x] = t_end;
+  }
 
-  cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -823,17 +827,14 @@ int window_bias_full(const float* alpha, const float* beta, const float* uv, con
 }
 
 template <typename K>
-static int launch_attn(K kern, const AttnParams& p, size_t smem, cudaStream_t st, const char* name) {
+static int launch_attn(K kern, const AttnParams& p, int grid, size_t smem, cudaStream_t st, const char* name) {
   PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  int grid = num_sms() * AT_CTAS_PER_SM;
-  if (grid > p.n_items) grid = p.n_items;
   kern<<<grid, AT_THREADS, smem, st>>>(p);
   return launch_status(name);
 }
 
-// `variant` (diagnostics build only; 0 in production): bits [0,4) force the image pairs per unit (15 = window-pair
-// schedule).
+// `variant` (diagnostics build only; 0 in production): 15 forces the window-pair schedule.
 int window_attn_tc(const bf16* qkv, bf16* out, const float* qkv_bias, const void* bias_full, int B, int H, int W, int C,
                    int heads, int window, int shift, int pano, float scale, long long* dbg, int mode, int variant,
                    cudaStream_t st) {
@@ -849,40 +850,28 @@ int window_attn_tc(const bf16* qkv, bf16* out, const float* qkv_bias, const void
   p.B = B; p.C = C; p.heads = heads; p.scale_l2 = scale * LOG2E;
   p.dbg = kDiag ? dbg : nullptr;
   p.mode = kDiag ? mode : 0;
+  p.variant = kDiag ? variant : 0;
   p.n_windows = B * p.g.nWh * p.g.nWw;
+  p.hc = 1; p.n_items = 0; p.nslots = 1; p.steps_per_head = 0;
   const int forced = kDiag ? (variant & 15) : 0;
   const size_t smem = attn_tc_smem_bytes();
+  const int ctas = num_sms() * AT_CTAS_PER_SM;
   const bool batch_inner = B >= 4 && forced != 15 && p.mode != 1;
   if (!batch_inner) {
     // window-pair schedule, one head per work item: sharing a window pair's token maps between the heads of a wider
     // item saves little (measured: equal at stage 0), while single-head items balance the small launches of the late
     // stages better (items are dealt out in contiguous ranges; -10% at stage 3)
-    p.hc = 1;
     p.n_items = ((p.n_windows + 1) / 2) * heads;
-    return launch_attn(window_attn_pair_kernel<7>, p, smem, st, "window_attn_pair_kernel");
+    return launch_attn(window_attn_pair_kernel<7>, p, ctas < p.n_items ? ctas : p.n_items, smem, st, "window_attn_pair_kernel");
   }
-  // image pairs per unit: as many as possible (the bias row and the token map are fetched once per unit) while the
-  // units still spread evenly over the resident CTAs (CTA c runs units c, c + grid, ...)
-  const int bp_total = (B + 1) / 2, ctas = num_sms() * AT_CTAS_PER_SM;
-  const int wh = p.g.nWh * p.g.nWw * heads;
-  double best = -1.0;
-  p.hc = 1;
-  for (int ch = 4; ch >= 1; ch >>= 1) {                 // measured: 8 is not better than 4 where both balance
-    const int64_t units = (int64_t)wh * ((bp_total + ch - 1) / ch);
-    const double steps_max = (double)((units + ctas - 1) / ctas) * ch;             // steps of the busiest CTA (upper bound)
-    const double eff = (double)wh * bp_total / ctas / steps_max;
-    if (forced ? ch == forced : (best < 0.9 && eff > best + 1e-9)) { best = eff; p.hc = ch; }
-  }
-  if (forced == 8) p.hc = 8;
-  p.nch = (bp_total + p.hc - 1) / p.hc;
-  p.n_items = wh * p.nch;                                                          // units: (window, chunk, head)
-  auto magic = [](int d) { return d == 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
-  p.magic_heads = magic(heads);
-  p.magic_nch = magic(p.nch);
-  p.magic_nww = magic(p.g.nWw);
-  PSW_REQUIRE((uint64_t)(p.n_items + num_sms() * AT_CTAS_PER_SM) * (uint64_t)(heads > p.nch ? heads : p.nch) < (1ull << 32),
-              PSW_ERR_UNSUPPORTED, "psw_window_attn_full_fwd: too many work units");
-  return launch_attn(window_attn_bi_kernel<7>, p, smem, st, "window_attn_bi_kernel");
+  // every resident CTA gets one head and an equal share of that head's (window position, image pair) list
+  const int64_t steps = (int64_t)p.g.nWh * p.g.nWw * ((B + 1) / 2);
+  PSW_REQUIRE(steps < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_window_attn_full_fwd: too many windows");
+  p.steps_per_head = (int)steps;
+  p.nslots = ctas / heads;
+  if (p.nslots < 1) p.nslots = 1;
+  if (p.nslots > steps) p.nslots = (int)steps;
+  return launch_attn(window_attn_bi_kernel<7>, p, p.nslots * heads, smem, st, "window_attn_bi_kernel");
 }
 
 }  // namespace psw

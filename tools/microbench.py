@@ -16,7 +16,25 @@ DEV = "cuda:0"
 B = int(os.environ.get("MB_BATCH", "32"))
 
 
+_WARM = [False]
+
+
+def warm_clocks(seconds=1.5):
+    """The SM clock of an idle GPU takes a while to ramp up: keep the GPU busy before the first timing."""
+    if _WARM[0]:
+        return
+    import time
+    a = torch.randn(4096, 4096, device=DEV, dtype=torch.bfloat16)
+    t0 = time.time()
+    while time.time() - t0 < seconds:
+        for _ in range(20):
+            a @ a
+        torch.cuda.synchronize()
+    _WARM[0] = True
+
+
 def time_op(fn, n_bufs, iters):
+    warm_clocks()
     for i in range(3):
         fn(i % n_bufs)
     torch.cuda.synchronize()
@@ -122,7 +140,7 @@ def attn_phases():
         torch.cuda.synchronize()
         v = ph.tolist()
         n = max(v[5], 1)
-        names = ["wait-S", "softmax", "PV-mma", "fence+barrier+S-issue+loads", "store"]
+        names = ["wait-S", "softmax", "PV-mma", "S-issue+loads", "store"]
         print(f"attn phases {H}x{W} C{C}: steps {v[5]}  " + "  ".join(f"{nm} {v[i] / n:.0f}" for i, nm in enumerate(names)) +
               f"  total/step {sum(v[:5]) / n:.0f} cyc", flush=True)
 
@@ -267,16 +285,15 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "linsweep":
 
 
 def attn_hc(iters=20):
-    """Image-pairs-per-unit sweep of the batch-innermost attention kernel (variant bits [0,4); 15 = the window-pair
-    schedule)."""
+    """Batch-innermost schedule vs the window-pair schedule (variant 15) of the tcgen05 attention kernel."""
     from panoswintransformerobjectdetection_b200 import _lib
     lib = _lib.load()
     for (H, W, C, heads) in STAGES:
         nb, qkv, out, qb, bf = _attn_setup(H, W, C, heads)
         res = []
-        for hc in (0, 1, 2, 4, 8, 15):
+        for hc in (0, 15):
             us = min(time_op(lambda i: _attn_diag(lib, qkv[i], out[i], bf, qb, H, W, C, heads, 3, variant=hc), nb, iters) for _ in range(3))
-            res.append(f"hc{hc if hc else '-auto'} {us:.1f}")
+            res.append(f"{'pair' if hc else 'batch-inner'} {us:.1f}")
         print(f"attn {H}x{W} C{C} h{heads}: " + "  ".join(res), flush=True)
 
 
@@ -369,3 +386,37 @@ def ln_stem(iters=20):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "lnstem":
     ln_stem()
+
+
+def attn_ctas():
+    """Per-CTA residency and phase cycles of the batch-innermost attention kernel."""
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    for (H, W, C, heads) in STAGES:
+        nb, qkv, out, qb, bf = _attn_setup(H, W, C, heads)
+        ph = torch.zeros(8 + 11 * 1024, dtype=torch.int64, device=DEV)
+        warm_clocks()
+        for i in range(30):
+            _attn_diag(lib, qkv[i % nb], out[i % nb], bf, qb, H, W, C, heads, 3, ph=ph, variant=32)
+        torch.cuda.synchronize()
+        v = ph[8:8 + 3 * 1024].view(-1, 3)
+        n = int((v[:, 2] > 0).sum())
+        v = v[:n]
+        pc = ph[8 + 3 * 1024:].view(-1, 8)[:n].float()
+        t0 = int(v[:, 1].min())
+        st, en = (v[:, 1] - t0).float() / 1e3, (v[:, 2] - t0).float() / 1e3
+        dur = en - st
+        steps = pc[:, 5].clamp(min=1)
+        cyc = pc[:, :5].sum(1)
+        names = ["wait-S", "softmax", "PV", "S-issue+loads", "store"]
+        print(f"attn ctas {H}x{W} C{C}: {n} CTAs, start max {float(st.max()):.1f} us, duration min {float(dur.min()):.1f} median "
+              f"{float(dur.median()):.1f} max {float(dur.max()):.1f} us, end max {float(en.max()):.1f} us; steps {float(steps.mean()):.1f}; "
+              f"loop cycles median {float(cyc.median()):.0f} -> {float((cyc / dur).median()) / 1e3:.2f} GHz apparent; per step: "
+              + "  ".join(f"{nm} {float((pc[:, i] / steps).mean()):.0f}" for i, nm in enumerate(names)), flush=True)
+        for c in (0, 1, 2, n // 2, n - 1):
+            print(f"   CTA {c}: SM {int(v[c, 0])} start {float(st[c]):.1f} end {float(en[c]):.1f} us, cycles/step "
+                  + " ".join(f"{float(pc[c, i] / steps[c]):.0f}" for i in range(5)), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "attnctas":
+    attn_ctas()
