@@ -145,6 +145,10 @@ def launch_work(fn, a):
     if fn == "psw_stem_conv3x3_c32_relu_fwd":
         B, H, W, co = a[4], a[5], a[6], a[7]
         return dict(kind="stem_conv2", shape=f"B{B} {H}x{W} 32->{co}", bytes=float(B * H * W * (64 + 2 * co)), flops=2.0 * B * H * W * 288 * co)
+    if fn == "psw_conv3x3_nhwc_fwd":
+        B, H, W, cin, cout = a[4], a[5], a[6], a[7], a[8]
+        return dict(kind="stem_conv2", shape=f"B{B} {H}x{W} {cin}->{cout} (GEMM view)", bytes=float(B * H * W * 2 * (cin + cout)),
+                    flops=2.0 * B * H * W * 9 * cin * cout)
     if fn == "psw_patch_conv_fwd":
         B, H, W, cin, cout, ph, pw = a[4], a[5], a[6], a[7], a[8], a[9], a[10]
         tok = B * (H // ph) * (W // pw)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PSW_ABI_VERSION 4   /* bumped with every change of a prototype below */
+#define PSW_ABI_VERSION 5   /* bumped with every change of a prototype below */
 
 #if defined(__GNUC__)
 #define PSW_API __attribute__((visibility("default")))
@@ -192,8 +192,9 @@ PSW_API int psw_layernorm_nchw_fwd(const void* x, float* y, const float* gamma, 
  * Stem, first layer: conv3x3(cin -> cout, padding 1) + eval-mode BatchNorm + ReLU (PatchEmbed.proj[0..2], reference
  * :743-745) on tcgen05.  img [B, cin, H, W] fp32 NCHW -> out [B, H, W, cout] bf16 NHWC.  w_folded [cout, cin*9]
  * (k = c*9 + ky*3 + kx) and bias_folded [cout] are the fp32 weights / bias with BatchNorm folded in:
- * w * g/sqrt(var+eps), (b - mean) * g/sqrt(var+eps) + beta.  Built for cin = 3, cout = 32 (embed_dim 96);
- * other widths return PSW_ERR_UNSUPPORTED and the caller keeps its library convolution.
+ * w * g/sqrt(var+eps), (b - mean) * g/sqrt(var+eps) + beta.  Built for cin = 3 and cout = 32 (embed_dim 96) or 64; a
+ * narrower layer is run with its weights / bias zero-padded to 64 output channels (the extra channels come out as 0,
+ * e.g. PanoSwin-B: 42 -> 64).  Other shapes return PSW_ERR_UNSUPPORTED.  W must be a multiple of 4.
  */
 PSW_API int psw_stem_conv3x3_relu_fwd(const float* img, const float* w_folded, const float* bias_folded, void* out,
                                       int B, int H, int W, int cin, int cout, void* stream);
@@ -206,6 +207,16 @@ PSW_API int psw_stem_conv3x3_relu_fwd(const float* img, const float* w_folded, c
  */
 PSW_API int psw_stem_conv3x3_c32_relu_fwd(const void* x, const void* w_taps, const float* bias, void* out,
                                           int B, int H, int W, int cout, void* stream);
+
+/*
+ * conv3x3(cin -> cout, stride 1, padding 1) + bias (+ ReLU) of an NHWC bf16 image as a tcgen05 GEMM over shifted 4-D
+ * TMA views of the input (no im2col, the zero padding is TMA's out-of-range fill): the second stem layer of the models
+ * the dedicated kernel above is not built for (PanoSwin-B: 42 -> 84 channels, zero-padded by the caller to 64 -> 96).
+ * x [B, H, W, cin] -> out [B, H, W, cout]; w [cout][3][3][cin] bf16 (BatchNorm folded in), bias [cout] fp32 or NULL.
+ * cin must be a multiple of 64, cout of 16.
+ */
+PSW_API int psw_conv3x3_nhwc_fwd(const void* x, const void* w, const float* bias, void* out, int B, int H, int W,
+                                 int cin, int cout, int relu, void* stream);
 
 /*
  * Stem, last layer: the non-overlapping patch convolution conv(cin -> cout, kernel = stride = patch) (PatchEmbed.proj[6],

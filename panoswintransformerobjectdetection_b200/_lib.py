@@ -12,7 +12,7 @@ PSW_EPI_GELU = 1
 
 _vp, _fp, _i, _i64, _f = C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float
 
-ABI_VERSION = 4            # must equal PSW_ABI_VERSION of include/panoswin_b200.h (bumped with every prototype change)
+ABI_VERSION = 5            # must equal PSW_ABI_VERSION of include/panoswin_b200.h (bumped with every prototype change)
 
 # name -> argtypes, exactly the prototypes of include/panoswin_b200.h
 SIGNATURES = {
@@ -36,6 +36,7 @@ SIGNATURES = {
     "psw_stem_conv3x3_relu_fwd": [_fp, _fp, _fp, _vp, _i, _i, _i, _i, _i, _vp],
     "psw_stem_conv3x3_c32_relu_fwd": [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _vp],
     "psw_patch_conv_fwd": [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "psw_conv3x3_nhwc_fwd": [_vp, _vp, _fp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "psw_cast": [_vp, _vp, _i64, _i, _i, _vp],
     "psw_conv2d_f32_fwd": [_fp, _fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "psw_layernorm_bwd": [_vp, _vp, _fp, _vp, _fp, _fp, _fp, _i64, _i, _f, _i, _i, _vp],

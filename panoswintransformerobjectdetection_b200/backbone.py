@@ -500,6 +500,40 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                 return ops.patch_conv(y, hit[1], hit[2], pe.patch_size)                                  # [B, Hs, Ws, E]
             y = F.conv2d(y.permute(0, 3, 1, 2), w3, b3, stride=pe.patch_size)
             return y.permute(0, 2, 3, 1).contiguous()      # no copy when the conv output is channels-last
+        generic = (conv1.in_channels == 3 and conv1.out_channels <= 64 and conv2.in_channels == conv1.out_channels
+                   and conv2.out_channels <= 256 and conv1.kernel_size == (3, 3) and conv2.kernel_size == (3, 3)
+                   and ph == pw and conv3.out_channels % 16 == 0 and x.shape[3] % 4 == 0)
+        if generic:
+            # other stem widths (PanoSwin-B: 42 / 84 channels): the same three tcgen05 kernels families on zero-padded
+            # channels -- conv1 -> 64, conv2 as a GEMM over shifted TMA views -> a multiple of 16 with pw * c % 64 == 0,
+            # patch conv on the padded input; the padding channels carry exact zeros
+            hit = self._weight_cache.get("stem_generic")
+            if hit is None or hit[0] != key:
+                c1, c2, E = conv1.out_channels, conv2.out_channels, conv3.out_channels
+                c2p = -(-c2 // 16) * 16
+                while (pw * c2p) % 64:
+                    c2p += 16
+                s1 = bn1.weight / torch.sqrt(bn1.running_var + bn1.eps)
+                s2 = bn2.weight / torch.sqrt(bn2.running_var + bn2.eps)
+                dev = x.device
+                w1p = torch.zeros(64, 27, device=dev)
+                w1p[:c1] = (conv1.weight * s1[:, None, None, None]).reshape(c1, -1).float()
+                b1p = torch.zeros(64, device=dev)
+                b1p[:c1] = ((conv1.bias - bn1.running_mean) * s1 + bn1.bias).float()
+                w2p = torch.zeros(c2p, 3, 3, 64, device=dev)
+                w2p[:c2, :, :, :c1] = (conv2.weight * s2[:, None, None, None]).permute(0, 2, 3, 1).float()
+                b2p = torch.zeros(c2p, device=dev)
+                b2p[:c2] = ((conv2.bias - bn2.running_mean) * s2 + bn2.bias).float()
+                w3p = torch.zeros(E, ph, pw, c2p, device=dev)
+                w3p[..., :c2] = conv3.weight.permute(0, 2, 3, 1).float()
+                b3p = None if conv3.bias is None else conv3.bias.detach().float().contiguous()
+                hit = (key, w1p.detach().contiguous(), b1p.detach().contiguous(), w2p.detach().to(torch.bfloat16).contiguous(),
+                       b2p.detach().contiguous(), w3p.detach().to(torch.bfloat16).contiguous(), b3p)
+                self._weight_cache["stem_generic"] = hit
+            _, w1p, b1p, w2p, b2p, w3p, b3p = hit
+            y = ops.stem_conv3x3_relu(x.contiguous(), w1p, b1p)                      # [B, H, W, 64] bf16 NHWC
+            y = ops.conv3x3_nhwc(y, w2p, b2p, relu=True)                             # [B, H, W, c2p]
+            return ops.patch_conv(y, w3p, b3p, pe.patch_size)                        # [B, Hs, Ws, E]
         if own_conv1:
             # fp32 NCHW image -> bf16 NHWC, seen by the next convolution as a channels-last NCHW tensor (no copy)
             y = ops.stem_conv3x3_relu(x.contiguous(), w1f, b1f).permute(0, 3, 1, 2)

@@ -36,11 +36,20 @@ constexpr int TC_TILE_BYTES = 32 * 64;      // epilogue staging tile: 32 rows x 
 // Patch-convolution view of the A operand (psw_patch_conv_fwd): token (ty, tx) of a non-overlapping ph x pw patch grid
 // is GEMM row ty * wt + tx, its K axis is (dy, dx, c): for a fixed dy the pw * cin values are contiguous in the NHWC
 // image, so x-tiles are boxes of a 3-D tensor {pw * cin, wt, B * H}.  tiles_x = 0 means a plain 2-D A operand.
+//
+// conv3 = 1 (psw_conv3x3_nhwc_fwd): 3 x 3 / stride 1 / pad 1 convolution of an NHWC image without im2col.  Output pixel
+// (b, y, x) is GEMM row (b * himg + y) * wt + x and its K axis is (tap = dy * 3 + dx, c): the x-tile of K-block
+// (tap, kc) is the box {64 channels, 128 pixels, 1 row, 1 image} of the 4-D tensor {cin, W, H, B} at
+// (64 kc, x0 + dx - 1, y + dy - 1, b) -- the same pixels shifted by one; coordinates outside the image are zero-filled
+// by TMA, which is the convolution's zero padding.  kb_per_dy = K-blocks per tap (cin / 64).
 struct ConvView {
   int tiles_x;            // M-tiles per token row
   int wt;                 // tokens per image row
   int kb_per_dy;          // K-blocks (64 elements) per patch row: pw * cin / 64
   int ph;                 // patch height
+  int conv3;              // 3 x 3 stride-1 view (see above)
+  int himg;               // conv3: rows per image
+  int relu;               // ReLU after the bias (any view)
 };
 
 struct alignas(16) TcSmemTail {
@@ -271,7 +280,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             mbar_arrive(&tail->full[stage]);
           } else {
             mbar_expect_tx(&tail->full[stage], stage_bytes);
-            if (cv.tiles_x) {
+            if (cv.conv3) {
+              const int trow = m_t / cv.tiles_x, x0 = (m_t - trow * cv.tiles_x) * TILE_M;
+              const int tap = kb / cv.kb_per_dy, dy = tap / 3, dx = tap - 3 * dy;
+              const int b = trow / cv.himg, yy = trow - b * cv.himg;
+              tma_load_4d(sa, &map_x, &tail->full[stage], (kb - tap * cv.kb_per_dy) * TC_BK, x0 + dx - 1, yy + dy - 1, b);
+            } else if (cv.tiles_x) {
               const int trow = m_t / cv.tiles_x, x0 = (m_t - trow * cv.tiles_x) * TILE_M;
               const int dy = kb / cv.kb_per_dy;
               tma_load_3d(sa, &map_x, &tail->full[stage], (kb - dy * cv.kb_per_dy) * TC_BK, x0, trow * cv.ph + dy);
@@ -633,6 +647,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
           }
         }
+        if (cv.relu) {
+#pragma unroll
+          for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
         uint32_t packed[16];                                  // the 64-byte output row of this lane
         if constexpr (CW == 32) {
           if (GELU && !RES) {
@@ -789,19 +807,32 @@ static bool use_pair(int64_t M, int N, int K, int* block_n) {
 }
 
 // conv != nullptr: x is an NHWC image [rows = B*H][W][cin] viewed through ConvView (wt tokens per row, ph x pw patches)
-struct ConvArgs { int BH, W, cin, ph, pw; };
+struct ConvArgs { int BH, W, cin, ph, pw, conv3, himg, relu; };
 
 template <bool GELU, bool RES, typename TO>
 static int launch_tc(const void* x, const void* w, const float* bias, const void* residual, void* y, int64_t M, int N,
                      int K, cudaStream_t st, const ConvArgs* conv = nullptr) {
   constexpr int CW = Chunk<TO>::CW;
   int block_n = pick_block_n(N);
-  const bool pair = use_pair(M, N, K, &block_n);
+  const bool pair = !(conv && conv->conv3) && use_pair(M, N, K, &block_n);
   const int cg = pair ? 2 : 1;
   CUtensorMap mx, mw, mr;
-  ConvView cv = {0, 0, 0, 0};
+  ConvView cv = {0, 0, 0, 0, 0, 0, 0};
   int rc;
-  if (conv) {
+  if (conv && conv->conv3) {
+    const uint64_t dims[4] = {(uint64_t)conv->cin, (uint64_t)conv->W, (uint64_t)conv->himg, (uint64_t)(conv->BH / conv->himg)};
+    const uint64_t strides[3] = {(uint64_t)conv->cin * 2, (uint64_t)conv->W * conv->cin * 2,
+                                 (uint64_t)conv->himg * conv->W * conv->cin * 2};
+    const uint32_t box[4] = {TC_BK, TC_BM, 1, 1};
+    rc = make_tensor_map_nd(&mx, x, 4, dims, strides, box, 2, CU_TENSOR_MAP_SWIZZLE_128B);
+    cv.tiles_x = 1;                                         // finalised per CTA-group size in launch_tc_gw
+    cv.wt = conv->W;
+    cv.kb_per_dy = conv->cin / TC_BK;
+    cv.ph = 1;
+    cv.conv3 = 1;
+    cv.himg = conv->himg;
+    cv.relu = conv->relu;
+  } else if (conv) {
     const uint64_t dims[3] = {(uint64_t)conv->pw * conv->cin, (uint64_t)(conv->W / conv->pw), (uint64_t)conv->BH};
     const uint64_t strides[2] = {(uint64_t)conv->pw * conv->cin * 2, (uint64_t)conv->W * conv->cin * 2};
     const uint32_t box[3] = {TC_BK, TC_BM, 1};
@@ -952,8 +983,26 @@ extern "C" PSW_API int psw_patch_conv_fwd(const void* x, const void* w, const fl
               "psw_patch_conv_fwd: pointers must be 16-byte aligned");
   const int64_t M = (int64_t)B * (H / patch_h) * (W / patch_w);
   PSW_REQUIRE(M < (1ll << 31) && (int64_t)B * H < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_patch_conv_fwd: too many tokens");
-  const ConvArgs conv = {B * H, W, cin, patch_h, patch_w};
+  const ConvArgs conv = {B * H, W, cin, patch_h, patch_w, 0, 0, 0};
   return launch_tc<false, false, bf16>(x, w, bias, nullptr, out, M, cout, patch_h * patch_w * cin, (cudaStream_t)stream, &conv);
+}
+
+// 3 x 3 / stride 1 / pad 1 convolution (+ bias, optional ReLU) of an NHWC bf16 image as a GEMM over shifted TMA views
+// (ConvView.conv3): the second stem convolution of the models whose stem widths the dedicated kernels of psw_stem2.cu
+// are not instantiated for (PatchEmbed.proj[3:6], reference :746-748; PanoSwin-B: 42 -> 84 channels, zero-padded to
+// 64 -> 96 by the caller).  w [cout][3][3][cin] bf16, out [B, H, W, cout] bf16.
+extern "C" PSW_API int psw_conv3x3_nhwc_fwd(const void* x, const void* w, const float* bias, void* out, int B, int H, int W,
+                                            int cin, int cout, int relu, void* stream) {
+  PSW_REQUIRE(x && w && out, PSW_ERR_BAD_ARG, "psw_conv3x3_nhwc_fwd: null pointer");
+  PSW_REQUIRE(B > 0 && H > 0 && W > 0 && cin > 0 && cout > 0, PSW_ERR_BAD_ARG, "psw_conv3x3_nhwc_fwd: bad dims");
+  PSW_REQUIRE(cin % TC_BK == 0 && cout % 16 == 0, PSW_ERR_UNSUPPORTED,
+              "psw_conv3x3_nhwc_fwd: needs cin %% 64 == 0 and cout %% 16 == 0 (zero-pad the channels); got cin=%d cout=%d", cin, cout);
+  PSW_REQUIRE(aligned16(x) && aligned16(w) && aligned16(out) && aligned16(bias), PSW_ERR_BAD_ARG,
+              "psw_conv3x3_nhwc_fwd: pointers must be 16-byte aligned");
+  const int64_t M = (int64_t)B * H * W;
+  PSW_REQUIRE(M < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_conv3x3_nhwc_fwd: too many pixels");
+  const ConvArgs conv = {B * H, W, cin, 1, 1, 1, H, relu ? 1 : 0};
+  return launch_tc<false, false, bf16>(x, w, bias, nullptr, out, M, cout, 9 * cin, (cudaStream_t)stream, &conv);
 }
 
 #ifdef PSW_DIAGNOSTICS

@@ -1,4 +1,4 @@
-// Stem, first layer: conv3x3(3 -> 32, pad 1) + folded BatchNorm + ReLU as a tcgen05 implicit GEMM that reads the
+// Stem, first layer: conv3x3(3 -> COUT = 32 or 64, pad 1) + folded BatchNorm + ReLU as a tcgen05 implicit GEMM that reads the
 // fp32 NCHW image directly and writes bf16 NHWC (reference: PatchEmbed.proj[0..2],
 // simple_panoswin_transformer.py:743-745, eval mode).  HBM-bound: 12 B read + 64 B written per pixel.
 //
@@ -9,7 +9,9 @@
 // pixel's 32 output channels back from TMEM (lane = pixel), adds the folded bias, applies ReLU and stores 64
 // contiguous bytes (a warp stores 2 KB contiguous).  All four im2col tiles are built before ONE proxy fence + barrier
 // per tile, the eight MMAs go to four TMEM accumulators, and the next tile's patch is prefetched with cp.async
-// (16 B groups) while they run.  52 KB smem, 128 TMEM columns: 4 CTAs per SM.
+// (16 B groups) while they run.  COUT = 32 (embed_dim 96): 52 KB smem, 128 TMEM columns, 4 CTAs per SM.  COUT = 64
+// serves the other stem widths (PanoSwin-B: 42 channels, zero-padded to 64 by the caller): a second staging tile per
+// sub-tile for channels 32..63, two TMA box stores per sub-tile, 2 CTAs per SM.
 #include "psw_common.cuh"
 
 namespace psw {
@@ -18,10 +20,11 @@ constexpr int ST_TH = 8, ST_TW = 64;             // output tile
 constexpr int ST_PH = ST_TH + 2;                 // patch rows  y0-1 .. y0+8
 constexpr int ST_PQ = 18;                        // float4 groups per patch row: columns x0-4 .. x0+67
 constexpr int ST_PP = 4 * ST_PQ;                 // patch row pitch in floats (72)
-constexpr int ST_CIN = 3, ST_COUT = 32, ST_K = 32;
+constexpr int ST_CIN = 3, ST_K = 32;
 constexpr int ST_THREADS = 128;
 constexpr int ST_PATCH_FLOATS = ST_CIN * ST_PH * ST_PP;
 
+template <int ST_COUT>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ wf, const float* __restrict__ bf,
                   const __grid_constant__ CUtensorMap map_out, int B, int H, int W) {
@@ -29,7 +32,9 @@ stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ wf, c
   extern __shared__ uint8_t st_smem_raw[];
   uint8_t* st_smem = st_smem_raw + ((1024u - (smem_u32(st_smem_raw) & 1023u)) & 1023u);
   uint8_t (*a_tile)[128 * 64] = reinterpret_cast<uint8_t (*)[128 * 64]>(st_smem);   // [NSUB] im2col tiles, SWIZZLE_64B
-  uint8_t* w_tile = st_smem + NSUB * 128 * 64;                                      // weights [32 out][32 k], SWIZZLE_64B
+  constexpr int NCH = ST_COUT / 32;                                                 // 32-channel groups of the output
+  uint8_t (*o_tile)[128 * 64] = a_tile + NSUB;                                      // [NSUB] staging of channels 32..63 (COUT = 64)
+  uint8_t* w_tile = st_smem + NCH * NSUB * 128 * 64;                                // weights [COUT out][32 k], SWIZZLE_64B
   float (*patch)[ST_PATCH_FLOATS] = reinterpret_cast<float (*)[ST_PATCH_FLOATS]>(w_tile + ST_COUT * 64);  // [2] fp32 patches
   float* bias_s = reinterpret_cast<float*>(patch + 2);
   uint64_t& bar = *reinterpret_cast<uint64_t*>(bias_s + ST_COUT);
@@ -53,7 +58,7 @@ stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ wf, c
     mbar_fence_init();
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(4 * ST_COUT) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   fence_async_shared();
@@ -145,8 +150,8 @@ stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ wf, c
 #pragma unroll
       for (int sub = 0; sub < NSUB; ++sub) {
         const uint64_t da = umma_smem_desc(smem_u32(a_tile[sub]), 16, 512, UMMA_SWIZZLE_64B);
-        umma_ss(tmem_base + (uint32_t)(sub * 32), da, db, idesc, 0);
-        umma_ss(tmem_base + (uint32_t)(sub * 32), da + 2, db + 2, idesc, 1);
+        umma_ss(tmem_base + (uint32_t)(sub * ST_COUT), da, db, idesc, 0);
+        umma_ss(tmem_base + (uint32_t)(sub * ST_COUT), da + 2, db + 2, idesc, 1);
       }
       umma_commit(&bar);
     }
@@ -162,19 +167,23 @@ stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ wf, c
     const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
     for (int sub = 0; sub < NSUB; ++sub) {
-      uint32_t acc[32];
-      tmem_ld_x32(tmem_base + lane_base + (uint32_t)(sub * 32), acc);
-      tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t w4[4];
+      for (int g = 0; g < NCH; ++g) {
+        uint32_t acc[32];
+        tmem_ld_x32(tmem_base + lane_base + (uint32_t)(sub * ST_COUT + g * 32), acc);
+        tmem_ld_wait();
+        uint8_t* stg = g == 0 ? a_tile[sub] : o_tile[sub];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(__uint_as_float(acc[8 * c + 2 * e]),
-                                                                 __uint_as_float(acc[8 * c + 2 * e + 1])), zero2);
-          w4[e] = *reinterpret_cast<const uint32_t*>(&h);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 h = __hmax2(__floats2bfloat162_rn(__uint_as_float(acc[8 * c + 2 * e]),
+                                                                   __uint_as_float(acc[8 * c + 2 * e + 1])), zero2);
+            w4[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(stg + tid * 64 + ((c ^ ((tid >> 1) & 3)) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
-        *reinterpret_cast<uint4*>(a_tile[sub] + tid * 64 + ((c ^ ((tid >> 1) & 3)) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
       }
     }
     fence_async_shared();
@@ -182,7 +191,10 @@ stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ wf, c
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-      for (int sub = 0; sub < NSUB; ++sub) tma_store_4d(&map_out, a_tile[sub], 0, x0, y0 + 2 * sub, b);
+      for (int sub = 0; sub < NSUB; ++sub) {
+        tma_store_4d(&map_out, a_tile[sub], 0, x0, y0 + 2 * sub, b);
+        if (NCH == 2) tma_store_4d(&map_out, o_tile[sub], 32, x0, y0 + 2 * sub, b);
+      }
       tma_store_commit();
     }
   }
@@ -192,7 +204,7 @@ stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ wf, c
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(4 * ST_COUT) : "memory");
   }
 }
 
@@ -200,28 +212,36 @@ stem_conv1_kernel(const float* __restrict__ img, const float* __restrict__ wf, c
 
 using namespace psw;
 
+template <int COUT>
+static int launch_conv1(const float* img, const float* w_folded, const float* bias_folded, void* out, int B, int H, int W,
+                        cudaStream_t st) {
+  const int64_t tiles = (int64_t)B * ((H + ST_TH - 1) / ST_TH) * ((W + ST_TW - 1) / ST_TW);
+  int64_t grid = (int64_t)num_sms() * (COUT == 32 ? 4 : 2);
+  if (grid > tiles) grid = tiles;
+  const size_t smem = 1024 + (size_t)(COUT / 32) * (ST_TH / 2) * 128 * 64 + COUT * 64 + 2 * ST_PATCH_FLOATS * sizeof(float) +
+                      COUT * sizeof(float) + 16;
+  auto kern = stem_conv1_kernel<COUT>;
+  PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // out as a 4-D tensor (channel, x, y, image); box = 32 channels x 64 pixels x 2 rows (one 128-pixel sub-tile)
+  CUtensorMap map_out;
+  const uint64_t dims[4] = {(uint64_t)COUT, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)COUT * 2, (uint64_t)W * COUT * 2, (uint64_t)H * W * COUT * 2};
+  const uint32_t box[4] = {32u, (uint32_t)ST_TW, 2u, 1u};
+  int rc = make_tensor_map_nd(&map_out, out, 4, dims, strides, box, 2, CU_TENSOR_MAP_SWIZZLE_64B);
+  if (rc) return rc;
+  kern<<<(unsigned)grid, ST_THREADS, smem, st>>>(img, w_folded, bias_folded, map_out, B, H, W);
+  return launch_status("stem_conv1_kernel");
+}
+
 extern "C" PSW_API int psw_stem_conv3x3_relu_fwd(const float* img, const float* w_folded, const float* bias_folded,
                                                  void* out, int B, int H, int W, int cin, int cout, void* stream) {
   PSW_REQUIRE(img && w_folded && bias_folded && out, PSW_ERR_BAD_ARG, "psw_stem_conv3x3_relu_fwd: null pointer");
   PSW_REQUIRE(B > 0 && H > 0 && W > 0, PSW_ERR_BAD_ARG, "psw_stem_conv3x3_relu_fwd: bad dims");
-  PSW_REQUIRE(cin == ST_CIN && cout == ST_COUT, PSW_ERR_UNSUPPORTED,
-              "psw_stem_conv3x3_relu_fwd: built for 3 -> 32 channels (embed_dim 96); got %d -> %d", cin, cout);
+  PSW_REQUIRE(cin == ST_CIN && (cout == 32 || cout == 64), PSW_ERR_UNSUPPORTED,
+              "psw_stem_conv3x3_relu_fwd: built for 3 -> 32 or 64 channels (zero-pad other widths up to 64); got %d -> %d", cin, cout);
   PSW_REQUIRE(aligned16(out) && aligned16(img), PSW_ERR_BAD_ARG, "psw_stem_conv3x3_relu_fwd: img / out must be 16-byte aligned");
   PSW_REQUIRE(W % 4 == 0, PSW_ERR_UNSUPPORTED, "psw_stem_conv3x3_relu_fwd: W must be a multiple of 4 (the patch-size padding guarantees it)");
-  const int64_t tiles = (int64_t)B * ((H + ST_TH - 1) / ST_TH) * ((W + ST_TW - 1) / ST_TW);
-  int64_t grid = (int64_t)num_sms() * 4;
-  if (grid > tiles) grid = tiles;
-  const size_t smem = 1024 + (size_t)(ST_TH / 2) * 128 * 64 + ST_COUT * 64 + 2 * ST_PATCH_FLOATS * sizeof(float) +
-                      ST_COUT * sizeof(float) + 16;
-  PSW_CUDA(cudaFuncSetAttribute(stem_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PSW_CUDA(cudaFuncSetAttribute(stem_conv1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  // out as a 4-D tensor (channel, x, y, image); box = 32 channels x 64 pixels x 2 rows (one 128-pixel sub-tile)
-  CUtensorMap map_out;
-  const uint64_t dims[4] = {(uint64_t)ST_COUT, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-  const uint64_t strides[3] = {(uint64_t)ST_COUT * 2, (uint64_t)W * ST_COUT * 2, (uint64_t)H * W * ST_COUT * 2};
-  const uint32_t box[4] = {(uint32_t)ST_COUT, (uint32_t)ST_TW, 2u, 1u};
-  int rc = make_tensor_map_nd(&map_out, out, 4, dims, strides, box, 2, CU_TENSOR_MAP_SWIZZLE_64B);
-  if (rc) return rc;
-  stem_conv1_kernel<<<(unsigned)grid, ST_THREADS, smem, (cudaStream_t)stream>>>(img, w_folded, bias_folded, map_out, B, H, W);
-  return launch_status("stem_conv1_kernel");
+  if (cout == 64) return launch_conv1<64>(img, w_folded, bias_folded, out, B, H, W, (cudaStream_t)stream);
+  return launch_conv1<32>(img, w_folded, bias_folded, out, B, H, W, (cudaStream_t)stream);
 }

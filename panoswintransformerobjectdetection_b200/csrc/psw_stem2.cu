@@ -42,12 +42,6 @@ template <int COUT> constexpr size_t s2_smem() {
   return 1024 + (size_t)S2_STAGES * S2_PATCH_PITCH + 9 * COUT * 64 + S2_EPI_WARPS * 32 * COUT * 2 + sizeof(S2Tail);
 }
 
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-
 template <int COUT>
 __global__ void __launch_bounds__(S2_THREADS, 1)
 stem_conv2_kernel(const __grid_constant__ CUtensorMap map_in, const bf16* __restrict__ w_taps, const float* __restrict__ bias,

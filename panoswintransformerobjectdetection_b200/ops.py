@@ -273,8 +273,9 @@ def layernorm_nchw(x, gamma, beta, H, W, eps=1e-5):
 
 
 def stem_conv3x3_relu(img, w_folded, bias_folded):
-    """conv3x3(pad 1) + folded BatchNorm + ReLU: fp32 NCHW image [B, 3, H, W] -> bf16 NHWC [B, H, W, 32]
-    (reference PatchEmbed.proj[0..2], :743-745).  w_folded [32, 27], bias_folded [32] fp32."""
+    """conv3x3(pad 1) + folded BatchNorm + ReLU: fp32 NCHW image [B, 3, H, W] -> bf16 NHWC [B, H, W, cout]
+    (reference PatchEmbed.proj[0..2], :743-745).  w_folded [cout, 27], bias_folded [cout] fp32, cout 32 or 64 (a
+    narrower layer is zero-padded by the caller)."""
     dev = _chk(img, w_folded, bias_folded)
     B, cin, H, W = img.shape
     cout = w_folded.shape[0]
@@ -299,6 +300,22 @@ def stem_conv3x3_c32_relu(x_nhwc, w_taps, bias):
     with torch.cuda.device(dev):
         _call("psw_stem_conv3x3_c32_relu_fwd", _ptr(x_nhwc), _ptr(w_taps), _ptr(_f32(bias, "bias")), _ptr(out), B, H, W,
               cout, _stream(dev))
+    return out
+
+
+def conv3x3_nhwc(x_nhwc, w_ohwi, bias, relu=True):
+    """conv3x3(stride 1, pad 1) + bias (+ ReLU) of an NHWC bf16 image as a GEMM over shifted TMA views (reference
+    PatchEmbed.proj[3..5], :746-748, for stem widths other than embed_dim 96's).  x [B, H, W, cin] -> [B, H, W, cout];
+    w_ohwi [cout, 3, 3, cin] bf16, bias [cout] fp32; cin % 64 == 0 and cout % 16 == 0 (zero-pad the channels)."""
+    dev = _chk(x_nhwc, w_ohwi, bias)
+    B, H, W, cin = x_nhwc.shape
+    cout = w_ohwi.shape[0]
+    if x_nhwc.dtype != torch.bfloat16 or w_ohwi.dtype != torch.bfloat16 or tuple(w_ohwi.shape) != (cout, 3, 3, cin):
+        raise PanoSwinB200Error("conv3x3_nhwc wants bf16 NHWC x and bf16 w [cout, 3, 3, cin]")
+    out = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=x_nhwc.device)
+    with torch.cuda.device(dev):
+        _call("psw_conv3x3_nhwc_fwd", _ptr(x_nhwc), _ptr(w_ohwi), _ptr(_f32(bias, "bias")), _ptr(out), B, H, W, cin, cout,
+              1 if relu else 0, _stream(dev))
     return out
 
 

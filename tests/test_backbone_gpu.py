@@ -250,7 +250,15 @@ def test_panoswin_b_shaped_config_matches_reference():
     m.set_compute_dtype("bf16")
     img4 = torch.cat([img, O.make_image((3, 3, 224, 448), 6)], 0)
     want4, wblocks4 = O.backbone_forward(sd, cfg, img4, return_blocks=True)
-    outs4, blocks4 = _run_with_blocks(m, img4.to(DEV), st)
+    from panoswintransformerobjectdetection_b200 import ops as P
+    seen = []
+    P.set_tracer(lambda fn, args, e0, e1: seen.append(fn))
+    try:
+        outs4, blocks4 = _run_with_blocks(m, img4.to(DEV), st)
+    finally:
+        P.set_tracer(None)
+    # the 42 / 84-channel stem runs on libpanoswin_b200 as well (zero-padded channels), not on a library convolution
+    assert {"psw_stem_conv3x3_relu_fwd", "psw_conv3x3_nhwc_fwd", "psw_patch_conv_fwd"} <= set(seen)
     for n in range(meta["n_blocks"]):
         assert rel_l2(blocks4[n][0], torch.from_numpy(z[f"block{n}"])) <= 1e-2, ("bf16 block vs reference", n)
         for b in range(4):

@@ -289,20 +289,42 @@ def test_errors_are_loud(ops):
         ops.window_attention(qkv.float(), t, t, None, torch.zeros(14, 28, 2, device=DEV), None, 1, 7, 7, True, 1.0)   # shift >= window
 
 
+@pytest.mark.parametrize("cout", [32, 64])
 @pytest.mark.parametrize("shape", [(2, 3, 64, 128), (1, 3, 52, 100), (1, 3, 9, 68), (3, 3, 16, 64), (1, 3, 20, 260)])
-def test_stem_conv3x3_relu(ops, shape):
-    """tcgen05 stem conv (3 -> 32) + folded BN + ReLU against fp32 conv on the bf16-rounded operands."""
+def test_stem_conv3x3_relu(ops, shape, cout):
+    """tcgen05 stem conv (3 -> 32 / 64) + folded BN + ReLU against fp32 conv on the bf16-rounded operands."""
     B, _, H, W = shape
-    g = _g(H + W)
+    g = _g(H + W + cout)
     img = torch.rand(shape, generator=g)
-    w = torch.randn(32, 3, 3, 3, generator=g) / 27 ** 0.5
-    b = torch.randn(32, generator=g) * 0.1
+    w = torch.randn(cout, 3, 3, 3, generator=g) / 27 ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
     wq = w.bfloat16().float()
     want = F.relu(F.conv2d(img.bfloat16().float(), wq, b, padding=1)).permute(0, 2, 3, 1)
-    got = ops.stem_conv3x3_relu(img.to(DEV), w.reshape(32, 27).to(DEV), b.to(DEV))
+    got = ops.stem_conv3x3_relu(img.to(DEV), w.reshape(cout, 27).to(DEV), b.to(DEV))
     torch.cuda.synchronize()
-    assert got.shape == (B, H, W, 32) and got.dtype == torch.bfloat16
+    assert got.shape == (B, H, W, cout) and got.dtype == torch.bfloat16
     assert rel_l2(got.float(), want) <= 4e-3
+
+
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("B,H,W,cin,cout", [(1, 8, 128, 64, 96), (2, 13, 100, 64, 96), (1, 4, 260, 64, 64), (3, 33, 129, 64, 48),
+                                             (2, 64, 256, 64, 96), (1, 5, 40, 128, 128)])
+def test_conv3x3_nhwc_gemm_view(ops, B, H, W, cin, cout, relu):
+    """conv3x3 (stride 1, pad 1) + bias (+ ReLU) of an NHWC bf16 image through the tcgen05 GEMM over shifted 4-D TMA views
+    (PanoSwin-B's second stem layer, channels zero-padded to 64 -> 96) vs torch fp32; ragged heights / widths and the image
+    borders rely on TMA's out-of-range zero fill."""
+    g = _g(B * 1000 + H * 10 + W + cout)
+    x = torch.randn(B, H, W, cin, generator=g).bfloat16()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (9 * cin) ** 0.5).bfloat16()
+    b = torch.randn(cout, generator=g)
+    want = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1).permute(0, 2, 3, 1)
+    if relu:
+        want = F.relu(want)
+    got = ops.conv3x3_nhwc(x.to(DEV), w.permute(0, 2, 3, 1).contiguous().to(DEV), b.to(DEV), relu=relu)
+    torch.cuda.synchronize()
+    assert got.shape == (B, H, W, cout) and got.dtype == torch.bfloat16
+    assert rel_l2(got.float(), want) <= 4e-3
+    assert (got.float().cpu() - want).abs().max() <= 0.06
 
 
 def test_stem_conv_rejects_unsupported_shapes(ops):
@@ -310,7 +332,7 @@ def test_stem_conv_rejects_unsupported_shapes(ops):
     w, b = torch.zeros(32, 27, device=DEV), torch.zeros(32, device=DEV)
     with pytest.raises(PanoSwinB200Error):                      # W must be a multiple of 4
         ops.stem_conv3x3_relu(torch.zeros(1, 3, 8, 70, device=DEV), w, b)
-    with pytest.raises(PanoSwinB200Error):                      # built for 3 -> 32 channels
+    with pytest.raises(PanoSwinB200Error):                      # built for 3 -> 32 or 64 channels
         ops.stem_conv3x3_relu(torch.zeros(1, 3, 8, 64, device=DEV), torch.zeros(48, 27, device=DEV), torch.zeros(48, device=DEV))
 
 
