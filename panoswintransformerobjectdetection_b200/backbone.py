@@ -485,7 +485,8 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
                 .to(torch.bfloat16).contiguous(), ((conv2.bias - bn2.running_mean) * s2 + bn2.bias).float().contiguous())
             self._weight_cache["stem_key"] = key
         (w1, b1), (w2, b2), (w3, b3), (w1f, b1f) = self._weight_cache["stem"]
-        own_conv1 = conv1.in_channels == 3 and conv1.out_channels == 32       # libpanoswin_b200 tcgen05 conv (E = 96)
+        own_conv1 = (conv1.in_channels == 3 and conv1.out_channels == 32      # libpanoswin_b200 tcgen05 conv (E = 96)
+                     and x.shape[3] % 4 == 0)                                 # (its patch loader moves 16-byte groups)
         own_conv2 = own_conv1 and conv2.in_channels == 32 and conv2.out_channels in (32, 64) and conv2.kernel_size == (3, 3)
         if own_conv2:
             w2t, b2f = self._weight_cache["stem2"]

@@ -8,7 +8,8 @@
 // arithmetic as in the forward, psw::source_token); padding cells -- zero tokens whose q / k / v equal the qkv bias
 // (:486-491, :344-347) -- send their gradient to d qkv_bias instead.  The table gradients are reduced per CTA in
 // shared memory and leave with one atomic per table entry; uv and the mask carry no gradient.
-// CUDA-core kernel for fp32 (parity path) and bf16 storage, any window size / head_dim.
+// CUDA-core kernel for fp32 (parity path) and bf16 storage, any window size / head_dim; bf16 with window 7 / head_dim 32
+// takes the tensor-core kernel of psw_attn_bwd_mma.cu.
 #include "psw_common.cuh"
 
 namespace psw {
@@ -190,6 +191,10 @@ static int window_attn_bwd(const T* qkv, const T* dout, const float* alpha, cons
   return launch_status("window_attn_bwd_kernel");
 }
 
+int window_attn_bwd_mma(const bf16* qkv, const bf16* dout, const float* alpha, const float* beta, const float* qkv_bias,
+                        const float* uv, const float* mask, bf16* dqkv, float* dalpha, float* dbeta, float* dqkv_bias, int B,
+                        int H, int W, int C, int heads, int shift, int pano, float scale, cudaStream_t st);
+
 }  // namespace psw
 
 using namespace psw;
@@ -217,6 +222,9 @@ extern "C" PSW_API int psw_window_attn_bwd(const void* qkv, const void* dout, co
     return window_attn_bwd<float>((const float*)qkv, (const float*)dout, alpha, beta, qkv_bias, uv, mask, (float*)dqkv, dalpha,
                                   dbeta, dqkv_bias, B, H, W, C, heads, window, shift, pano_mode, scale, st);
   PSW_REQUIRE(dtype == PSW_BF16, PSW_ERR_BAD_ARG, "psw_window_attn_bwd: unknown dtype %d", dtype);
+  if (window == 7 && C / heads == 32 && aligned16(qkv) && aligned16(dout) && aligned16(dqkv))   // tensor-core kernel (psw_attn_bwd_mma.cu)
+    return window_attn_bwd_mma((const bf16*)qkv, (const bf16*)dout, alpha, beta, qkv_bias, uv, mask, (bf16*)dqkv, dalpha, dbeta,
+                               dqkv_bias, B, H, W, C, heads, shift, pano_mode, scale, st);
   return window_attn_bwd<bf16>((const bf16*)qkv, (const bf16*)dout, alpha, beta, qkv_bias, uv, mask, (bf16*)dqkv, dalpha, dbeta,
                                dqkv_bias, B, H, W, C, heads, window, shift, pano_mode, scale, st);
 }
