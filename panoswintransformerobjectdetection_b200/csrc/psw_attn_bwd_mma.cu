@@ -76,6 +76,7 @@ window_attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
   float* svv = su + N;
   int* ssrc = reinterpret_cast<int*>(svv + N);             // [64] source token or -1
   uint4* spad = reinterpret_cast<uint4*>(ssrc + 64);       // [3][4]: bf16 qkv bias of this head (padding cells)
+  float* sqb = reinterpret_cast<float*>(spad + 12);        // [3][32] d qkv_bias of this head through the padding cells
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int e = blockIdx.x % heads;
@@ -86,7 +87,10 @@ window_attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
 
   // ---------------------------------------------------------------- once per CTA
   for (int i = tid; i < 4 * 64 * BW_RP / 8; i += BW_THREADS) reinterpret_cast<uint4*>(sq)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 2 * BW_TAB; i += BW_THREADS) sta[i] = 0.f;
+  if (tid < 96) sqb[tid] = 0.f;
+  float* sal = reinterpret_cast<float*>(sdS);              // [169] alpha, [169] beta of this head (scratch: dS is not in use yet)
+  float* sbe = sal + BW_TAB;
+  for (int i = tid; i < BW_TAB; i += BW_THREADS) { sal[i] = alpha[i * heads + e]; sbe[i] = beta[i * heads + e]; }
   if (tid < 64) {
     int s = -1;
     float uu = 0.f, vv = 0.f;
@@ -109,21 +113,33 @@ window_attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
     spad[j] = r;
   }
   __syncthreads();
+  // great-circle distances: symmetric, so every pair is evaluated once (fp32 evaluation order of the forward kernels,
+  // great_circle.py:82-86; cos v per token in su's neighbour array)
+  if (g.pano) {
+    float* scos = reinterpret_cast<float*>(sP);            // [49] scratch: the P tile is not in use yet
+    if (tid < N) scos[tid] = cosf(svv[tid]);
+    __syncthreads();
+    for (int p = tid; p < 25 * (N + 1); p += BW_THREADS) {   // upper triangle, rows r and N - 1 - r folded into one of N + 1
+      const int r = p / (N + 1), c = p - r * (N + 1);
+      int i, j;
+      if (c < N - r) { i = r; j = r + c; } else { i = N - 1 - r; j = i + (c - (N - r)); }
+      const float sdv = sinf(0.5f * fabsf(svv[j] - svv[i]));
+      const float sdu = sinf(0.5f * (su[j] - su[i]));
+      const float a = sdv * sdv + (scos[j] * scos[i]) * (sdu * sdu);
+      const float d = asinf(sqrtf(fminf(a, 1.0f))) * 2.0f;
+      shav[i * BW_TP + j] = d;
+      shav[j * BW_TP + i] = d;
+    }
+    __syncthreads();
+  }
   for (int p = tid; p < N * N; p += BW_THREADS) {
     const int i = p / N, j = p - i * N;
     const int ri = i / WS, ci = i - ri * WS, rj = j / WS, cj = j - rj * WS;
     const int idx = (ri - rj + WS - 1) * TW + (ci - cj + WS - 1);
-    float d = 0.f;
-    if (g.pano) {                                          // fp32 evaluation order of the forward kernels (great_circle.py:82-86)
-      const float sdv = sinf(0.5f * fabsf(svv[j] - svv[i]));
-      const float sdu = sinf(0.5f * (su[j] - su[i]));
-      const float a = sdv * sdv + (cosf(svv[j]) * cosf(svv[i])) * (sdu * sdu);
-      d = asinf(sqrtf(fminf(a, 1.0f))) * 2.0f;
-    }
-    float b = fmaf(d, alpha[idx * heads + e], beta[idx * heads + e]);
+    const float d = g.pano ? shav[i * BW_TP + j] : 0.f;
+    float b = fmaf(d, sal[idx], sbe[idx]);
     if (mask) b += mask[((int64_t)wi * N + i) * N + j];
     sbias[i * BW_TP + j] = b * BW_LOG2E;
-    shav[i * BW_TP + j] = d;
   }
   __syncthreads();
 
@@ -137,22 +153,43 @@ window_attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
 #pragma unroll
     for (int c = 0; c < 4; ++c) tab[nt][c] = 0.f;
 
-  for (int b = 0; b < B; ++b) {
-    // ---- q / k / v / dO rows of this window, head and image -> shared memory (16-byte chunks; padding cells: bias / 0)
-    for (int idx = tid; idx < 4 * N * 4; idx += BW_THREADS) {
-      const int part = idx / (N * 4);
-      const int rem = idx - part * (N * 4);
-      const int tok = rem >> 2, ch = rem & 3;
-      const int s = ssrc[tok];
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (s >= 0) {
-        const bf16* src = part < 3 ? qkv + ((int64_t)b * HW + s) * C3 + part * C + e * 32 + ch * 8
-                                   : dout + ((int64_t)b * HW + s) * C + e * 32 + ch * 8;
-        v = __ldg(reinterpret_cast<const uint4*>(src));
-      } else if (part < 3) {
-        v = spad[part * 4 + ch];
+  // images of this CTA: the batch is split over gridDim.y when (windows x heads) alone does not fill the GPU
+  const int b_per = (B + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int b_begin = (int)blockIdx.y * b_per;
+  const int b_end = b_begin + b_per < B ? b_begin + b_per : B;
+  for (int b = b_begin; b < b_end; ++b) {
+    // ---- q / k / v / dO rows of this window, head and image -> shared memory (16-byte chunks; padding cells: bias / 0).
+    //      All of a thread's loads are issued before the first store, so their latencies overlap.
+    {
+      constexpr int ITEMS = (4 * N * 4 + BW_THREADS - 1) / BW_THREADS;     // 7
+      uint4 v[ITEMS];
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int idx = tid + it * BW_THREADS;
+        v[it] = make_uint4(0, 0, 0, 0);
+        if (idx < 4 * N * 4) {
+          const int part = idx / (N * 4);
+          const int rem = idx - part * (N * 4);
+          const int tok = rem >> 2, ch = rem & 3;
+          const int s = ssrc[tok];
+          if (s >= 0) {
+            const bf16* src = part < 3 ? qkv + ((int64_t)b * HW + s) * C3 + part * C + e * 32 + ch * 8
+                                       : dout + ((int64_t)b * HW + s) * C + e * 32 + ch * 8;
+            v[it] = __ldg(reinterpret_cast<const uint4*>(src));
+          } else if (part < 3) {
+            v[it] = spad[part * 4 + ch];
+          }
+        }
       }
-      *reinterpret_cast<uint4*>(sq + (part * 64 + tok) * BW_RP + ch * 8) = v;
+#pragma unroll
+      for (int it = 0; it < ITEMS; ++it) {
+        const int idx = tid + it * BW_THREADS;
+        if (idx < 4 * N * 4) {
+          const int part = idx / (N * 4);
+          const int rem = idx - part * (N * 4);
+          *reinterpret_cast<uint4*>(sq + (part * 64 + (rem >> 2)) * BW_RP + (rem & 3) * 8) = v[it];
+        }
+      }
     }
     __syncthreads();
 
@@ -317,8 +354,8 @@ window_attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w4[k]);
-          atomicAdd(dqkv_bias + part * C + e * 32 + ch * 8 + 2 * k, __low2float(h));
-          atomicAdd(dqkv_bias + part * C + e * 32 + ch * 8 + 2 * k + 1, __high2float(h));
+          atomicAdd(sqb + part * 32 + ch * 8 + 2 * k, __low2float(h));
+          atomicAdd(sqb + part * 32 + ch * 8 + 2 * k + 1, __high2float(h));
         }
       }
     }
@@ -326,25 +363,35 @@ window_attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict_
   }
 
   // ---------------------------------------------------------------- table gradients of this (window, head)
+  // d beta[idx] = sum of dS over the (i, j) pairs at relative position idx, d alpha[idx] the same weighted with the
+  // great-circle distance: the accumulated dS goes to shared memory (the bias table is dead by now) and one thread per
+  // table entry walks over its <= 49 pairs -- no shared-memory atomics.
+  float* sds = sbias;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const int i = (c & 2) ? i1 : i0;
       const int j = 8 * nt + 2 * tq + (c & 1);
-      if (i < N && j < N) {
-        const int ri = i / WS, ci = i - ri * WS, rj = j / WS, cj = j - rj * WS;
-        const int idx = (ri - rj + WS - 1) * TW + (ci - cj + WS - 1);
-        atomicAdd(&stb[idx], tab[nt][c]);
-        if (g.pano) atomicAdd(&sta[idx], shav[i * BW_TP + j] * tab[nt][c]);
-      }
+      if (i < N && j < N) sds[i * BW_TP + j] = tab[nt][c];
     }
   }
   __syncthreads();
   for (int t = tid; t < BW_TAB; t += BW_THREADS) {
-    if (g.pano && dalpha) atomicAdd(dalpha + t * heads + e, sta[t]);
-    if (dbeta) atomicAdd(dbeta + t * heads + e, stb[t]);
+    const int dr = t / TW - (WS - 1), dc = t - (t / TW) * TW - (WS - 1);     // idx = (ri - rj + 6) * 13 + (ci - cj + 6)
+    float sb = 0.f, sa = 0.f;
+    for (int ri = (dr > 0 ? dr : 0); ri < (dr < 0 ? WS + dr : WS); ++ri) {
+      for (int ci = (dc > 0 ? dc : 0); ci < (dc < 0 ? WS + dc : WS); ++ci) {
+        const int i = ri * WS + ci, j = (ri - dr) * WS + (ci - dc);
+        const float d = sds[i * BW_TP + j];
+        sb += d;
+        sa = fmaf(shav[i * BW_TP + j], d, sa);
+      }
+    }
+    if (g.pano && dalpha) atomicAdd(dalpha + t * heads + e, sa);
+    if (dbeta) atomicAdd(dbeta + t * heads + e, sb);
   }
+  if (dqkv_bias && tid < 96 && sqb[tid] != 0.f) atomicAdd(dqkv_bias + (tid >> 5) * C + e * 32 + (tid & 31), sqb[tid]);
 }
 
 // bf16, window 7, head_dim 32; the table / bias gradients must be zero on entry (the caller clears them)
@@ -353,11 +400,16 @@ int window_attn_bwd_mma(const bf16* qkv, const bf16* dout, const float* alpha, c
                         int H, int W, int C, int heads, int shift, int pano, float scale, cudaStream_t st) {
   WinGeom g = make_geom(H, W, 7, shift, pano);
   const size_t smem = (size_t)4 * 64 * BW_RP * 2 + (size_t)2 * 64 * BW_PP * 2 + (size_t)2 * BW_N * BW_TP * 4 + 2 * BW_TAB * 4 +
-                      2 * BW_N * 4 + 64 * 4 + 12 * 16;
+                      2 * BW_N * 4 + 64 * 4 + 12 * 16 + 96 * 4;
   const int64_t blocks = (int64_t)g.nWh * g.nWw * heads;
   PSW_REQUIRE(blocks < (1ll << 31), PSW_ERR_UNSUPPORTED, "psw_window_attn_bwd: too many windows");
+  // a CTA walks over images serially (its per-window setup is amortised); split the batch until ~3 waves of CTAs exist
+  int splits = (int)((3ll * 3 * num_sms() + blocks - 1) / blocks);
+  if (splits > B) splits = B;
+  if (splits < 1) splits = 1;
+  splits = (B + ((B + splits - 1) / splits) - 1) / ((B + splits - 1) / splits);
   PSW_CUDA(cudaFuncSetAttribute(window_attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  window_attn_bwd_mma_kernel<<<(unsigned)blocks, BW_THREADS, smem, st>>>(qkv, dout, alpha, beta, qkv_bias, uv, mask, dqkv, dalpha,
+  window_attn_bwd_mma_kernel<<<dim3((unsigned)blocks, (unsigned)splits), BW_THREADS, smem, st>>>(qkv, dout, alpha, beta, qkv_bias, uv, mask, dqkv, dalpha,
                                                                           dbeta, dqkv_bias, g, B, C, heads, scale);
   return launch_status("window_attn_bwd_mma_kernel");
 }
