@@ -6,7 +6,7 @@
 // activations is ever made.  One CTA owns a 128 (n) x 128 (k) tile of dW for one slice of the rows (the output is tiny
 // and the contraction huge, so the rows are split over the grid) and adds its tile to dW with fp32 reductions.
 //   warp 0: TMA producer (4-stage mbarrier ring, 32 KB per stage)   warp 1: MMA issuer (4 x K=16 per stage), TMEM owner
-//   warps 2-5: epilogue, one per TMEM lane quadrant: tcgen05.ld -> red.global.add.f32
+//   warps 2-5: epilogue, one per TMEM lane quadrant: tcgen05.ld -> red.global.add.v4.f32 (16-byte vector reductions)
 #include "psw_common.cuh"
 
 namespace psw {
@@ -92,11 +92,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         uint32_t v[32];
         tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
         tmem_ld_wait();
-        if (n < N) {
+        if (n < N) {                                         // K % 8 == 0: a group of four columns is inside or outside
           float* row = dw + (size_t)n * K + k0 + cc * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (k0 + cc * 32 + j < K) atomicAdd(row + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; j += 4)
+            if (k0 + cc * 32 + j < K)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + j), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3])) : "memory");
         }
       }
     }
