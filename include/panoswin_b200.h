@@ -293,7 +293,9 @@ PSW_API int psw_transpose(const void* src, void* dst, int64_t rows, int64_t cols
  * written), dalpha / dbeta [(2*window-1)^2, heads] fp32, dqkv_bias [3C] fp32 = the gradient that reaches the qkv bias
  * through the PADDING cells (zero tokens whose q / k / v are the bias, reference :486-491; the bias gradient of the
  * real tokens is psw_linear_bwd's db).  The probabilities are recomputed from qkv; uv / mask carry no gradient.
- * qkv_bias and dqkv_bias are both NULL or both given; dalpha is untouched in planar mode.  Any window / head_dim.
+ * qkv_bias and dqkv_bias are both NULL or both given; dalpha is untouched in planar mode.  Any window / head_dim
+ * (CUDA-core kernel); PSW_BF16 with window 7 and head_dim 32 runs on tensor cores (psw_attn_bwd_mma.cu), where padding
+ * cells take the bf16-rounded bias like psw_window_attn_full_fwd.
  */
 PSW_API int psw_window_attn_bwd(const void* qkv, const void* dout, const float* alpha, const float* beta,
                                 const float* qkv_bias, const float* uv, const float* mask, void* dqkv, float* dalpha,
