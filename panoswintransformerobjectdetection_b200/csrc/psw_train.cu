@@ -41,10 +41,23 @@ template <typename T> __device__ __forceinline__ void load4_or_zero(const T* bas
 
 // One warp per row, four passes over the row (it is re-read from L1 / L2): mean, centred variance, the two
 // reductions of the gradient, dx.  stats[2r] = mean, stats[2r + 1] = rstd feed the parameter-gradient kernel.
-template <typename TX, typename TDY, typename TDX>
+// KP > 0 (C <= 128 KP): the parameter gradients ride along -- every lane keeps the partial sums of its 4 KP columns over
+// the rows of its warp in registers, the eight warps of a CTA meet in shared memory, one atomic per column and CTA:
+// dgamma / dbeta (zero on entry) need no second pass over x and dy.
+template <typename TX, typename TDY, typename TDX, int KP>
 __global__ void __launch_bounds__(256)
 ln_bwd_rows_kernel(const TX* __restrict__ x, const TDY* __restrict__ dy, const float* __restrict__ gamma,
-                   TDX* __restrict__ dx, float* __restrict__ stats, RowMap m, int64_t rows, float eps) {
+                   TDX* __restrict__ dx, float* __restrict__ stats, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   RowMap m, int64_t rows, float eps) {
+  constexpr int KQ = KP > 0 ? KP : 1;
+  __shared__ float s_pg[KP > 0 ? 128 * KP : 1], s_pb[KP > 0 ? 128 * KP : 1];
+  float pg[4 * KQ], pb[4 * KQ];
+#pragma unroll
+  for (int k = 0; k < 4 * KQ; ++k) { pg[k] = 0.f; pb[k] = 0.f; }
+  if (KP > 0) {
+    for (int c = threadIdx.x; c < 128 * KP; c += 256) { s_pg[c] = 0.f; s_pb[c] = 0.f; }
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int C = m.C;
@@ -80,18 +93,52 @@ ln_bwd_rows_kernel(const TX* __restrict__ x, const TDY* __restrict__ dy, const f
     }
     a = warp_sum(a) * inv_c;
     b = warp_sum(b) * inv_c;
-    for (int c = lane * 4; c < C; c += 128) {
-      const int64_t off = row_offset(m, r, c);
-      if (off < 0) continue;                                // zero padding of an odd map: no gradient to store
-      float v[4], g[4], w[4], o[4];
-      load4(x + off, v);
-      load4(dy + r * C + c, g);
-      load4(gamma + c, w);
+    if (KP > 0) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = rstd * (g[k] * w[k] - a - (v[k] - mean) * rstd * b);
-      store4(dx + off, o);
+      for (int q = 0; q < KQ; ++q) {
+        const int c = lane * 4 + 128 * q;
+        if (c < C) {
+          const int64_t off = row_offset(m, r, c);
+          float v[4], g[4], w[4], o[4];
+          load4_or_zero(x, off, v);
+          load4(dy + r * C + c, g);
+          load4(gamma + c, w);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float xh = (v[k] - mean) * rstd;
+            o[k] = rstd * (g[k] * w[k] - a - xh * b);
+            pg[4 * q + k] = fmaf(g[k], xh, pg[4 * q + k]);
+            pb[4 * q + k] += g[k];
+          }
+          if (off >= 0) store4(dx + off, o);                // zero padding of an odd map: no gradient to store
+        }
+      }
+    } else {
+      for (int c = lane * 4; c < C; c += 128) {
+        const int64_t off = row_offset(m, r, c);
+        if (off < 0) continue;                              // zero padding of an odd map: no gradient to store
+        float v[4], g[4], w[4], o[4];
+        load4(x + off, v);
+        load4(dy + r * C + c, g);
+        load4(gamma + c, w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = rstd * (g[k] * w[k] - a - (v[k] - mean) * rstd * b);
+        store4(dx + off, o);
+      }
     }
     if (lane == 0 && stats) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+  }
+  if (KP > 0) {
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) {
+      const int c = lane * 4 + 128 * q;
+      if (c < C) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { atomicAdd(&s_pg[c + k], pg[4 * q + k]); atomicAdd(&s_pb[c + k], pb[4 * q + k]); }
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) { atomicAdd(dgamma + c, s_pg[c]); atomicAdd(dbeta + c, s_pb[c]); }
   }
 }
 
@@ -134,7 +181,25 @@ static int ln_bwd_launch(const void* x, const void* dy, const float* gamma, void
   int64_t blocks = (rows + 7) / 8;
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  ln_bwd_rows_kernel<TX, TDY, TDX><<<(unsigned)blocks, 256, 0, st>>>((const TX*)x, (const TDY*)dy, gamma, (TDX*)dx, stats, m, rows, eps);
+  if (dgamma && m.C <= 1024) {                              // parameter gradients inside the row pass
+    PSW_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * m.C, st));
+    PSW_CUDA(cudaMemsetAsync(dbeta, 0, sizeof(float) * m.C, st));
+    const int64_t cap2 = (int64_t)num_sms() * 4;            // fewer, longer-lived CTAs: one atomic per column and CTA
+    if (blocks > cap2) blocks = cap2;
+    const int kp = (m.C + 127) / 128;
+#define PSW_LN_BWD_KP(KP_) \
+    ln_bwd_rows_kernel<TX, TDY, TDX, KP_><<<(unsigned)blocks, 256, 0, st>>>((const TX*)x, (const TDY*)dy, gamma, (TDX*)dx, stats, \
+                                                                           dgamma, dbeta, m, rows, eps)
+    if (kp <= 1) PSW_LN_BWD_KP(1);
+    else if (kp <= 2) PSW_LN_BWD_KP(2);
+    else if (kp <= 3) PSW_LN_BWD_KP(3);
+    else if (kp <= 6) PSW_LN_BWD_KP(6);
+    else PSW_LN_BWD_KP(8);
+#undef PSW_LN_BWD_KP
+    return launch_status("ln_bwd_rows_kernel");
+  }
+  ln_bwd_rows_kernel<TX, TDY, TDX, 0><<<(unsigned)blocks, 256, 0, st>>>((const TX*)x, (const TDY*)dy, gamma, (TDX*)dx, stats, nullptr,
+                                                                         nullptr, m, rows, eps);
   int rc = launch_status("ln_bwd_rows_kernel");
   if (rc || !dgamma) return rc;
   PSW_CUDA(cudaMemsetAsync(dgamma, 0, sizeof(float) * m.C, st));

@@ -420,3 +420,29 @@ def attn_ctas():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "attnctas":
     attn_ctas()
+
+
+def linear_stage0(iters=20):
+    """block_n sweep of the stage-0 qkv GEMM (M = 32 x 32768, N = 288, K = 96) and the stage-1 qkv / fc1 shapes."""
+    from panoswintransformerobjectdetection_b200 import _lib
+    lib = _lib.load()
+    for (M, N, K, gelu) in [(B * 32768, 288, 96, 0), (B * 8192, 576, 192, 0), (B * 8192, 768, 192, 1)]:
+        nb = max(2, int(400e6 // (M * (K + N) * 2)) + 1)
+        x = [torch.randn(M, K, device=DEV).bfloat16() for _ in range(nb)]
+        y = [torch.empty(M, N, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
+        w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+        b = torch.randn(N, device=DEV)
+        res = []
+        for bn in (0, 64, 96, 128, 160, 192, 224, 256):
+            lib.psw_diag_linear_mode(((1 << 26) | (bn << 16)) if bn else 0)
+            try:
+                us = min(time_op(lambda i: ops.linear(x[i], w, b, gelu=bool(gelu), out=y[i]), nb, iters) for _ in range(2))
+                res.append(f"bn{bn if bn else '-auto'} {us:.1f}")
+            except Exception as e:  # noqa: BLE001
+                res.append(f"bn{bn} failed")
+            lib.psw_diag_linear_mode(0)
+        print(f"linear M{M} N{N} K{K} gelu{gelu} [us]: " + "  ".join(res), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "linstage0":
+    linear_stage0()
