@@ -327,24 +327,34 @@ gemm_strided_kernel(const TA* __restrict__ A, const TB* __restrict__ B, TC* __re
   }
 }
 
-// db[n] = sum_m dy[m, n]
+// db[n] = sum_m dy[m, n] (N % 4 == 0): a 128-column x rows_per_block slab per block, a lane owns four adjacent columns
+// (one 8- or 16-byte load per row), the eight warps take every eighth row; one atomic per column and block
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ dy, float* __restrict__ db, int64_t M, int N) {
-  __shared__ float sb[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
-  const int64_t r0 = (int64_t)blockIdx.y * LNP_ROWS;
-  const int64_t r1 = r0 + LNP_ROWS < M ? r0 + LNP_ROWS : M;
-  float b = 0.f;
-  if (c < N)
-    for (int64_t r = r0 + ty; r < r1; r += 8) b += to_f32(dy[r * N + c]);
-  sb[ty][tx] = b;
-  __syncthreads();
-  if (ty == 0 && c < N) {
+colsum_kernel(const T* __restrict__ dy, float* __restrict__ db, int64_t M, int N, int rows_per_block) {
+  __shared__ float sb[8][132];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < N) {
+#pragma unroll 4
+    for (int64_t r = r0 + w; r < r1; r += 8) {
+      float v[4];
+      load4(dy + r * N + c, v);
 #pragma unroll
-    for (int k = 1; k < 8; ++k) b += sb[k][tx];
-    atomicAdd(db + c, b);
+      for (int k = 0; k < 4; ++k) acc[k] += v[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sb[w][lane * 4 + k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < 128 && blockIdx.x * 128 + threadIdx.x < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sb[k][threadIdx.x];
+    atomicAdd(db + blockIdx.x * 128 + threadIdx.x, t);
   }
 }
 
@@ -393,8 +403,13 @@ static int linear_bwd_simt(const T* x, const T* w, const T* dy, TDX* dx, float* 
   }
   if (db) {
     PSW_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * N, st));
-    dim3 grid((N + 31) / 32, (unsigned)((M + LNP_ROWS - 1) / LNP_ROWS));
-    colsum_kernel<T><<<grid, 256, 0, st>>>(dy, db, M, N);
+    PSW_REQUIRE(N % 4 == 0, PSW_ERR_UNSUPPORTED, "psw_linear_bwd: the bias gradient needs N %% 4 == 0 (N=%d)", N);
+    const int col_groups = (N + 127) / 128;
+    int64_t rpb = M * col_groups / (8ll * num_sms());       // ~8 blocks per SM in flight, 64 .. 2048 rows each
+    rpb = rpb < 64 ? 64 : (rpb > 2048 ? 2048 : rpb);
+    rpb = (rpb + 7) / 8 * 8;
+    dim3 grid(col_groups, (unsigned)((M + rpb - 1) / rpb));
+    colsum_kernel<T><<<grid, 256, 0, st>>>(dy, db, M, N, (int)rpb);
     return launch_status("colsum_kernel");
   }
   return 0;
