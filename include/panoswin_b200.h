@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PSW_ABI_VERSION 5   /* bumped with every change of a prototype below */
+#define PSW_ABI_VERSION 6   /* bumped with every change of a prototype below */
 
 #if defined(__GNUC__)
 #define PSW_API __attribute__((visibility("default")))
@@ -286,6 +286,20 @@ PSW_API int psw_gelu_bwd(const void* h, const void* dy, void* dh, int64_t n, int
 
 /* dst [cols, rows] = src [rows, cols]^T (helper of the bf16 backward path). */
 PSW_API int psw_transpose(const void* src, void* dst, int64_t rows, int64_t cols, int dtype, void* stream);
+
+/*
+ * Train-mode BatchNorm2d + ReLU of the stem on NHWC bf16 activations (PatchEmbed.proj[1:3] / [4:6], reference :743-748
+ * under model.train(): batch statistics), x / y / dy / dx [pixels, C] bf16, C % 8 == 0 and C <= 256.
+ *   psw_bn_stats_fwd        sum[c], sumsq[c] (fp32) over the pixels
+ *   psw_bn_apply_relu_fwd   y = relu(x * scale[c] + shift[c]) with scale = gamma * rstd, shift = beta - mean * scale
+ *   psw_bn_relu_bwd         dx and dgamma / dbeta [C] fp32 from x, the forward output y (its sign is the ReLU mask), dy, the
+ *                           batch mean / rstd and gamma
+ */
+PSW_API int psw_bn_stats_fwd(const void* x, float* sum, float* sumsq, int64_t npix, int C, void* stream);
+PSW_API int psw_bn_apply_relu_fwd(const void* x, void* y, const float* scale, const float* shift, int64_t npix, int C,
+                                  void* stream);
+PSW_API int psw_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* mean, const float* rstd,
+                            const float* gamma, void* dx, float* dgamma, float* dbeta, int64_t npix, int C, void* stream);
 
 /*
  * Gradient of the fused window attention (psw_window_attn_fwd and psw_window_attn_full_fwd: same function of qkv,

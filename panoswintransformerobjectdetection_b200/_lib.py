@@ -12,7 +12,7 @@ PSW_EPI_GELU = 1
 
 _vp, _fp, _i, _i64, _f = C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float
 
-ABI_VERSION = 5            # must equal PSW_ABI_VERSION of include/panoswin_b200.h (bumped with every prototype change)
+ABI_VERSION = 6            # must equal PSW_ABI_VERSION of include/panoswin_b200.h (bumped with every prototype change)
 
 # name -> argtypes, exactly the prototypes of include/panoswin_b200.h
 SIGNATURES = {
@@ -43,6 +43,9 @@ SIGNATURES = {
     "psw_patch_merge_ln_bwd": [_vp, _vp, _fp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _f, _i, _i, _vp],
     "psw_linear_bwd_workspace_bytes": [_i64, _i, _i, _i],
     "psw_linear_bwd": [_vp, _vp, _vp, _vp, _fp, _fp, _i64, _i, _i, _i, _i, _vp, _i64, _vp],
+    "psw_bn_stats_fwd": [_vp, _fp, _fp, _i64, _i, _vp],
+    "psw_bn_apply_relu_fwd": [_vp, _vp, _fp, _fp, _i64, _i, _vp],
+    "psw_bn_relu_bwd": [_vp, _vp, _vp, _fp, _fp, _fp, _vp, _fp, _fp, _i64, _i, _vp],
     "psw_gelu_fwd": [_vp, _vp, _i64, _i, _vp],
     "psw_gelu_bwd": [_vp, _vp, _vp, _i64, _i, _vp],
     "psw_transpose": [_vp, _vp, _i64, _i64, _i, _vp],

@@ -90,6 +90,35 @@ class GeluFn(torch.autograd.Function):
         return ops.gelu_bwd(h, dy.contiguous())
 
 
+class BatchNormReluFn(torch.autograd.Function):
+    """Train-mode BatchNorm2d + ReLU of the stem on a channels-last bf16 NCHW tensor (reference PatchEmbed.proj[1:3] /
+    [4:6], :743-748, with batch statistics).  Updates the module's running statistics like nn.BatchNorm2d (momentum,
+    unbiased variance) when they are given.  x [B, C, H, W] bf16 channels_last -> same."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps):
+        xh = x.permute(0, 2, 3, 1)                           # NHWC view of the channels-last tensor
+        if not xh.is_contiguous():
+            xh = xh.contiguous()
+        y, mean, rstd, var = ops.bn_relu_train(xh, gamma.detach().float().contiguous(), beta.detach().float().contiguous(), eps)
+        if running_mean is not None:
+            n = xh.numel() // xh.shape[-1]
+            with torch.no_grad():
+                running_mean.mul_(1 - momentum).add_(mean.to(running_mean.dtype), alpha=momentum)
+                running_var.mul_(1 - momentum).add_((var * (n / max(n - 1, 1))).to(running_var.dtype), alpha=momentum)
+        ctx.save_for_backward(xh, y, mean, rstd, gamma)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, y, mean, rstd, gamma = ctx.saved_tensors
+        dyh = dy.permute(0, 2, 3, 1)
+        if dyh.dtype != torch.bfloat16 or not dyh.is_contiguous():
+            dyh = dyh.to(torch.bfloat16).contiguous()
+        dx, dg, db = ops.bn_relu_bwd(xh, y, dyh, mean, rstd, gamma.detach().float().contiguous())
+        return dx.permute(0, 3, 1, 2), dg.to(gamma.dtype), db.to(gamma.dtype), None, None, None, None
+
+
 class WindowAttentionFn(torch.autograd.Function):
     """Fused pano / planar (shifted-)window attention core (reference :274-311 minus the two linears, with the shift,
     padding, partition, reverse and crop of :376-409, :473-519 folded in).  Saves qkv only; the backward kernel

@@ -609,8 +609,8 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
     def _forward_train(self, img: torch.Tensor) -> Tuple[torch.Tensor, ...]:
         """forward() in train mode with gradients (reference :940-979 under autograd; callers
         mmdet/apis/train.py:91-99, mmdet/utils/optimizer.py:22-33).  Every op of the block path runs on a
-        libpanoswin_b200 kernel forward AND backward (autograd.py); the stem (convolutions + train-mode BatchNorm with
-        batch statistics) and the 5-input abs_encoder go through torch.  compute dtype fp32: CUDA-core kernels,
+        libpanoswin_b200 kernel forward AND backward (autograd.py); the stem's convolutions and the 5-input abs_encoder go
+        through torch, its train-mode BatchNorm + ReLU (batch statistics) through libpanoswin_b200 in bf16 mode.  compute dtype fp32: CUDA-core kernels,
         gradients within 1e-4 of torch autograd; bf16: bf16 activations, fp32 residual stream and parameters, tcgen05
         forward / input-gradient GEMMs.  DropPath (:533-534) and `use_checkpoint` (:705-706) are honoured."""
         cd = self._compute_dtype
@@ -626,8 +626,21 @@ class SimplePanoSwinTransformer(nn.Module, DoubleModeModule):
         if cd == torch.bfloat16:
             # throughput mode: the stem's convolutions forward and backward in bf16 channels-last (cuDNN under autocast,
             # BatchNorm statistics in fp32) -- what the reference does under apex O1 (mmdet/apis/train.py:82-88)
+            conv1, bn1, _, conv2, bn2, _, conv3 = pe.proj
+            own_bn = all(isinstance(b, nn.BatchNorm2d) and b.training and b.affine and b.track_running_stats
+                         and b.momentum is not None and b.num_features % 8 == 0 and b.num_features <= 256 for b in (bn1, bn2))
             with torch.autocast("cuda", dtype=torch.bfloat16):
-                tok = pe.proj(img.contiguous(memory_format=torch.channels_last)).float()
+                x0 = img.contiguous(memory_format=torch.channels_last)
+                if own_bn:                                        # train-mode BatchNorm + ReLU on libpanoswin_b200 (NHWC bf16)
+                    y = x0
+                    for conv, bn in ((conv1, bn1), (conv2, bn2)):
+                        y = AG.BatchNormReluFn.apply(conv(y), bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                                     bn.momentum, bn.eps)
+                        with torch.no_grad():
+                            bn.num_batches_tracked.add_(1)
+                    tok = conv3(y).float()
+                else:
+                    tok = pe.proj(x0).float()
         else:
             prev = torch.backends.cudnn.allow_tf32
             torch.backends.cudnn.allow_tf32 = False

@@ -433,6 +433,42 @@ def gelu_bwd(h, dy):
     return dh
 
 
+def bn_relu_train(x_nhwc, gamma, beta, eps):
+    """Train-mode BatchNorm2d + ReLU on an NHWC bf16 tensor [..., C] (batch statistics, biased variance; reference
+    PatchEmbed.proj[1:3] / [4:6] under model.train()).  Returns (y, mean, rstd, var_biased): y bf16 like x, the rest fp32 [C]."""
+    dev = _chk(x_nhwc, gamma, beta)
+    C = x_nhwc.shape[-1]
+    npix = x_nhwc.numel() // C
+    if x_nhwc.dtype != torch.bfloat16 or not x_nhwc.is_contiguous():
+        raise PanoSwinB200Error("bn_relu_train wants a contiguous bf16 NHWC tensor")
+    sums = torch.empty(2, C, dtype=torch.float32, device=x_nhwc.device)
+    with torch.cuda.device(dev):
+        _call("psw_bn_stats_fwd", _ptr(x_nhwc), _ptr(sums[0]), _ptr(sums[1]), npix, C, _stream(dev))
+    mean = sums[0] / npix
+    var = (sums[1] / npix - mean * mean).clamp_min_(0.0)
+    rstd = torch.rsqrt(var + eps)
+    scale = (_f32(gamma, "gamma") * rstd).contiguous()
+    shift = (_f32(beta, "beta") - mean * scale).contiguous()
+    y = torch.empty_like(x_nhwc)
+    with torch.cuda.device(dev):
+        _call("psw_bn_apply_relu_fwd", _ptr(x_nhwc), _ptr(y), _ptr(scale), _ptr(shift), npix, C, _stream(dev))
+    return y, mean, rstd, var
+
+
+def bn_relu_bwd(x_nhwc, y, dy, mean, rstd, gamma):
+    """Gradients of bn_relu_train: (dx bf16 like x, dgamma, dbeta fp32 [C])."""
+    dev = _chk(x_nhwc, y, dy, mean, rstd, gamma)
+    C = x_nhwc.shape[-1]
+    npix = x_nhwc.numel() // C
+    dx = torch.empty_like(x_nhwc)
+    dg = torch.empty(C, dtype=torch.float32, device=x_nhwc.device)
+    db = torch.empty(C, dtype=torch.float32, device=x_nhwc.device)
+    with torch.cuda.device(dev):
+        _call("psw_bn_relu_bwd", _ptr(x_nhwc), _ptr(y), _ptr(dy), _ptr(mean), _ptr(rstd), _ptr(_f32(gamma, "gamma")), _ptr(dx),
+              _ptr(dg), _ptr(db), npix, C, _stream(dev))
+    return dx, dg, db
+
+
 def transpose(x):
     """[R, C] -> [C, R] (contiguous)."""
     dev = _chk(x)

@@ -258,3 +258,31 @@ def test_adamw_steps_reduce_the_loss(dtype):
     with torch.no_grad():
         outs = m(img)
     assert all(torch.isfinite(o).all() for o in outs)
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 24, 40), (3, 64, 17, 33), (1, 48, 9, 20), (2, 128, 8, 8)])
+def test_stem_batchnorm_relu_train(AG, B, C, H, W):
+    """Train-mode BatchNorm2d + ReLU of the stem (NHWC bf16 kernels): output, running statistics and the gradients of the
+    input, gamma and beta against torch's fp32 batch_norm + relu under autograd on the same bf16-rounded input."""
+    g = _g(B * 100 + C + H)
+    x = (torch.randn(B, C, H, W, generator=g) * 1.5 + 0.3).bfloat16()
+    gamma = torch.rand(C, generator=g) + 0.5
+    beta = torch.randn(C, generator=g) * 0.2
+    dy = torch.randn(B, C, H, W, generator=g).bfloat16()
+    rm, rv = torch.zeros(C), torch.ones(C)
+    xr = x.double().requires_grad_(True)
+    gr, br = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rmr, rvr = rm.double().clone(), rv.double().clone()
+    want = F.relu(F.batch_norm(xr, rmr, rvr, gr, br, True, 0.1, 1e-5))
+    want.backward(dy.double())
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    gd, bd = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    rmd, rvd = rm.to(DEV), rv.to(DEV)
+    got = AG.BatchNormReluFn.apply(xd, gd, bd, rmd, rvd, 0.1, 1e-5)
+    assert got.shape == (B, C, H, W) and got.dtype == torch.bfloat16
+    assert rel_l2(got.float(), want) <= 4e-3
+    got.backward(dy.to(DEV).contiguous(memory_format=torch.channels_last))
+    assert rel_l2(rmd, rmr) <= 1e-4 and rel_l2(rvd, rvr) <= 1e-4
+    # the ReLU mask comes from the bf16-rounded output: elements within rounding of zero may flip
+    assert rel_l2(xd.grad.float(), xr.grad) <= 1.5e-2
+    assert rel_l2(gd.grad, gr.grad) <= 1e-2 and rel_l2(bd.grad, br.grad) <= 1e-2
