@@ -633,8 +633,8 @@ window_attn_bi_kernel(const AttnParams p) {
     umma_commit(&bars[0]);
   };
 
-  long long t_start = 0;
-  if (kDiag && (p.variant & 32) && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+  long long t_start = 0, c_start = 0, c_loop = 0;
+  if (kDiag && (p.variant & 32) && tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start)); c_start = clock64(); }
   // software pipeline over steps: cur = n (computed now), nxt = n+1, nn = n+2, n3 = n+3
   BiIt cur, nxt, nn, n3;
   cur.wi = l0 / BP; cur.bp = l0 - cur.wi * BP; cur.ic = 0; cur.k = 0;
@@ -655,6 +655,7 @@ window_attn_bi_kernel(const AttnParams p) {
   uint32_t par = 0;
   long long ph[6] = {0, 0, 0, 0, 0, 0};
   const bool prof = kDiag && p.dbg != nullptr && (blockIdx.x == 0 || (p.variant & 32)) && tid == 0;
+  if (prof) c_loop = clock64();
   while (cur.k < nsteps) {
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     if (prof) c0 = clock64();
@@ -747,6 +748,8 @@ window_attn_bi_kernel(const AttnParams p) {
     for (int k = 0; k < 6; ++k) p.dbg[k] = ph[k];
   if (kDiag && (p.variant & 32) && tid == 0 && p.dbg != nullptr) {
     for (int k = 0; k < 6; ++k) p.dbg[8 + 3 * 1024 + 8 * blockIdx.x + k] = ph[k];
+    p.dbg[8 + 3 * 1024 + 8 * blockIdx.x + 6] = clock64() - c_start;
+    p.dbg[8 + 3 * 1024 + 8 * blockIdx.x + 7] = clock64() - c_loop;
     long long t_end;
     uint32_t smid;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));

@@ -409,6 +409,11 @@ def attn_ctas():
         steps = pc[:, 5].clamp(min=1)
         cyc = pc[:, :5].sum(1)
         names = ["wait-S", "softmax", "PV", "S-issue+loads", "store"]
+        # the per-phase sums below cover only ~60% of the loop's cycles (the clock reads are not ordered against the
+        # asynchronous work around them): read them as proportions, the lifetime / loop cycle counts as absolutes
+        print(f"  clock64 / globaltimer over the CTA lifetime: {float((pc[:, 6] / dur).median()) / 1e3:.3f} GHz; loop share of the "
+              f"lifetime cycles {float((pc[:, 7] / pc[:, 6]).median()):.3f}; phase-sum share {float((cyc / pc[:, 6]).median()):.3f}; "
+              f"loop cycles per step {float((pc[:, 7] / steps).median()):.0f}")
         print(f"attn ctas {H}x{W} C{C}: {n} CTAs, start max {float(st.max()):.1f} us, duration min {float(dur.min()):.1f} median "
               f"{float(dur.median()):.1f} max {float(dur.max()):.1f} us, end max {float(en.max()):.1f} us; steps {float(steps.mean()):.1f}; "
               f"loop cycles median {float(cyc.median()):.0f} -> {float((cyc / dur).median()) / 1e3:.2f} GHz apparent; per step: "
