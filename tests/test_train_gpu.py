@@ -286,3 +286,36 @@ def test_stem_batchnorm_relu_train(AG, B, C, H, W):
     # the ReLU mask comes from the bf16-rounded output: elements within rounding of zero may flip
     assert rel_l2(xd.grad.float(), xr.grad) <= 1.5e-2
     assert rel_l2(gd.grad, gr.grad) <= 1e-2 and rel_l2(bd.grad, br.grad) <= 1e-2
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_graphed_train_step_matches_the_eager_step(dtype):
+    """runtime.GraphedTrainStep: three optimizer steps as CUDA-graph replays (forward + backward into one flat gradient
+    buffer, then the capturable AdamW) give the parameters of the same three phases run eagerly, and the loss falls."""
+    from panoswintransformerobjectdetection_b200.runtime import GraphedTrainStep
+    cfg = O.make_config(embed_dim=32, depths=(2, 2, 2), num_heads=(1, 2, 4), out_indices=(0, 1, 2))
+    imgs = [O.make_image((2, 3, 64, 128), 20 + i).to(DEV) for i in range(3)]
+
+    def run(graphs):
+        m = _train_model(cfg, O.make_state_dict(cfg, 6), dtype)
+        ts = GraphedTrainStep(m, lambda outs: sum(o.square().mean() for o in outs), imgs[0],
+                              lambda ps: torch.optim.AdamW(ps, lr=1e-3, weight_decay=0.05, capturable=True), graphs=graphs, warmup=0 if not graphs else 2)
+        return m, ts
+
+    m_e, ts_e = run(False)
+    m_g, ts_g = run(True)
+    # the graphed instance took `warmup` optimizer steps on imgs[0] while warming up: give the eager one the same
+    for _ in range(2):
+        ts_e.step(imgs[0])
+    losses = []
+    for im in imgs:
+        le, lg = ts_e.step(im), ts_g.step(im)
+        losses.append((float(le), float(lg)))
+    # Adam divides by sqrt(v): run-to-run differences in the order of the atomics that sum the bias-table / bias gradients are
+    # amplified to ~1e-4 of a parameter after five steps, so this compares procedures, not roundings
+    tol = 1e-3 if dtype == "fp32" else 3e-2
+    for (n, pe), (_, pg) in zip(m_e.named_parameters(), m_g.named_parameters()):
+        assert torch.isfinite(pg).all(), n
+        assert rel_l2(pg, pe) <= tol, n
+    assert all(abs(a - b) <= tol * max(1.0, abs(a)) for a, b in losses)
+    assert len(ts_g.params) == len(ts_e.params) > 0
