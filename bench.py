@@ -323,7 +323,7 @@ def run_extras(args, dev, world, rank, timed):
             import gc
             gc.collect()
             ts = GraphedTrainStep(m, lambda outs: sum(o.square().mean() for o in outs), img,
-                                  lambda ps: torch.optim.AdamW(ps, lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05, capturable=True))
+                                  lambda ps: torch.optim.AdamW(ps, lr=1e-4, betas=(0.9, 0.999), weight_decay=0.05, capturable=True, fused=True))   # fused: one multi-tensor kernel (-1.3 ms against the foreach form)
             for _ in range(2):
                 ts.step()
             ms_g = timed(ts.step, 5) / 5
