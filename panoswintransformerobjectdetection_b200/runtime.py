@@ -243,7 +243,7 @@ class _null_context:
 class GraphedTrainStep:
     """One data-parallel training step as two CUDA-graph replays around one gradient all-reduce:
 
-        graph A   zero the flat gradient buffer, forward, loss, backward     (every .grad is a view of ONE flat buffer)
+        graph A   forward, loss, backward, one multi-tensor copy of the gradients into ONE flat buffer
         NCCL      all_reduce(flat gradient, AVG) over the data-parallel group (skipped for a single process)
         graph B   optimizer step (capturable AdamW)
 
@@ -288,8 +288,9 @@ class GraphedTrainStep:
         off = 0
         for p in model.parameters():
             p.grad = None
+        self.views = []
         for p in self.params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)    # autograd accumulates in place into the view
+            self.views.append(self.flat_grad[off:off + p.numel()].view_as(p))
             off += p.numel()
         self.optimizer = make_optimizer(self.params)
         self.loss = None
@@ -313,9 +314,16 @@ class GraphedTrainStep:
                 self.optimizer.step()
 
     def _fwd_bwd(self):
-        self.flat_grad.zero_()
+        # .grad unset: autograd hands every parameter its freshly computed gradient (no zero-fill, no read-modify-write
+        # accumulation -- 170 small launches per step otherwise), then ONE multi-tensor copy gathers them in the flat buffer
+        # and .grad is re-pointed at the buffer's views for the all-reduce and the optimizer
+        for p in self.params:
+            p.grad = None
         self.loss = self.loss_fn(self.model(self.static_in))
         self.loss.backward()
+        torch._foreach_copy_(self.views, [p.grad for p in self.params])
+        for p, v in zip(self.params, self.views):
+            p.grad = v
 
     def _allreduce(self):
         if self.world > 1:
