@@ -786,9 +786,14 @@ static size_t attn_tc_smem_bytes() {
 // ---------------------------------------------------------------------------------------------------
 __global__ void bias_full_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ uv,
                                  const float* __restrict__ mask, float* __restrict__ table, WinGeom g, int heads) {
+  // One CTA per (window, head group): the great-circle distances depend on the window only, so they are evaluated once
+  // (symmetric: 1,225 pairs for a 7 x 7 window) and every head of the group re-uses them -- a CTA per (window, head)
+  // spent its time in sinf / asinf, 3x (stage 0) to 24x (stage 3) redundantly.
   const int ws = g.ws, N = ws * ws, tw = 2 * ws - 1;
   __shared__ float su[64], sv[64], scv[64];
-  const int wi = blockIdx.x, e = blockIdx.y;
+  __shared__ float shav[64 * 65];                               // [i][j], pitch 65
+  __shared__ uint16_t sidx[AT_FULL_CHUNKS * 64 * 4];            // table index (ri - rj + ws - 1) * tw + (ci - cj + ws - 1), 0xffff outside
+  const int wi = blockIdx.x;
   const int wr = wi / g.nWw, wc = wi - wr * g.nWw;
   for (int t = threadIdx.x; t < N; t += blockDim.x) {
     const int r = t / ws, c = t - r * ws;
@@ -797,26 +802,43 @@ __global__ void bias_full_kernel(const float* __restrict__ alpha, const float* _
     if (s >= 0 && uv != nullptr) { uu = uv[2 * s]; vv = uv[2 * s + 1]; }
     su[t] = uu; sv[t] = vv; scv[t] = cosf(vv);
   }
-  __syncthreads();
-  float* out = table + ((size_t)wi * heads + e) * (AT_FULL_CHUNKS * 64 * 4);
   for (int q = threadIdx.x; q < AT_FULL_CHUNKS * 64 * 4; q += blockDim.x) {
     const int k = q >> 8, i = (q >> 2) & 63, j = 4 * k + (q & 3);
-    float b = 0.f;
+    uint16_t idx = 0xffffu;
     if (i < N && j < N) {
-      float d = 0.f;
-      if (uv != nullptr) {
-        const float sdv = sinf(0.5f * fabsf(sv[j] - sv[i]));
-        const float sdu = sinf(0.5f * (su[j] - su[i]));
-        const float a = sdv * sdv + (scv[j] * scv[i]) * (sdu * sdu);
-        d = asinf(sqrtf(fminf(a, 1.0f))) * 2.0f;
-      }
       const int ri = i / ws, ci = i - ri * ws, rj = j / ws, cj = j - rj * ws;
-      const int idx = (ri - rj + ws - 1) * tw + (ci - cj + ws - 1);
-      b = fmaf(d, alpha[idx * heads + e], beta[idx * heads + e]);
-      if (mask != nullptr) b += mask[((size_t)wi * N + i) * N + j];
-      b *= LOG2E;
+      idx = (uint16_t)((ri - rj + ws - 1) * tw + (ci - cj + ws - 1));
     }
-    out[q] = b;
+    sidx[q] = idx;
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < N * N; p += blockDim.x) {
+    const int i = p / N, j = p - i * N;
+    if (j < i) continue;                                        // upper triangle; mirrored below
+    float d = 0.f;
+    if (uv != nullptr) {
+      const float sdv = sinf(0.5f * fabsf(sv[j] - sv[i]));
+      const float sdu = sinf(0.5f * (su[j] - su[i]));
+      const float a = sdv * sdv + (scv[j] * scv[i]) * (sdu * sdu);
+      d = asinf(sqrtf(fminf(a, 1.0f))) * 2.0f;
+    }
+    shav[i * 65 + j] = d;
+    shav[j * 65 + i] = d;
+  }
+  __syncthreads();
+  for (int e = blockIdx.y; e < heads; e += gridDim.y) {
+    float* out = table + ((size_t)wi * heads + e) * (AT_FULL_CHUNKS * 64 * 4);
+    for (int q = threadIdx.x; q < AT_FULL_CHUNKS * 64 * 4; q += blockDim.x) {
+      const int idx = sidx[q];
+      float b = 0.f;
+      if (idx != 0xffff) {
+        const int k = q >> 8, i = (q >> 2) & 63, j = 4 * k + (q & 3);
+        b = fmaf(shav[i * 65 + j], alpha[idx * heads + e], beta[idx * heads + e]);
+        if (mask != nullptr) b += mask[((size_t)wi * N + i) * N + j];
+        b *= LOG2E;
+      }
+      out[q] = b;
+    }
   }
 }
 
@@ -825,7 +847,11 @@ int window_bias_full(const float* alpha, const float* beta, const float* uv, con
   PSW_REQUIRE(window * window <= 4 * AT_FULL_CHUNKS && window * window <= 64, PSW_ERR_UNSUPPORTED,
               "psw_window_bias_full: window %d too large", window);
   WinGeom g = make_geom(H, W, window, shift, pano);
-  bias_full_kernel<<<dim3(g.nWh * g.nWw, heads), 256, 0, st>>>(alpha, beta, pano ? uv : nullptr, mask, (float*)table, g, heads);
+  const int windows = g.nWh * g.nWw;
+  int groups = (4 * num_sms() + windows - 1) / windows;         // head groups per window: enough CTAs for ~4 per SM
+  if (groups > heads) groups = heads;
+  if (groups < 1) groups = 1;
+  bias_full_kernel<<<dim3(windows, groups), 256, 0, st>>>(alpha, beta, pano ? uv : nullptr, mask, (float*)table, g, heads);
   return launch_status("bias_full_kernel");
 }
 
